@@ -1,0 +1,458 @@
+"""CPU fp64 oracle for the CFMM optimal-routing hot path  --  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` legs may import this module.  The product package
+(``cfmm_routing_code_b200``) never does; its CUDA path fails loudly instead of
+falling back to anything in here.
+
+PARITY UNPINNED BY THE REFERENCE: the reference (angeris/cfmm-routing-code) has no
+tests and no recorded outputs, and its only numerical engine (cvxpy + ECOS/Clarabel,
+unpinned, ``README.md:6-9``) is not installable in this image.  What pins this oracle
+instead: (1) ``oracle/primal_scipy.py`` solves the reference's *primal* program
+(``arbitrage.py:50-82`` literally: variables Delta_i, Lambda_i >= 0, the three phi
+constraints, the utility) with scipy SLSQP, an independent method; (2) zero duality
+gap between that primal point and this module's dual point; (3) closed-form /
+brute-force cross-checks in ``tests/test_oracle.py``.
+
+What is restated here (reference file:line):
+  * problem data layout: ``local_indices`` / ``reserves`` / ``fees``     arbitrage.py:5-28
+  * net trade  psi = sum_i A_i (Lambda_i - Delta_i)                      arbitrage.py:42-54
+  * post-trade reserves  R + gamma*Delta - Lambda (fee on Delta only)    arbitrage.py:60
+  * phi = weighted geometric mean  (cp.geo_mean(x, p=w))                 arbitrage.py:65
+  * phi = constant product        (cp.geo_mean(x) on 2 tokens)           arbitrage.py:68-70
+  * phi = constant sum, plus new_reserves >= 0                           arbitrage.py:73-74
+  * utilities: arbitrage  max c'psi, psi>=0                              arbitrage.py:57,77
+               liquidation max psi[t], psi_j = -a_j                      liquidation.py:57,77-80
+               swap        max psi[out], psi + t e_in >= 0               two-asset.py:66,86
+
+The reference hands this program to an interior-point solver.  The oracle (and the
+CUDA product) solve the same program by dual decomposition on the token price vector
+nu: g(nu) = sum_j (nu_j - c_j) a_j + sum_i arb_i(A_i' nu), where arb_i is the optimal
+arbitrage value of pool i at local prices, and grad g = a + psi(nu).
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+KIND_GEOMEAN = 0   # weighted geometric mean; constant product is the (1/2, 1/2) 2-token case
+KIND_CONST_SUM = 1
+
+_TINY = 1e-300
+
+
+# --------------------------------------------------------------------------------------
+# problem container (CSR over pools) -- replaces the dense A_i of arbitrage.py:42-48
+# --------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class Pools:
+    n_tokens: int
+    pool_ptr: np.ndarray   # int64 [m+1]
+    tok_idx: np.ndarray    # int32 [nnz]   local_indices, concatenated
+    reserves: np.ndarray   # f64   [nnz]
+    weights: np.ndarray    # f64   [nnz]   normalised per pool (sum 1); unused for const-sum
+    gamma: np.ndarray      # f64   [m]     fees[i] = 1 - fee
+    kind: np.ndarray       # uint8 [m]
+
+    @property
+    def m(self) -> int:
+        return len(self.gamma)
+
+    def arity(self) -> np.ndarray:
+        return np.diff(self.pool_ptr)
+
+    @staticmethod
+    def from_lists(n_tokens, local_indices, reserves, fees, kinds, weights=None) -> "Pools":
+        """Build from the reference's literals (arbitrage.py:5-28).  ``kinds[i]`` is
+        'geomean' | 'product' | 'sum'; ``weights[i]`` the cvxpy ``p=`` vector or None."""
+        ptr = [0]
+        idx, res, wts, kd = [], [], [], []
+        for i, l in enumerate(local_indices):
+            k = len(l)
+            ptr.append(ptr[-1] + k)
+            idx += list(l)
+            res += [float(x) for x in reserves[i]]
+            kk = kinds[i]
+            if kk in ("sum", KIND_CONST_SUM):
+                kd.append(KIND_CONST_SUM)
+                wts += [0.0] * k
+            else:
+                kd.append(KIND_GEOMEAN)
+                w = np.ones(k) if (weights is None or weights[i] is None) else np.asarray(weights[i], float)
+                wts += list(w / w.sum())     # cvxpy geo_mean normalises p to sum 1
+        return Pools(int(n_tokens), np.asarray(ptr, np.int64), np.asarray(idx, np.int32),
+                     np.asarray(res, np.float64), np.asarray(wts, np.float64),
+                     np.asarray(fees, np.float64), np.asarray(kd, np.uint8))
+
+
+@dataclasses.dataclass
+class Utility:
+    """U(psi) = c'psi - I{psi_j + a_j >= 0 (free_nu=False, eq=False), = 0 (eq), free (pinned)}.
+    Dual: g(nu) = sum_j (nu_j - c_j) a_j + sum_i arb_i, over nu_j >= c_j | nu_j free | nu_j = c_j."""
+    c: np.ndarray        # f64 [n]
+    a: np.ndarray        # f64 [n]
+    eq: np.ndarray       # bool [n]   psi_j + a_j == 0   (nu_j free, > 0)
+    pinned: np.ndarray   # bool [n]   psi_j unconstrained (nu_j = c_j)
+
+    @staticmethod
+    def arbitrage(market_value) -> "Utility":           # arbitrage.py:57,77
+        c = np.asarray(market_value, float)
+        n = len(c)
+        return Utility(c, np.zeros(n), np.zeros(n, bool), np.zeros(n, bool))
+
+    @staticmethod
+    def liquidate(n, target, basket) -> "Utility":      # liquidation.py:57,77-80
+        c = np.zeros(n); c[target] = 1.0
+        a = np.asarray(basket, float).copy(); a[target] = 0.0
+        eq = np.ones(n, bool); eq[target] = False
+        pinned = np.zeros(n, bool); pinned[target] = True
+        return Utility(c, a, eq, pinned)
+
+    @staticmethod
+    def swap(n, tok_in, tok_out, t) -> "Utility":       # two-asset.py:41-45,66,86
+        c = np.zeros(n); c[tok_out] = 1.0
+        a = np.zeros(n); a[tok_in] = float(t)
+        return Utility(c, a, np.zeros(n, bool), np.zeros(n, bool))
+
+
+# --------------------------------------------------------------------------------------
+# per-pool optimal arbitrage, scalar restatements (small cases; the definitional form)
+# --------------------------------------------------------------------------------------
+def arb_geomean_scalar(R, w, gamma, nu):
+    """max nu'(L-D) s.t. prod (R+gamma D-L)^w >= prod R^w, D,L>=0   (arbitrage.py:60,65).
+    KKT: x_j = clip(R_j, gamma*M*w_j/nu_j, M*w_j/nu_j); in logs h(s)=0 with s = log M,
+    h(s) = sum_j w_j [max(s-tA_j,0) + min(s-tB_j,0)],  tB_j = log(R_j nu_j / w_j),
+    tA_j = tB_j - log gamma.  Exact root by walking the sorted breakpoints."""
+    R = np.asarray(R, float); w = np.asarray(w, float); nu = np.asarray(nu, float)
+    w = w / w.sum()
+    tB = np.log(R * nu / w)
+    tA = tB - np.log(gamma)
+    k = len(R)
+    zero = np.zeros(k)
+    if tB.max() <= tA.min():            # no-trade cone
+        return zero, zero.copy(), -np.inf
+    h = lambda s: float(np.sum(w * (np.maximum(s - tA, 0) + np.minimum(s - tB, 0))))
+    bps = np.sort(np.concatenate([tA, tB]))
+    s = None
+    for p in range(len(bps) - 1):
+        hl, hr = h(bps[p]), h(bps[p + 1])
+        if hl <= 0.0 <= hr:
+            s = bps[p] if hr == hl else bps[p] - hl * (bps[p + 1] - bps[p]) / (hr - hl)
+            break
+    assert s is not None
+    D = R * np.expm1(np.maximum(s - tA, 0)) / gamma
+    L = -R * np.expm1(np.minimum(s - tB, 0))
+    return D, L, s
+
+
+def arb_product_scalar(R, gamma, nu):
+    """Closed form for sqrt(x1 x2) >= sqrt(R1 R2)  (arbitrage.py:68-70)."""
+    D = np.zeros(2); L = np.zeros(2)
+    p0, p1 = nu[0] * R[0], nu[1] * R[1]
+    if gamma * p1 > p0:       # tender token 0, receive token 1
+        t = np.sqrt(gamma * p1 / p0)
+        D[0] = R[0] * (t - 1) / gamma; L[1] = R[1] * (1 - 1 / t)
+    elif gamma * p0 > p1:
+        t = np.sqrt(gamma * p0 / p1)
+        D[1] = R[1] * (t - 1) / gamma; L[0] = R[0] * (1 - 1 / t)
+    return D, L
+
+
+def _order(z, R, theta_bar, eps):
+    """One constant-sum limit order (tender a, receive up to R of b), proximal-multiplier form.
+    psi(z) = max_{0<=th<=R} th*z - (th-theta_bar)^2/(2 sigma), sigma = R/eps, z = gamma nu_b/nu_a - 1.
+    Returns psi, th = psi'(z), psi''(z).  eps=0: the exact bang-bang LP (th = R if z>0 else 0)."""
+    z = np.asarray(z, float)
+    if eps <= 0:
+        th = np.where(z > 0, R, 0.0)
+        return th * z, th, np.zeros_like(z)
+    sigma = R / eps
+    th = np.clip(theta_bar + sigma * z, 0.0, R)
+    psi = th * z - (th - theta_bar) ** 2 / (2.0 * sigma)
+    curv = np.where((th > 0) & (th < R), sigma, 0.0)
+    return psi, th, curv
+
+
+def arb_sum_scalar(R, gamma, nu, eps=0.0, theta_bar=(0.0, 0.0)):
+    """2-token constant-sum pool with x >= 0 (arbitrage.py:73-74): an LP, bang-bang in nu.
+    Each direction is a limit order: tender a, receive up to R_b of b, gamma per unit.
+    eps>0 is the proximal-multiplier smoothing (see _order); theta_bar[b] is the multiplier
+    (= current fill estimate) of the order that pays out token b.  The smoothed arb value
+    (nu_a/gamma) psi(r-1) is the perspective of a convex function: convex, degree 1, and its
+    gradient (L - D) always satisfies the pool's own constraints (it only over-pays)."""
+    D = np.zeros(2); L = np.zeros(2)
+    for a, b in ((0, 1), (1, 0)):
+        r = gamma * nu[b] / nu[a]
+        psi, th, _ = _order(r - 1.0, float(R[b]), float(theta_bar[b]), eps)
+        L[b] += float(th)
+        D[a] += float((r * th - psi) / gamma)
+    return D, L
+
+
+# --------------------------------------------------------------------------------------
+# bucketed, vectorised evaluation (same math; used for 1e4..1e6 pools and as cpu baseline)
+# --------------------------------------------------------------------------------------
+class Buckets:
+    """Pools regrouped by (kind, arity) so each group is a dense (m_g, k) array."""
+
+    def __init__(self, pools: Pools):
+        self.pools = pools
+        ar = pools.arity()
+        self.groups = []
+        keys = sorted(set(zip(pools.kind.tolist(), ar.tolist())))
+        for kd, k in keys:
+            sel = np.nonzero((pools.kind == kd) & (ar == k))[0]
+            off = pools.pool_ptr[sel][:, None] + np.arange(k)[None, :]
+            g = dict(kind=kd, k=k, sel=sel, off=off,
+                     idx=pools.tok_idx[off].astype(np.int64), R=pools.reserves[off],
+                     w=pools.weights[off], gamma=pools.gamma[sel])
+            if kd == KIND_GEOMEAN:
+                g["c"] = np.log(g["R"] / g["w"])
+                g["lg"] = np.log(g["gamma"])
+                g["is_cp"] = bool(k == 2 and np.all(g["w"] == 0.5))
+            self.groups.append(g)
+
+
+def _geomean_group(g, nu, lognu):
+    idx, R, w, gam = g["idx"], g["R"], g["w"], g["gamma"]
+    if g.get("is_cp"):
+        n0, n1 = nu[idx[:, 0]], nu[idx[:, 1]]
+        p0, p1 = n0 * R[:, 0], n1 * R[:, 1]
+        f = gam * p1 > p0                      # 0 -> 1
+        b = gam * p0 > p1                      # 1 -> 0
+        q = np.where(f, gam * p1 / p0, np.where(b, gam * p0 / p1, 1.0))
+        t = np.sqrt(q)
+        D = np.zeros_like(R); L = np.zeros_like(R)
+        D[:, 0] = np.where(f, R[:, 0] * (t - 1) / gam, 0.0)
+        L[:, 1] = np.where(f, R[:, 1] * (1 - 1 / t), 0.0)
+        D[:, 1] = np.where(b, R[:, 1] * (t - 1) / gam, 0.0)
+        L[:, 0] = np.where(b, R[:, 0] * (1 - 1 / t), 0.0)
+        # Hessian coefficient M = 2 sqrt(k nu0 nu1 / gamma) on trading pools
+        M = np.where(f | b, 2.0 * np.sqrt(p0 * p1 / gam), 0.0)
+        act = np.stack([f | b, f | b], 1)
+        return D, L, M, act
+    tB = g["c"] + lognu[idx]
+    tA = tB - g["lg"][:, None]
+    trade = tB.max(1) > tA.min(1)
+    T = np.concatenate([tA, tB], 1)                                   # (m, 2k)
+    hT = (w[:, None, :] * (np.maximum(T[:, :, None] - tA[:, None, :], 0)
+                           + np.minimum(T[:, :, None] - tB[:, None, :], 0))).sum(2)
+    Tm = np.where(hT <= 0, T, -np.inf)
+    p = Tm.argmax(1)
+    rows = np.arange(len(p))
+    sL, hL = T[rows, p], hT[rows, p]
+    W = (w * ((sL[:, None] >= tA) | (sL[:, None] < tB))).sum(1)
+    s = np.where(hL < 0, sL - hL / np.maximum(W, _TINY), sL)
+    zA = np.where(trade[:, None], np.maximum(s[:, None] - tA, 0), 0.0)
+    zB = np.where(trade[:, None], np.minimum(s[:, None] - tB, 0), 0.0)
+    D = R * np.expm1(zA) / gam[:, None]
+    L = -R * np.expm1(zB)
+    act = (zA > 0) | (zB < 0)
+    M = np.where(trade, np.exp(s), 0.0)
+    return D, L, M, act
+
+
+def _sum_group(g, nu, eps):
+    assert g["k"] == 2, "constant-sum pools are 2-token (arbitrage.py:11,19)"
+    idx, R, gam = g["idx"], g["R"], g["gamma"]
+    tb = g.setdefault("theta_bar", np.zeros_like(R))
+    D = np.zeros_like(R); L = np.zeros_like(R)
+    hcoef = np.zeros(len(gam))
+    for a, b in ((0, 1), (1, 0)):
+        na, nb = nu[idx[:, a]], nu[idx[:, b]]
+        r = gam * nb / na
+        psi, th, curv = _order(r - 1.0, R[:, b], tb[:, b], eps)
+        L[:, b] = th
+        D[:, a] = (r * th - psi) / gam
+        hcoef += curv * nb * r
+    return D, L, hcoef
+
+
+def evaluate(bk: Buckets, nu, eps=0.0, want_trades=False, want_hess=False):
+    """One dual evaluation: psi(nu) = sum_i A_i(L_i - D_i), arb(nu) = sum_i nu_i'(L_i - D_i).
+    Returns dict(psi, arb[, delta, lam (CSR order)][, hess dense n x n])."""
+    pools = bk.pools
+    n = pools.n_tokens
+    nu = np.asarray(nu, float)
+    lognu = np.log(nu)
+    psi = np.zeros(n)
+    arb = 0.0
+    out = {}
+    if want_trades:
+        delta = np.zeros_like(pools.reserves); lam = np.zeros_like(pools.reserves)
+    if want_hess:
+        Hs = np.zeros((n, n))   # scaled: true Hessian = diag(1/nu) Hs diag(1/nu)
+    for g in bk.groups:
+        if g["kind"] == KIND_GEOMEAN:
+            D, L, M, act = _geomean_group(g, nu, lognu)
+        else:
+            D, L, hc = _sum_group(g, nu, eps)
+        y = L - D
+        np.add.at(psi, g["idx"].ravel(), y.ravel())
+        arb += float(np.sum(nu[g["idx"]] * y))
+        if want_trades:
+            delta[g["off"].ravel()] = D.ravel(); lam[g["off"].ravel()] = L.ravel()
+        if want_hess:
+            idx = g["idx"]
+            if g["kind"] == KIND_GEOMEAN:
+                wa = g["w"] * act
+                Wa = np.maximum(wa.sum(1), _TINY)
+                np.add.at(Hs, (idx.ravel(), idx.ravel()), (M[:, None] * wa).ravel())
+                blk = -(M / Wa)[:, None, None] * wa[:, :, None] * wa[:, None, :]
+                ii = np.repeat(idx[:, :, None], g["k"], 2); jj = np.repeat(idx[:, None, :], g["k"], 1)
+                np.add.at(Hs, (ii.ravel(), jj.ravel()), blk.ravel())
+            else:
+                i0, i1 = idx[:, 0], idx[:, 1]
+                np.add.at(Hs, (i0, i0), hc); np.add.at(Hs, (i1, i1), hc)
+                np.add.at(Hs, (i0, i1), -hc); np.add.at(Hs, (i1, i0), -hc)
+    out["psi"] = psi; out["arb"] = arb
+    if want_trades:
+        out["delta"] = delta; out["lam"] = lam
+    if want_hess:
+        out["hess_scaled"] = Hs
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# outer solver: projected Newton on the (smoothed) dual, dense linear algebra (small n)
+# --------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class Result:
+    value: float                 # = prob.value   (arbitrage.py:84)
+    psi: np.ndarray              # = psi.value    (liquidation.py:87)
+    deltas: List[np.ndarray]     # = deltas[i].value   (two-asset.py:97)
+    lambdas: List[np.ndarray]    # = lambdas[i].value
+    nu: np.ndarray
+    dual_value: float
+    gap: float                   # (dual - primal)/max(|dual|, tiny)
+    primal_infeas: float         # relative to gross token flow
+    iters: int
+    evals: int
+    status: str
+
+
+def _bounds(util: Utility, nu_floor):
+    lb = np.where(util.eq, nu_floor, np.maximum(util.c, nu_floor))
+    return lb
+
+
+def dual_value(util: Utility, nu, arb):
+    return float(np.dot(nu - util.c, util.a) + arb)
+
+
+def residuals(util: Utility, nu, psi, flow_scale):
+    """primal objective, complementarity gap, infeasibility (all from one evaluation)."""
+    s = psi + util.a                      # must be >=0 (ineq) / ==0 (eq) / free (pinned)
+    viol = np.where(util.pinned, 0.0, np.where(util.eq, np.abs(s), np.maximum(-s, 0.0)))
+    infeas = float(np.max(viol / flow_scale)) if len(viol) else 0.0
+    primal = float(np.dot(util.c, psi))
+    return primal, infeas
+
+
+def solve(pools: Pools, util: Utility, nu0=None, tol=1e-9, eps=1e-3, max_outer=40, max_inner=100,
+          verbose=False) -> Result:
+    """Method of multipliers on the constant-sum fills (outer) around a projected (active-set)
+    Newton method on the smooth dual g_t(nu) (inner).  Dense n x n Hessian -- fine for the
+    oracle's sizes (n <= ~1000).  With no constant-sum pool there is one outer pass."""
+    bk = Buckets(pools)
+    n = pools.n_tokens
+    sum_groups = [g for g in bk.groups if g["kind"] == KIND_CONST_SUM]
+    for g in sum_groups:
+        g["theta_bar"] = np.zeros_like(g["R"])
+    scale = np.maximum(np.abs(util.c).max(), 1.0)
+    nu_floor = 1e-12 * scale
+    lb = _bounds(util, nu_floor)
+    fixed = util.pinned.copy()
+    if nu0 is None:
+        nu = np.where(util.c > 0, util.c, scale)
+        nu = np.maximum(nu, lb)
+    else:
+        nu = np.maximum(np.asarray(nu0, float), lb)
+    nu[fixed] = util.c[fixed]
+    evals = 0; iters = 0
+    status = "max_iter"
+    eps_t = eps if sum_groups else 0.0
+
+    def G(nu_, **kw):
+        nonlocal evals
+        evals += 1
+        ev = evaluate(bk, nu_, eps_t, **kw)
+        ev["g"] = dual_value(util, nu_, ev["arb"])
+        ev["grad"] = util.a + ev["psi"]
+        return ev
+
+    for outer in range(max_outer):
+        ev = G(nu, want_hess=True)
+        inner_status = "max_iter"
+        for _ in range(max_inner):
+            iters += 1
+            grad = ev["grad"]
+            at_lb = (nu <= lb * (1 + 1e-14)) & ~util.eq
+            active = fixed | (at_lb & (grad > 0))
+            free = ~active
+            pg = np.where(free, nu * grad, 0.0)      # value units
+            denom = max(abs(ev["g"]), 1e-3 * np.dot(nu, np.abs(grad)), 1e-300)
+            err = np.abs(pg).sum() / denom
+            if verbose:
+                print(f"outer={outer} it={iters} g={ev['g']:.15g} err={err:.3e} free={free.sum()}")
+            if err <= tol:
+                inner_status = "optimal"
+                break
+            Hs = ev["hess_scaled"][np.ix_(free, free)]
+            rhs = -(nu * grad)[free]
+            reg = 1e-14 * max(np.trace(Hs) / max(free.sum(), 1), 1e-300)
+            try:
+                dt = np.linalg.solve(Hs + reg * np.eye(len(rhs)), rhs)
+            except np.linalg.LinAlgError:
+                dt = np.linalg.lstsq(Hs, rhs, rcond=None)[0]
+            d = np.zeros(n); d[free] = nu[free] * dt
+            if not np.all(np.isfinite(d)) or np.dot(d, grad) >= 0:
+                d = np.where(free, -nu * nu * grad / max(np.abs(nu * grad).max(), 1e-300), 0.0)
+            alpha = 1.0
+            g0 = ev["g"]
+            ok = False
+            for _ls in range(60):
+                nu_t = np.maximum(nu + alpha * d, lb)
+                nu_t = np.clip(nu_t, nu * 1e-3, nu * 1e3)     # prices stay positive
+                nu_t[fixed] = util.c[fixed]
+                ev_t = G(nu_t, want_hess=True)
+                if ev_t["g"] <= g0 + 1e-4 * np.dot(grad, nu_t - nu) or \
+                        abs(ev_t["g"] - g0) <= 1e-15 * abs(g0):
+                    ok = True
+                    break
+                alpha *= 0.5
+            if not ok:
+                inner_status = "line_search_failed"
+                break
+            nu, ev = nu_t, ev_t
+        status = inner_status
+        if not sum_groups:
+            break
+        # multiplier update: theta_bar <- theta*(nu); stop when the fills are stationary
+        fin = evaluate(bk, nu, eps_t, want_trades=True)
+        evals += 1
+        move = 0.0
+        for g in sum_groups:
+            th = fin["lam"][g["off"]]                     # Lambda_b IS the fill of the order paying b
+            move = max(move, float(np.max(np.abs(th - g["theta_bar"]) / g["R"])))
+            g["theta_bar"] = th.copy()
+        if verbose:
+            print(f"outer={outer} multiplier move={move:.3e}")
+        if move <= tol and inner_status == "optimal":
+            break
+    fin = evaluate(bk, nu, eps_t, want_trades=True)
+    exact = evaluate(bk, nu, 0.0)
+    evals += 2
+    gross = np.zeros(n)
+    np.add.at(gross, pools.tok_idx, fin["delta"] + fin["lam"])
+    flow_scale = np.maximum(gross, np.abs(util.a)) + 1e-300
+    flow_scale = np.maximum(flow_scale, 1e-9 * flow_scale.max())
+    primal, infeas = residuals(util, nu, fin["psi"], flow_scale)
+    dval = dual_value(util, nu, exact["arb"])
+    gap = (dval - primal) / max(abs(dval), 1e-300)
+    ptr = pools.pool_ptr
+    deltas = [fin["delta"][ptr[i]:ptr[i + 1]].copy() for i in range(pools.m)]
+    lambdas = [fin["lam"][ptr[i]:ptr[i + 1]].copy() for i in range(pools.m)]
+    return Result(primal, fin["psi"], deltas, lambdas, nu, dval, gap, infeas, iters, evals, status)
