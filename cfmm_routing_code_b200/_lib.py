@@ -1,0 +1,90 @@
+"""ctypes binding of libcfmm_b200.so (the C ABI in include/cfmm_b200.h).
+
+There is no CPU fallback: if the library cannot be built or loaded, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+KIND_PRODUCT, KIND_SUM, KIND_GEOMEAN = 0, 1, 2
+
+_ERRORS = {
+    -1: "CFMM_E_NULL (required pointer is NULL)",
+    -2: "CFMM_E_KIND (unknown kind / unsupported arity)",
+    -3: "CFMM_E_SIZE (bad size)",
+    -4: "CFMM_E_CUDA (CUDA runtime error)",
+    -5: "CFMM_E_NODEVICE (no sm_100 device)",
+    -6: "CFMM_E_STATE (handle used in the wrong state)",
+}
+
+
+class CfmmError(RuntimeError):
+    pass
+
+
+class Bucket(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("arity", C.c_int32), ("n_pools", C.c_int64),
+        ("reserves", C.c_void_p), ("tok_idx", C.c_void_p), ("gamma", C.c_void_p),
+        ("weights", C.c_void_p), ("logrw", C.c_void_p), ("theta_bar", C.c_void_p),
+    ]
+
+
+class EvalOut(C.Structure):
+    _fields_ = [("delta", C.c_void_p), ("lambda_", C.c_void_p), ("hcoef", C.c_void_p), ("hmask", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load(build_if_missing: bool = True):
+    """Load (building first if the .so is absent or stale and nvcc is present)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if build_if_missing and _build.needs_build():
+        try:
+            _build.build_library()
+        except Exception as e:  # stale .so + no nvcc (GPU box): use what travelled
+            if not os.path.exists(path):
+                raise CfmmError(f"libcfmm_b200.so is missing and could not be built: {e}") from e
+    if not os.path.exists(path):
+        raise CfmmError("libcfmm_b200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(path)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    lib.cfmm_arb_eval.argtypes = [C.POINTER(Bucket), i32, vp, vp, dbl, vp, vp, C.POINTER(EvalOut), vp]
+    lib.cfmm_arb_eval.restype = C.c_int
+    for name in ("cfmm_hvp", "cfmm_hess_diag", "cfmm_hess_dense"):
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+    lib.cfmm_hvp.argtypes = [C.POINTER(Bucket), i32, vp, vp, vp, vp, vp]
+    lib.cfmm_hess_diag.argtypes = [C.POINTER(Bucket), i32, vp, vp, vp, vp]
+    lib.cfmm_hess_dense.argtypes = [C.POINTER(Bucket), i32, vp, vp, vp, vp]
+    lib.cfmm_sum_update_multipliers.argtypes = [C.POINTER(Bucket), vp, vp, vp, vp]
+    lib.cfmm_sum_update_multipliers.restype = C.c_int
+    lib.cfmm_zero.argtypes = [vp, i64, vp]
+    lib.cfmm_zero.restype = C.c_int
+    lib.cfmm_set_scatter_mode.argtypes = [i32]
+    lib.cfmm_set_scatter_mode.restype = C.c_int
+    lib.cfmm_launch_count.restype = i64
+    lib.cfmm_reset_launch_count.restype = None
+    lib.cfmm_last_cuda_error.restype = C.c_char_p
+    lib.cfmm_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "cfmm call"):
+    if rc != 0:
+        extra = ""
+        if rc == -4 and _lib is not None:
+            extra = ": " + _lib.cfmm_last_cuda_error().decode()
+        raise CfmmError(f"{what} failed: {_ERRORS.get(rc, rc)}{extra}")

@@ -1,0 +1,123 @@
+"""Drop-in boundary for the reference's cvxpy call site.
+
+The reference has no library API: a script builds literals (arbitrage.py:5-36), wires cvxpy objects
+(arbitrage.py:50-78) and calls ``prob.solve()`` (arbitrage.py:82), then reads ``prob.value`` /
+``psi.value`` / ``deltas[i].value`` / ``lambdas[i].value`` (arbitrage.py:84, liquidation.py:87,
+two-asset.py:94-100).  ``solve()`` takes the same literals and returns those same quantities.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .pools import HostPools, PoolStore
+from .solver import Comm, DualSpec, SolveInfo, solve_dual
+
+
+# ----------------------------------------------------------------------------------------------
+# utilities  U(psi)
+# ----------------------------------------------------------------------------------------------
+class Arbitrage:
+    """maximise market_value @ psi  s.t. psi >= 0          (arbitrage.py:57, :77)"""
+
+    def __init__(self, market_value):
+        self.c = np.asarray(market_value, float)
+        if np.any(self.c <= 0):
+            raise ValueError("market_value must be positive")
+
+    def spec(self, n):
+        if len(self.c) != n:
+            raise ValueError("market_value needs one entry per token")
+        return DualSpec(self.c, np.zeros(n), np.zeros(n, bool), np.zeros(n, bool))
+
+
+class Liquidate:
+    """maximise psi[target]  s.t. psi[j] + current_assets[j] == 0 for j != target   (liquidation.py:57, :77-80)"""
+
+    def __init__(self, target, current_assets):
+        self.target = int(target)
+        self.assets = np.asarray(current_assets, float)
+
+    def spec(self, n):
+        if len(self.assets) != n:
+            raise ValueError("current_assets needs one entry per token")
+        c = np.zeros(n); c[self.target] = 1.0
+        a = self.assets.copy(); a[self.target] = 0.0
+        eq = np.ones(n, bool); eq[self.target] = False
+        pinned = np.zeros(n, bool); pinned[self.target] = True
+        return DualSpec(c, a, eq, pinned)
+
+
+class Swap:
+    """maximise psi[tok_out]  s.t. psi + t e_in >= 0        (two-asset.py:41-45, :66, :86)"""
+
+    def __init__(self, tok_in, tok_out, t):
+        self.tok_in, self.tok_out, self.t = int(tok_in), int(tok_out), float(t)
+
+    def spec(self, n):
+        c = np.zeros(n); c[self.tok_out] = 1.0
+        a = np.zeros(n); a[self.tok_in] = self.t
+        return DualSpec(c, a, np.zeros(n, bool), np.zeros(n, bool))
+
+
+# ----------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class Result:
+    value: float                  # prob.value                      arbitrage.py:84
+    psi: np.ndarray               # psi.value                       liquidation.py:87
+    deltas: List[np.ndarray]      # deltas[i].value                 two-asset.py:97
+    lambdas: List[np.ndarray]     # lambdas[i].value                two-asset.py:97
+    nu: np.ndarray                # optimal dual prices (new)
+    dual_value: float
+    gap: float
+    primal_infeas: float
+    iters: int
+    evals: int
+    hvps: int
+    status: str                   # 'optimal' | 'max_iter' | 'line_search_failed'   (cf. prob.status)
+    wall_s: float
+    info: Optional[SolveInfo] = None
+
+
+def solve(local_indices, reserves, fees, kinds, weights=None, utility=None, n_tokens: Optional[int] = None,
+          nu0=None, tol: float = 1e-8, max_iter: int = 100, device="cuda", verbose: bool = False,
+          **solver_kw) -> Result:
+    """Solve the routing problem the reference scripts pose.  `kinds[i]` in {'geomean','product','sum'}
+    names the cvxpy atom on pool i (arbitrage.py:63-74); `weights[i]` is the geo_mean ``p=`` vector."""
+    if utility is None:
+        raise ValueError("utility is required: Arbitrage(c) | Liquidate(target, assets) | Swap(i, o, t)")
+    if n_tokens is None:
+        n_tokens = 1 + max(int(t) for l in local_indices for t in l)
+    hp = HostPools.from_lists(n_tokens, local_indices, reserves, fees, kinds, weights)
+    return solve_pools(hp, utility, nu0=nu0, tol=tol, max_iter=max_iter, device=device, verbose=verbose,
+                       **solver_kw)
+
+
+def solve_pools(hp: HostPools, utility, nu0=None, tol: float = 1e-8, max_iter: int = 100, device="cuda",
+                verbose: bool = False, store: Optional[PoolStore] = None, want_trades: bool = True,
+                **solver_kw) -> Result:
+    """Same as solve() on CSR host arrays.  Under torch.distributed (world_size > 1) every rank passes the
+    full problem and keeps its contiguous shard; psi/value are global, deltas/lambdas are this rank's."""
+    comm = Comm()
+    if store is None:
+        rank = comm.dist.get_rank() if comm.dist is not None else 0
+        world = comm.dist.get_world_size() if comm.dist is not None else 1
+        store = PoolStore(hp, device=device, rank=rank, world=world)
+    spec = utility.spec(hp.n_tokens)
+    info = solve_dual(store, spec, nu0=nu0, tol=tol, max_inner=max_iter, comm=comm, verbose=verbose,
+                      final_trades=want_trades, **solver_kw)
+    deltas: List[np.ndarray] = []
+    lambdas: List[np.ndarray] = []
+    if want_trades:
+        d, l = store.gather_trades()
+        ptr = hp.pool_ptr
+        deltas = [d[ptr[i]:ptr[i + 1]] for i in range(hp.m)] if hp.m <= 100_000 else [d]
+        lambdas = [l[ptr[i]:ptr[i + 1]] for i in range(hp.m)] if hp.m <= 100_000 else [l]
+    return Result(value=info.primal_value, psi=info.psi.cpu().numpy(), deltas=deltas, lambdas=lambdas,
+                  nu=info.nu.cpu().numpy(), dual_value=info.dual_value, gap=info.gap,
+                  primal_infeas=info.primal_infeas, iters=info.iters, evals=info.evals, hvps=info.hvps,
+                  status=info.status, wall_s=info.wall_s, info=info)

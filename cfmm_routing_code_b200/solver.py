@@ -1,0 +1,238 @@
+"""Outer dual solver: what replaces `prob.solve()` (arbitrage.py:81-82 / liquidation.py:84-85 /
+two-asset.py:90-91) once the per-pool subproblems are evaluated by the CUDA kernels.
+
+    minimise   g(nu) = sum_j (nu_j - c_j) a_j + sum_i arb_i(A_i' nu)
+    over       nu_j >= c_j (inequality tokens) | nu_j > 0 free (equality tokens) | nu_j = c_j (objective-only)
+
+grad g = a + psi(nu) and the Hessian is sum_i A_i H_i A_i', so one dual evaluation is one pass of the
+pool kernels plus (multi-GPU) ONE all-reduce of the (n_tokens+1)-vector [psi | arb].
+
+Method: projected (active-set) Newton in log-price coordinates; the Newton system is solved either by
+Jacobi-preconditioned truncated CG on kernel Hessian-vector products (large n, matrix free) or by a
+dense Cholesky (small n).  Constant-sum pools make g piecewise linear; they are handled by the method of
+multipliers on their fills (theta_bar), which keeps every inner problem smooth and converges to the exact
+kink solution (both reference instances sit on such a kink).
+
+The vector algebra is torch on whatever device the evaluator lives on; the evaluator protocol is
+    n_tokens, has_sum, evaluate(nu, eps, trades, hess) -> acc[n+1], hvp(vt), hess_diag(), hess_dense(),
+    update_multipliers() -> move[1], reset_multipliers()
+`PoolStore` (CUDA) is the only evaluator this package ships.
+"""
+from __future__ import annotations
+
+import dataclasses
+import time
+from typing import Optional
+
+import numpy as np
+import torch
+
+
+@dataclasses.dataclass
+class DualSpec:
+    """Utility in 'linear + box' form (see api.Arbitrage / Liquidate / Swap)."""
+    c: np.ndarray        # objective coefficients on psi
+    a: np.ndarray        # endowment: constraint is psi_j + a_j >= 0 | == 0
+    eq: np.ndarray       # bool: psi_j + a_j == 0
+    pinned: np.ndarray   # bool: psi_j unconstrained, nu_j = c_j
+
+
+@dataclasses.dataclass
+class SolveInfo:
+    nu: torch.Tensor
+    psi: torch.Tensor
+    dual_value: float
+    primal_value: float
+    gap: float
+    primal_infeas: float
+    err: float
+    iters: int
+    outer: int
+    evals: int
+    hvps: int
+    status: str
+    wall_s: float
+    history: list
+
+
+class Comm:
+    """Sum all-reduce over torch.distributed when world_size > 1, else a no-op."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
+        self.calls = 0
+
+    def allreduce(self, t: torch.Tensor) -> torch.Tensor:
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+            self.calls += 1
+        return t
+
+    def allreduce_max(self, t: torch.Tensor) -> torch.Tensor:
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t
+
+
+def default_nu0(spec: DualSpec) -> np.ndarray:
+    c = np.asarray(spec.c, float)
+    pos = c[c > 0]
+    scale = float(np.median(pos)) if len(pos) else 1.0
+    return np.where(c > 0, c, scale)
+
+
+def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 1e-3, max_outer: int = 40,
+               max_inner: int = 100, linear_solver: str = "auto", cg_max: int = 200, comm: Optional[Comm] = None,
+               verbose: bool = False, final_trades: bool = True) -> SolveInfo:
+    t_start = time.perf_counter()
+    comm = comm or Comm()
+    n = ev.n_tokens
+    dev = ev.device
+    f64 = dict(dtype=torch.float64, device=dev)
+    c = torch.as_tensor(np.asarray(spec.c, float), **f64)
+    a = torch.as_tensor(np.asarray(spec.a, float), **f64)
+    eq = torch.as_tensor(np.asarray(spec.eq, bool), device=dev)
+    fixed = torch.as_tensor(np.asarray(spec.pinned, bool), device=dev)
+    scale = max(float(np.abs(spec.c).max()), 1.0)
+    floor = 1e-12 * scale
+    lb = torch.where(eq, torch.full_like(c, floor), torch.clamp(c, min=floor))
+    nu = torch.as_tensor(default_nu0(spec) if nu0 is None else np.asarray(nu0, float), **f64).clone()
+    nu = torch.maximum(nu, lb)
+    nu = torch.where(fixed, c, nu)
+    has_sum = bool(ev.has_sum)
+    eps_t = float(eps) if has_sum else 0.0
+    if has_sum:
+        ev.reset_multipliers()
+    if linear_solver == "auto":
+        linear_solver = "dense" if (n <= 256 or (has_sum and n <= 4096)) else "cg"
+    evals0, hvps0 = ev.evals, ev.hvps
+    history = []
+
+    def G(nu_, hess=True, trades=False):
+        acc = comm.allreduce(ev.evaluate(nu_, eps_t, trades=trades, hess=hess))
+        psi = acc[:n].clone()
+        g = torch.dot(nu_ - c, a) + acc[n]
+        return psi, g
+
+    iters = 0
+    status = "max_iter"
+    err = float("inf")
+    outer_done = 0
+    for outer in range(max_outer):
+        outer_done = outer + 1
+        psi, g = G(nu)
+        inner_status = "max_iter"
+        for _ in range(max_inner):
+            iters += 1
+            grad = a + psi
+            near = (nu <= lb * (1.0 + min(1e-2, max(err if np.isfinite(err) else 1e-2, 1e-14)))) & ~eq
+            active = fixed | (near & (grad > 0))
+            free = ~active
+            fr = free.to(torch.float64)
+            pg = nu * grad * fr
+            stats = torch.stack([pg.abs().sum(), g.abs(), torch.dot(nu, grad.abs())]).tolist()
+            err = stats[0] / max(stats[1], 1e-3 * stats[2], 1e-300)
+            history.append((time.perf_counter() - t_start, ev.evals - evals0, err))
+            if verbose:
+                print(f"outer {outer} it {iters} g={float(g):.15g} err={err:.3e} free={int(free.sum())}")
+            if err <= tol:
+                inner_status = "optimal"
+                break
+            rhs = -pg
+            # ---- Newton direction in log-price coordinates: Hs dt = -(nu*grad) on the free set
+            if linear_solver == "dense":
+                Hs = comm.allreduce(ev.hess_dense())
+                Hm = Hs * fr[:, None] * fr[None, :]
+                dg = torch.diagonal(Hm)
+                reg = 1e-14 * float(dg.sum()) / max(int(free.sum()), 1)
+                Hm = Hm + torch.diag((1.0 - fr) + reg * fr)
+                L, info = torch.linalg.cholesky_ex(Hm)
+                if int(info) == 0:
+                    dt = torch.cholesky_solve(rhs[:, None], L)[:, 0]
+                else:
+                    dt = torch.linalg.lstsq(Hm, rhs[:, None]).solution[:, 0]
+                dt = dt * fr
+            else:
+                diag = comm.allreduce(ev.hess_diag())
+                dt = _pcg(ev, comm, rhs, fr, diag, eta=min(0.1, err ** 0.5), max_it=cg_max)
+            slope = torch.dot(pg, dt)     # = grad . (nu*dt)
+            if not bool(torch.isfinite(slope)) or float(slope) >= 0.0:
+                dt = -pg / pg.abs().max().clamp(min=1e-300)
+            # ---- projected Armijo backtracking along nu * exp(alpha dt)
+            alpha = 1.0
+            g0 = float(g)
+            ok = False
+            for _ls in range(50):
+                nu_t = torch.maximum(nu * torch.exp(torch.clamp(alpha * dt, -20.0, 20.0)), lb)
+                nu_t = torch.where(fixed, c, nu_t)
+                psi_t, g_t = G(nu_t)
+                lin = float(torch.dot(grad, nu_t - nu))
+                gt = float(g_t)
+                if gt <= g0 + 1e-4 * lin or abs(gt - g0) <= 1e-15 * abs(g0):
+                    ok = True
+                    break
+                alpha *= 0.5
+            if not ok:
+                inner_status = "line_search_failed"
+                break
+            nu, psi, g = nu_t, psi_t, g_t
+        status = inner_status
+        if not has_sum:
+            break
+        # method of multipliers: theta_bar <- fills at the inner solution
+        G(nu, hess=False, trades=True)
+        move = float(comm.allreduce_max(ev.update_multipliers().clone()))
+        if verbose:
+            print(f"outer {outer}: multiplier move {move:.3e}")
+        if move <= tol and inner_status == "optimal":
+            break
+    # ---- final read-back + certificate: primal from the (smoothed, pool-feasible) trades, dual exact
+    psi_f, _ = G(nu, hess=False, trades=final_trades)
+    if has_sum:
+        acc0 = comm.allreduce(ev.evaluate(nu, 0.0, trades=False, hess=False))
+        arb_exact = float(acc0[n])
+    else:
+        arb_exact = float(torch.dot(nu, psi_f))     # arb = nu'psi for the exact evaluation
+    dual = float(torch.dot(nu - c, a)) + arb_exact
+    primal = float(torch.dot(c, psi_f))
+    s = psi_f + a
+    viol = torch.where(fixed, torch.zeros_like(s), torch.where(eq, s.abs(), torch.clamp(-s, min=0.0)))
+    # value-weighted infeasibility relative to the dual value (scale-free)
+    infeas = float(torch.dot(nu, viol)) / max(abs(dual), 1e-300)
+    gap = (dual - primal) / max(abs(dual), 1e-300)
+    return SolveInfo(nu=nu, psi=psi_f, dual_value=dual, primal_value=primal, gap=gap, primal_infeas=infeas,
+                     err=err, iters=iters, outer=outer_done, evals=ev.evals - evals0, hvps=ev.hvps - hvps0,
+                     status=status, wall_s=time.perf_counter() - t_start, history=history)
+
+
+def _pcg(ev, comm, rhs, fr, diag, eta, max_it):
+    """Truncated Jacobi-PCG for Hs x = rhs restricted to the free coordinates (fr = 0/1 mask)."""
+    minv = fr / torch.clamp(diag, min=1e-300)
+    x = torch.zeros_like(rhs)
+    r = rhs * fr
+    z = minv * r
+    p = z.clone()
+    rz = torch.dot(r, z)
+    r0 = float(torch.sqrt(torch.dot(z, r)))
+    if r0 == 0.0:
+        return x
+    for k in range(max_it):
+        Hp = comm.allreduce(ev.hvp(p)) * fr
+        pHp = torch.dot(p, Hp)
+        vals = torch.stack([pHp, rz, torch.dot(p, p * torch.clamp(diag, min=1e-300))]).tolist()
+        if vals[0] <= 1e-14 * vals[2]:          # (near-)zero curvature: homogeneity direction
+            if k == 0:
+                x = p.clone()
+            break
+        alpha = vals[1] / vals[0]
+        x = x + alpha * p
+        r = r - alpha * Hp
+        z = minv * r
+        rz_new = torch.dot(r, z)
+        rn = float(rz_new)
+        if rn <= 0.0 or rn ** 0.5 <= eta * r0:
+            break
+        p = z + (rn / vals[1]) * p
+        rz = rz_new
+    return x

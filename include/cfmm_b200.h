@@ -1,0 +1,109 @@
+/*
+ * cfmm_b200.h -- C ABI of the B200-native CFMM routing hot path (libcfmm_b200.so).
+ *
+ * The reference (angeris/cfmm-routing-code) has no FFI: its boundary is the cvxpy call site.
+ * Each entry point below names the reference lines it replaces.  All pointers are DEVICE
+ * pointers unless the name ends in _host; nothing is allocated inside the *_eval/_hvp calls;
+ * every call is asynchronous on `stream` (a cudaStream_t passed as void*), capturable in a CUDA
+ * graph, and returns 0 or a negative CFMM_E_* code.  No host threads, no CPU fallback.
+ *
+ * Pool storage ("bucket"): pools of one kind and one arity k, slot-major SoA, n_pools long:
+ *   reserves[k][n_pools]  f64   R_i            arbitrage.py:14-20  (reserves)
+ *   tok_idx [k][n_pools]  i32   local_indices  arbitrage.py:6-12   (replaces dense A_i, :42-48)
+ *   gamma   [n_pools]     f64   fees[i]        arbitrage.py:22-28
+ *   weights [k][n_pools]  f64   normalised p/sum(p) of cp.geo_mean(x, p=...)   arbitrage.py:65
+ *   logrw   [k][n_pools]  f64   log(R/w), precomputed once (weighted pools only)
+ *   theta_bar[2][n_pools] f64   constant-sum fills (multipliers of the kink), updated by the solver
+ */
+#ifndef CFMM_B200_H
+#define CFMM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    CFMM_KIND_PRODUCT = 0, /* sqrt(x1 x2) >= sqrt(R1 R2)                 arbitrage.py:68-70 */
+    CFMM_KIND_SUM = 1,     /* sum(x) >= sum(R), x >= 0                   arbitrage.py:73-74 */
+    CFMM_KIND_GEOMEAN = 2  /* prod x^w >= prod R^w                       arbitrage.py:65    */
+};
+
+enum {
+    CFMM_OK = 0,
+    CFMM_E_NULL = -1,      /* required pointer is NULL                                  */
+    CFMM_E_KIND = -2,      /* unknown kind, or arity not supported for that kind         */
+    CFMM_E_SIZE = -3,      /* negative / overflowing size                                */
+    CFMM_E_CUDA = -4,      /* CUDA runtime error (see cfmm_last_cuda_error)              */
+    CFMM_E_NODEVICE = -5,  /* no sm_100 device                                           */
+    CFMM_E_STATE = -6      /* handle used in the wrong state                             */
+};
+
+typedef struct cfmm_bucket {
+    int32_t kind;          /* CFMM_KIND_*                                                */
+    int32_t arity;         /* tokens per pool: 2 for PRODUCT and SUM, 2..32 for GEOMEAN  */
+    int64_t n_pools;
+    const double* reserves;
+    const int32_t* tok_idx;
+    const double* gamma;
+    const double* weights;   /* GEOMEAN only */
+    const double* logrw;     /* GEOMEAN only */
+    const double* theta_bar; /* SUM only     */
+} cfmm_bucket;
+
+/* Optional per-pool outputs of one evaluation (any pointer may be NULL). */
+typedef struct cfmm_eval_out {
+    double* delta;   /* [arity][n_pools]  = deltas[i].value    arbitrage.py:51, two-asset.py:97  */
+    double* lambda;  /* [arity][n_pools]  = lambdas[i].value   arbitrage.py:52, two-asset.py:97  */
+    double* hcoef;   /* [n_pools] curvature coefficient of arb_i in log-price coordinates        */
+    uint32_t* hmask; /* [n_pools] GEOMEAN: bit j set iff token j is traded                      */
+} cfmm_eval_out;
+
+/*
+ * One dual evaluation over one bucket: for every pool solve the optimal-arbitrage subproblem at
+ * prices nu (what `prob.solve()` does for all pools at once, arbitrage.py:81-82, restricted to
+ * fixed nu), then ACCUMULATE
+ *     psi[j]  += sum_i (A_i (Lambda_i - Delta_i))_j       (psi, arbitrage.py:54)
+ *     arb[0]  += sum_i nu_i' (Lambda_i - Delta_i)          (the pool part of the dual value)
+ * nu, log_nu: [n_tokens] (log_nu = log(nu), read by GEOMEAN buckets only).  eps: ramp width of the
+ * constant-sum proximal smoothing (0 = exact bang-bang LP).  psi/arb must be zeroed by the caller
+ * before the first bucket (cfmm_zero does it on the stream).
+ */
+int cfmm_arb_eval(const cfmm_bucket* bucket, int32_t n_tokens, const double* nu, const double* log_nu,
+                  double eps, double* psi, double* arb, const cfmm_eval_out* out, void* stream);
+
+/* y[j] += (Hs vt)_j where Hs = sum_i A_i Hs_i A_i' is the dual Hessian in log-price coordinates
+ * (true Hessian = diag(1/nu) Hs diag(1/nu)), vt = v / nu.  Uses hcoef/hmask from cfmm_arb_eval. */
+int cfmm_hvp(const cfmm_bucket* bucket, int32_t n_tokens, const double* hcoef, const uint32_t* hmask,
+             const double* vt, double* y, void* stream);
+
+/* diag[j] += (Hs)_jj  (Jacobi preconditioner). */
+int cfmm_hess_diag(const cfmm_bucket* bucket, int32_t n_tokens, const double* hcoef, const uint32_t* hmask,
+                   double* diag, void* stream);
+
+/* H[j*n_tokens + k] += (Hs)_jk, dense row-major n_tokens x n_tokens (small n / direct solves). */
+int cfmm_hess_dense(const cfmm_bucket* bucket, int32_t n_tokens, const double* hcoef, const uint32_t* hmask,
+                    double* H, void* stream);
+
+/* SUM buckets: theta_bar <- current fills (= lambda), returns max_i |change|/R in move[0] (device). */
+int cfmm_sum_update_multipliers(const cfmm_bucket* bucket, const double* lambda, double* theta_bar_out,
+                                double* move, void* stream);
+
+/* cudaMemsetAsync(ptr, 0, bytes) on the stream -- lets a host language zero psi/arb without torch. */
+int cfmm_zero(void* ptr, int64_t bytes, void* stream);
+
+/* Tuning knob for experiments (scatter mode: 0 = auto, 1 = global red.add, 2 = shared-memory
+ * privatised histogram).  Not part of the reference-facing surface. */
+int cfmm_set_scatter_mode(int32_t mode);
+
+/* Introspection: number of kernel launches issued by this library since load / last reset. */
+int64_t cfmm_launch_count(void);
+void cfmm_reset_launch_count(void);
+const char* cfmm_last_cuda_error(void);
+const char* cfmm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFMM_B200_H */

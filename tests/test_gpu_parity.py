@@ -1,0 +1,202 @@
+"""CUDA path vs the CPU oracle, through the C ABI (libcfmm_b200.so).  Run on the B200 box: pytest -m gpu."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import cfmm_routing_code_b200 as cf
+from cfmm_routing_code_b200 import _lib, instances as I
+from oracle import cfmm_oracle as O
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+F64 = dict(dtype=torch.float64, device="cuda")
+
+
+def _oracle_eval(hp, nu, eps=0.0, theta=None, **kw):
+    bk = O.Buckets(H.oracle_pools(hp))
+    if theta is not None:
+        for g in bk.groups:
+            if g["kind"] == O.KIND_CONST_SUM:
+                g["theta_bar"] = theta[g["off"]]
+    return O.evaluate(bk, nu, eps, **kw)
+
+
+def _check_eval(hp, nu, eps=0.0, theta=None, scatter_mode=0):
+    st = cf.PoolStore(hp)
+    st.lib.cfmm_set_scatter_mode(scatter_mode)
+    try:
+        if theta is not None:
+            for b in st.buckets:
+                if b.kind == _lib.KIND_SUM:
+                    b.theta_bar.copy_(torch.as_tensor(theta[b.off], **F64))
+        acc = st.evaluate(torch.as_tensor(nu, **F64), eps, trades=True, hess=True).cpu().numpy()
+        d, l = st.gather_trades()
+    finally:
+        st.lib.cfmm_set_scatter_mode(0)
+    ref = _oracle_eval(hp, nu, eps, theta, want_trades=True, want_hess=True)
+    Rmax = np.maximum.reduceat(hp.reserves, hp.pool_ptr[:-1])
+    Rrep = np.repeat(Rmax, np.diff(hp.pool_ptr))
+    # bit-level agreement is not expected (sqrt/exp/sum order); 1e-12 of the reserve scale is
+    assert np.max(np.abs(d - ref["delta"]) / Rrep) <= 1e-12
+    assert np.max(np.abs(l - ref["lam"]) / Rrep) <= 1e-12
+    gross = np.zeros(hp.n_tokens)
+    np.add.at(gross, hp.tok_idx, ref["delta"] + ref["lam"])
+    assert np.max(np.abs(acc[:-1] - ref["psi"]) / (gross + 1e-300 + 1e-9 * gross.max())) <= 1e-11
+    assert abs(acc[-1] - ref["arb"]) <= 1e-11 * np.dot(nu, gross)
+    return st, ref
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_product_eval_matches_oracle(mode):
+    hp, s = H.cp_host_pools(20_000, 97, seed=11)
+    _check_eval(hp, H.random_prices(s["prices"], 1), scatter_mode=mode)
+
+
+def test_product_eval_extreme_prices_and_no_trade():
+    hp, s = H.cp_host_pools(4096, 31, seed=12)
+    _check_eval(hp, s["prices"] * np.exp(3.0 * np.random.default_rng(0).standard_normal(31)))
+    # exactly the pool-implied prices: inside every no-trade cone -> psi == 0
+    hp2 = cf.HostPools.from_pairs(2, np.array([[0, 1]] * 8), np.array([[10.0, 20.0]] * 8), np.full(8, 0.997))
+    st = cf.PoolStore(hp2)
+    acc = st.evaluate(torch.tensor([2.0, 1.0], **F64)).cpu().numpy()
+    assert not acc.any()
+
+
+@pytest.mark.parametrize("eps", [0.0, 1e-3])
+def test_mixed_eval_matches_oracle(eps):
+    hp, s = H.mixed_host_pools(6000, 120, seed=21)
+    rng = np.random.default_rng(2)
+    theta = rng.random(len(hp.reserves)) * hp.reserves * (eps > 0)
+    _check_eval(hp, H.random_prices(s["prices"], 3, 0.03), eps=eps, theta=theta)
+
+
+def test_large_arity_generic_kernel():
+    rng = np.random.default_rng(5)
+    n, m, k = 64, 300, 13
+    idx = np.stack([rng.choice(n, k, replace=False) for _ in range(m)])
+    hp = cf.HostPools.from_lists(n, idx.tolist(), np.exp(rng.normal(3, 1, (m, k))).tolist(),
+                                 rng.choice([0.997, 0.99], m).tolist(), ["geomean"] * m,
+                                 rng.dirichlet(np.ones(k), m).tolist())
+    _check_eval(hp, np.exp(rng.normal(0, 0.2, n)))
+
+
+def test_hessian_products_match_oracle():
+    hp, s = H.mixed_host_pools(5000, 60, seed=31)
+    nu = H.random_prices(s["prices"], 4, 0.03)
+    rng = np.random.default_rng(6)
+    theta = 0.5 * hp.reserves
+    st, ref = _check_eval(hp, nu, eps=1e-2, theta=theta)
+    Hs = ref["hess_scaled"]
+    scale = np.abs(Hs).max()
+    np.testing.assert_allclose(st.hess_dense().cpu().numpy(), Hs, atol=1e-11 * scale)
+    np.testing.assert_allclose(st.hess_diag().cpu().numpy(), np.diag(Hs), atol=1e-11 * scale)
+    v = rng.standard_normal(60)
+    np.testing.assert_allclose(st.hvp(torch.as_tensor(v, **F64)).cpu().numpy(), Hs @ v, atol=1e-10 * scale)
+
+
+def test_reference_instances_end_to_end(golden):
+    d = I.arbitrage_instance()
+    r = cf.solve(d["local_indices"], d["reserves"], d["fees"], d["kinds"], d["weights"],
+                 utility=cf.Arbitrage(d["market_value"]), tol=1e-9)
+    g = golden["arbitrage"]
+    assert r.status == "optimal"
+    assert abs(r.value - g["value"]) <= 1e-6 * abs(g["value"])          # BASELINE.md pass criterion
+    assert abs(r.value - golden["survey_8c"]["arbitrage"]) <= 1e-8 * 21.5
+    np.testing.assert_allclose(r.psi, g["psi"], atol=1e-6 * 3.25)
+    for i in range(5):
+        np.testing.assert_allclose(r.deltas[i], g["deltas"][i], atol=5e-5)
+        np.testing.assert_allclose(r.lambdas[i], g["lambdas"][i], atol=5e-5)
+    d = I.liquidation_instance()
+    r = cf.solve(d["local_indices"], d["reserves"], d["fees"], d["kinds"], d["weights"],
+                 utility=cf.Liquidate(d["target"], d["current_assets"]), tol=1e-9)
+    g = golden["liquidation"]
+    assert r.status == "optimal"
+    assert abs(r.psi[4] - g["value"]) <= 1e-6 * g["value"]
+    np.testing.assert_allclose(r.psi, g["psi"], atol=1e-6 * 15.9)
+    d = I.two_asset_instance()
+    for j in (0, 7, 15, 23, 31, 49):
+        r = cf.solve(d["local_indices"], d["reserves"], d["fees"], d["kinds"], d["weights"],
+                     utility=cf.Swap(0, 2, d["amounts"][j]), tol=1e-9)
+        assert abs(r.value - golden["two_asset"][j]["value"]) <= 1e-6 * max(1.0, golden["two_asset"][j]["value"]), j
+
+
+@pytest.mark.parametrize("linear_solver", ["cg", "dense"])
+def test_cfg2_solve_matches_oracle(linear_solver):
+    """BASELINE.json configs[1]: 10k constant-product pools, 256 tokens."""
+    hp, s = H.cp_host_pools(10_000, 256, seed=0)
+    r = cf.solve_pools(hp, cf.Arbitrage(s["prices"]), tol=1e-9, linear_solver=linear_solver)
+    ro = O.solve(H.oracle_pools(hp), O.Utility.arbitrage(s["prices"]), tol=1e-10)
+    assert r.status == "optimal" and ro.status == "optimal"
+    assert abs(r.value - ro.value) <= 1e-8 * abs(ro.value)
+    assert abs(r.gap) <= 1e-8 and r.primal_infeas <= 1e-8
+    gross = np.zeros(256); np.add.at(gross, hp.tok_idx, np.concatenate(ro.deltas) + np.concatenate(ro.lambdas))
+    assert np.max(np.abs(r.psi - ro.psi) / gross.max()) <= 1e-7
+
+
+def test_cfg3_small_mixed_solve_matches_oracle():
+    hp, s = H.mixed_host_pools(8000, 150, seed=1)
+    r = cf.solve_pools(hp, cf.Arbitrage(s["prices"]), tol=1e-8)
+    ro = O.solve(H.oracle_pools(hp), O.Utility.arbitrage(s["prices"]), tol=1e-9)
+    assert r.status == "optimal"
+    assert abs(r.value - ro.value) <= 1e-6 * abs(ro.value)
+    assert abs(r.gap) <= 1e-6 and r.primal_infeas <= 1e-6
+
+
+def test_cfg4_small_liquidation_matches_oracle():
+    hp, s = H.mixed_host_pools(8000, 150, seed=2)
+    basket = I.synth_basket(150, s["prices"], seed=2)
+    nu0 = s["prices"] / s["prices"][0]
+    r = cf.solve_pools(hp, cf.Liquidate(0, basket), nu0=nu0, tol=1e-8)
+    ro = O.solve(H.oracle_pools(hp), O.Utility.liquidate(150, 0, basket), nu0=nu0, tol=1e-9)
+    assert r.status == "optimal"
+    assert abs(r.value - ro.value) <= 1e-6 * abs(ro.value)
+    np.testing.assert_allclose(r.psi[1:], -basket[1:], atol=1e-6 * basket.max())
+
+
+def test_full_size_properties_1m_pools():
+    """BASELINE.json configs[4] size (1M pools, 4096 tokens): oracle-free invariants."""
+    hp, s = H.cp_host_pools(1_000_000, 4096, seed=3)
+    st = cf.PoolStore(hp)
+    nu = torch.as_tensor(H.random_prices(s["prices"], 9, 0.01), **F64)
+    a1 = st.evaluate(nu).clone()
+    a2 = st.evaluate(7.0 * nu).clone()
+    gross = float(a1[:-1].abs().max())
+    assert float((a1[:-1] - a2[:-1]).abs().max()) <= 1e-9 * gross          # psi is degree 0
+    assert abs(float(a2[-1]) - 7.0 * float(a1[-1])) <= 1e-10 * abs(float(a2[-1]))   # arb is degree 1
+    assert abs(float(torch.dot(nu, a1[:-1])) - float(a1[-1])) <= 1e-9 * abs(float(a1[-1]))  # arb = nu'psi
+    # shard additivity: two half-stores sum to the whole (what the multi-GPU all-reduce relies on)
+    h0 = cf.PoolStore(hp, rank=0, world=2).evaluate(nu).clone()
+    h1 = cf.PoolStore(hp, rank=1, world=2).evaluate(nu).clone()
+    assert float((h0 + h1 - a1)[:-1].abs().max()) <= 1e-9 * gross
+    # a 100k-pool slice against the oracle (the oracle finishes this in well under a second)
+    sub = cf.HostPools.from_pairs(4096, hp.tok_idx.reshape(-1, 2)[:100_000], hp.reserves.reshape(-1, 2)[:100_000],
+                                  hp.gamma[:100_000])
+    _check_eval(sub, nu.cpu().numpy())
+
+
+def test_full_size_solve_reaches_1e6_gap():
+    hp, s = H.cp_host_pools(1_000_000, 4096, seed=3)
+    r = cf.solve_pools(hp, cf.Arbitrage(s["prices"]), tol=1e-6, want_trades=False)
+    assert r.status == "optimal"
+    assert abs(r.gap) <= 1e-6 and r.primal_infeas <= 1e-6
+    assert r.value > 0
+
+
+def test_error_codes_and_empty_bucket():
+    lib = _lib.load()
+    b = _lib.Bucket(_lib.KIND_PRODUCT, 2, 10, None, None, None, None, None, None)
+    assert lib.cfmm_arb_eval(C.byref(b), 4, None, None, 0.0, None, None, None, None) == -1
+    x = torch.zeros(8, **F64)
+    b = _lib.Bucket(7, 2, 0, x.data_ptr(), x.data_ptr(), x.data_ptr(), None, None, None)
+    assert lib.cfmm_arb_eval(C.byref(b), 4, x.data_ptr(), None, 0.0, x.data_ptr(), x.data_ptr(), None, None) == -2
+    b = _lib.Bucket(_lib.KIND_SUM, 3, 1, x.data_ptr(), x.data_ptr(), x.data_ptr(), None, None, None)
+    assert lib.cfmm_arb_eval(C.byref(b), 4, x.data_ptr(), None, 0.0, x.data_ptr(), x.data_ptr(), None, None) == -2
+    b = _lib.Bucket(_lib.KIND_PRODUCT, 2, 0, None, None, None, None, None, None)     # empty: a no-op
+    assert lib.cfmm_arb_eval(C.byref(b), 4, x.data_ptr(), None, 0.0, x.data_ptr(), x.data_ptr(), None, None) == 0
+    with pytest.raises(ValueError):
+        cf.HostPools.from_lists(3, [[0, 1, 2]], [[1, 1, 1]], [0.99], ["sum"])
+    with pytest.raises(ValueError):
+        cf.HostPools.from_pairs(2, [[0, 1]], [[1.0, -1.0]], [0.99]).validate()

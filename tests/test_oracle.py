@@ -1,0 +1,137 @@
+"""Oracle vs golden vectors, closed forms and brute force (CPU only)."""
+import numpy as np
+import pytest
+from scipy import optimize
+
+from cfmm_routing_code_b200 import instances as I
+from oracle import cfmm_oracle as O
+import helpers as H
+
+
+def _solve(d, util):
+    return O.solve(H.oracle_pools(H.host_pools(d)), util, tol=1e-10)
+
+
+def test_arbitrage_matches_golden(golden):
+    d = I.arbitrage_instance()
+    r = _solve(d, O.Utility.arbitrage(d["market_value"]))
+    g = golden["arbitrage"]
+    assert r.status == "optimal"
+    assert abs(r.value - g["value"]) <= 1e-8 * abs(g["value"])           # scipy-primal golden
+    assert abs(r.value - golden["survey_8c"]["arbitrage"]) <= 1e-9 * 21.5   # SURVEY 8c (zero-gap) value
+    np.testing.assert_allclose(r.psi, g["psi"], atol=2e-6)
+    assert abs(r.gap) <= 1e-8 and r.primal_infeas <= 1e-8
+    for i in range(5):
+        np.testing.assert_allclose(r.deltas[i], g["deltas"][i], atol=5e-5)
+        np.testing.assert_allclose(r.lambdas[i], g["lambdas"][i], atol=5e-5)
+
+
+def test_liquidation_matches_golden(golden):
+    d = I.liquidation_instance()
+    r = _solve(d, O.Utility.liquidate(5, d["target"], d["current_assets"]))
+    g = golden["liquidation"]
+    assert r.status == "optimal"
+    assert abs(r.value - g["value"]) <= 1e-8 * abs(g["value"])
+    assert abs(r.value - golden["survey_8c"]["liquidation"]) <= 1e-9 * 16
+    np.testing.assert_allclose(r.psi, g["psi"], atol=2e-6)
+
+
+def test_two_asset_sweep_matches_golden(golden):
+    d = I.two_asset_instance()
+    P = H.oracle_pools(H.host_pools(d))
+    for j in range(0, 50, 3):
+        r = O.solve(P, O.Utility.swap(3, 0, 2, d["amounts"][j]), tol=1e-10)
+        g = golden["two_asset"][j]
+        assert abs(r.value - g["value"]) <= 1e-7 * max(abs(g["value"]), 1), j
+    assert abs(golden["two_asset"][0]["value"] - golden["survey_8c"]["two_asset_t0"]) < 1e-8
+    assert abs(golden["two_asset"][49]["value"] - golden["survey_8c"]["two_asset_t50"]) < 1e-8
+
+
+def test_product_closed_form_equals_geomean_breakpoint_solver():
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        R = np.exp(rng.normal(3, 1, 2)); nu = np.exp(rng.normal(0, 1, 2)); gam = rng.choice([0.997, 0.999, 0.95])
+        D1, L1 = O.arb_product_scalar(R, gam, nu)
+        D2, L2, _ = O.arb_geomean_scalar(R, [0.5, 0.5], gam, nu)
+        np.testing.assert_allclose(D1, D2, rtol=1e-9, atol=1e-12 * R.max())
+        np.testing.assert_allclose(L1, L2, rtol=1e-9, atol=1e-12 * R.max())
+
+
+def test_geomean_scalar_is_optimal_vs_brute_force():
+    """The KKT solution beats random feasible trades and matches SLSQP on the pool's own program."""
+    rng = np.random.default_rng(1)
+    for k in (2, 3, 5):
+        R = np.exp(rng.normal(2, 0.5, k)); w = rng.dirichlet(np.ones(k)); nu = np.exp(rng.normal(0, 0.3, k))
+        gam = 0.99
+        D, L, _ = O.arb_geomean_scalar(R, w, gam, nu)
+        x = R + gam * D - L
+        assert np.dot(w, np.log(x)) >= np.dot(w, np.log(R)) - 1e-12      # feasible (arbitrage.py:65)
+        val = np.dot(nu, L - D)
+        f = lambda z: -np.dot(nu, z[k:] - z[:k])
+        con = dict(type="ineq", fun=lambda z: np.dot(w, np.log(np.maximum(R + gam * z[:k] - z[k:], 1e-300))
+                                                     - np.log(R)))
+        res = optimize.minimize(f, np.zeros(2 * k), method="SLSQP", bounds=[(0, None)] * (2 * k),
+                                constraints=[con], options=dict(ftol=1e-14, maxiter=500))
+        assert val >= -res.fun - 1e-7 * max(1, abs(val))
+
+
+def test_no_trade_cone_and_homogeneity():
+    R = np.array([10.0, 20.0]); gam = 0.997
+    nu = np.array([2.0, 1.0])                   # pool price R1/R0 = 2 = nu0/nu1: inside the cone
+    D, L = O.arb_product_scalar(R, gam, nu)
+    assert not D.any() and not L.any()
+    D, L, _ = O.arb_geomean_scalar(R, [0.5, 0.5], gam, nu)
+    assert not D.any() and not L.any()
+    nu = np.array([2.3, 1.0])
+    D1, L1 = O.arb_product_scalar(R, gam, nu)
+    D2, L2 = O.arb_product_scalar(R, gam, 7.5 * nu)
+    np.testing.assert_allclose(D1, D2, rtol=1e-13); np.testing.assert_allclose(L1, L2, rtol=1e-13)
+
+
+def test_const_sum_lp_rule_and_smoothing_is_pool_feasible():
+    R = np.array([10.0, 10.0]); gam = 0.999
+    D, L = O.arb_sum_scalar(R, gam, np.array([1.0, 1.01]))      # token 1 dearer: drain it
+    assert L[1] == 10.0 and abs(D[0] - 10.0 / gam) < 1e-12 and L[0] == 0 and D[1] == 0
+    D, L = O.arb_sum_scalar(R, gam, np.array([1.0, 1.0005]))    # inside the fee band: nothing
+    assert not D.any() and not L.any()
+    for thb in (0.0, 3.0):
+        for r in np.linspace(0.999, 1.003, 9):
+            nu = np.array([1.0, r / gam])
+            D, L = O.arb_sum_scalar(R, gam, nu, eps=1e-3, theta_bar=(0.0, thb))
+            x = R + gam * D - L
+            assert x.sum() >= R.sum() - 1e-12 and np.all(x >= -1e-12)      # arbitrage.py:73-74
+
+
+def test_vectorised_evaluation_equals_scalar_solvers():
+    hp, s = H.mixed_host_pools(600, 40, seed=5)
+    P = H.oracle_pools(hp)
+    nu = H.random_prices(s["prices"], 7)
+    ev = O.evaluate(O.Buckets(P), nu, eps=0.0, want_trades=True)
+    ptr = P.pool_ptr
+    for i in range(P.m):
+        sl = slice(ptr[i], ptr[i + 1])
+        R, w, loc = P.reserves[sl], P.weights[sl], nu[P.tok_idx[sl]]
+        if P.kind[i] == O.KIND_CONST_SUM:
+            D, L = O.arb_sum_scalar(R, P.gamma[i], loc)
+        else:
+            D, L, _ = O.arb_geomean_scalar(R, w, P.gamma[i], loc)
+        np.testing.assert_allclose(ev["delta"][sl], D, rtol=1e-9, atol=1e-11 * R.max())
+        np.testing.assert_allclose(ev["lam"][sl], L, rtol=1e-9, atol=1e-11 * R.max())
+
+
+def test_gradient_and_hessian_by_finite_differences():
+    hp, s = H.mixed_host_pools(300, 12, seed=3)
+    hp.kind[:] = 0                      # geomean only: smooth
+    hp.weights[hp.weights == 0] = 0.5
+    P = H.oracle_pools(hp)
+    bk = O.Buckets(P)
+    nu = H.random_prices(s["prices"], 11, 0.2)
+    ev = O.evaluate(bk, nu, want_hess=True)
+    Hs = ev["hess_scaled"] / nu[:, None] / nu[None, :]
+    for j in range(12):
+        h = 1e-6 * nu[j]
+        e = np.zeros(12); e[j] = h
+        ep, em = O.evaluate(bk, nu + e), O.evaluate(bk, nu - e)
+        assert abs((ep["arb"] - em["arb"]) / (2 * h) - ev["psi"][j]) <= 1e-5 * (abs(ev["psi"][j]) + 1)
+        np.testing.assert_allclose((ep["psi"] - em["psi"]) / (2 * h), Hs[:, j],
+                                   atol=2e-4 * np.abs(Hs[:, j]).max())
