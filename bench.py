@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py -- pools x dual-evaluations / second on BASELINE.json configs[4] (1M constant-product pools,
+4096 tokens), plus wall-clock to 1e-6 relative gap, the HBM roofline of the dominant kernel, and the CPU
+baseline timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--scaling weak|strong]
+
+A "step" is one dual evaluation: the per-pool optimal-arbitrage kernel over this rank's pools, accumulating
+psi(nu) and the dual value (+ one all-reduce of the (n_tokens+1)-vector when N > 1).  Steps rotate over 8
+independent pool instances per GPU (8 x 32 MB = 256 MB > the 126 MB L2), so every step streams its pools from
+HBM.  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M_POOLS = 1_000_000
+N_TOKENS = 4096
+N_INSTANCES = 8
+METRIC = "pools x dual-evaluations / second (1M constant-product pools, 4096 tokens); time to 1e-6 rel-gap reported beside it"
+UNIT = "pool-evals/s"
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (the recipe's clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.stop = threading.Event()
+        self.index = index
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU legs (the ONLY places this file executes oracle/)
+# --------------------------------------------------------------------------------------------------
+def cpu_eval_throughput(seconds_budget=12.0):
+    """oracle (numpy port) dual evaluations over the full 1M-pool instance on the host: pool-evals/s."""
+    from cfmm_routing_code_b200 import instances as I
+    from oracle import cfmm_oracle as O
+    s = I.synth_const_product(M_POOLS, N_TOKENS, seed=3)
+    P = O.Pools(N_TOKENS, np.arange(0, 2 * M_POOLS + 1, 2, dtype=np.int64), s["idx"].reshape(-1).astype(np.int32),
+                s["reserves"].reshape(-1), np.full(2 * M_POOLS, 0.5), s["gamma"], np.zeros(M_POOLS, np.uint8))
+    bk = O.Buckets(P)
+    nu = s["prices"] * np.exp(0.01 * np.random.default_rng(0).standard_normal(N_TOKENS))
+    O.evaluate(bk, nu)            # warm
+    t0 = time.perf_counter(); k = 0
+    while True:
+        O.evaluate(bk, nu * (1 + 1e-3 * k)); k += 1
+        dt = time.perf_counter() - t0
+        if dt > seconds_budget or k >= 50:
+            break
+    return M_POOLS * k / dt, k, dt
+
+
+def run_reference(args):
+    """The reference's path on the host cores.  cvxpy (the reference's solver) is probed at run time; it is
+    not in this image, so the oracle port (same dual evaluation, numpy, 1 thread) stands in -- kind 'port'."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    try:
+        import cvxpy  # noqa: F401
+        have_cvxpy = True
+    except Exception:
+        have_cvxpy = False
+    vals = []
+    per_step_budget = max(2.0, min(20.0, 120.0 / max(args.steps + args.warmup, 1)))
+    for i in range(args.warmup + args.steps):
+        v, k, dt = cpu_eval_throughput(per_step_budget)
+        if i >= args.warmup:
+            vals.append((v, k, dt))
+    value = float(np.mean([v for v, _, _ in vals]))
+    sample = f"{vals[0][1]} oracle dual evaluations of the full 1M-pool/4096-token instance per step (numpy, fp64)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean([dt / k for _, k, dt in vals])),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args.gpus, args.scaling),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "note": "reference solver (cvxpy) " + ("present but not used for this metric" if have_cvxpy
+                                                               else "unavailable in image")},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus, scaling):
+    per = M_POOLS if scaling == "weak" else M_POOLS // n_gpus
+    return {"workload": "BASELINE.json configs[4]: 1M constant-product pools, 4096 tokens, Arbitrage(c=p), seed 3",
+            "pools_per_gpu": per, "n_tokens": N_TOKENS, "parallelism": f"pool-shard x{n_gpus}",
+            "l2": f"rotating {N_INSTANCES} pool instances per GPU ({N_INSTANCES * per * 32 // 2**20} MiB) > 126 MB L2",
+            "collective": "none" if n_gpus == 1 else "one all-reduce of n_tokens+1 f64 per step (NCCL)"}
+
+
+# --------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import cfmm_routing_code_b200 as cf
+    from cfmm_routing_code_b200 import instances as I
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU leg")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+    per = M_POOLS if args.scaling == "weak" else M_POOLS // world
+    f64 = dict(dtype=torch.float64, device=dev)
+
+    stores, nus = [], []
+    for k in range(N_INSTANCES):
+        # weak: every rank owns `per` pools of its own (seeded by rank); strong: rank's slice of the seed-3 instance
+        if args.scaling == "weak":
+            s = I.synth_const_product(per, N_TOKENS, seed=3 + 100 * k + 7919 * rank)
+        else:
+            s = I.synth_const_product(M_POOLS, N_TOKENS, seed=3 + 100 * k)
+            sl = slice(rank * per, (rank + 1) * per)
+            s = dict(s, idx=s["idx"][sl], reserves=s["reserves"][sl], gamma=s["gamma"][sl])
+        hp = cf.HostPools.from_pairs(N_TOKENS, s["idx"], s["reserves"], s["gamma"])
+        stores.append(cf.PoolStore(hp, device=dev, validate=False))
+        p = I.synth_const_product(8, N_TOKENS, seed=3)["prices"]        # same token prices on every rank
+        nus.append(torch.as_tensor(p * np.exp(0.01 * np.random.default_rng(k).standard_normal(N_TOKENS)), **f64))
+    lib = stores[0].lib
+
+    def step(i):
+        acc = stores[i % N_INSTANCES].evaluate(nus[i % N_INSTANCES])
+        if world > 1:
+            dist.all_reduce(acc)
+        return acc
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lib.cfmm_reset_launch_count()
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        e1.record()
+        barrier()
+    launches = int(lib.cfmm_launch_count())
+    ms = torch.tensor([e0.elapsed_time(e1)], **f64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms)
+    ms_per_step = total_ms / args.steps
+    value = n_gpus * per / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (k_eval_pair<PRODUCT>): algorithmic bytes / avg launch duration
+    alg_bytes = stores[0].algorithmic_bytes_per_eval()
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tfile):
+        try:
+            traffic = json.load(open(tfile)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "k_eval_pair<PRODUCT>", "algorithmic_bytes_per_launch": alg_bytes,
+                "peak_source": peak_src,
+                "note": "duration = timed region / steps (includes the 32 KB memset, launch gaps" +
+                        (", all-reduce)" if world > 1 else ")")}
+
+    # ---- e2e: the public API on HOST buffers: upload pools, solve to 1e-6, read psi/nu back
+    e2e = None
+    time_to_gap = None
+    if (rank == 0 or world > 1) and not args.no_e2e:
+        s = I.synth_const_product(M_POOLS, N_TOKENS, seed=3)
+        hp = cf.HostPools.from_pairs(N_TOKENS, s["idx"], s["reserves"], s["gamma"])
+        runs = []
+        for rep in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            r = cf.solve_pools(hp, cf.Arbitrage(s["prices"]), tol=1e-6, want_trades=False, device=dev)
+            torch.cuda.synchronize()
+            runs.append((time.perf_counter() - t0, r))
+        wall, r = min(runs, key=lambda x: x[0])
+        if world > 1:
+            w = torch.tensor([wall], **f64); dist.all_reduce(w, op=dist.ReduceOp.MAX); wall = float(w)
+        h2d = hp.reserves.nbytes + hp.tok_idx.nbytes + hp.gamma.nbytes + 8 * N_TOKENS
+        e2e = {"value": M_POOLS * r.evals / wall, "unit": UNIT, "h2d_bytes_per_step": int(h2d / max(world, 1)),
+               "d2h_bytes_per_step": 16 * N_TOKENS + 64,
+               "what": "cf.solve_pools(host numpy pools, Arbitrage(p), tol=1e-6): upload + solve + psi/nu read-back; "
+                       "value = pools x dual evaluations / wall",
+               "wall_s": wall, "evals": r.evals, "hvps": r.hvps, "iters": r.iters, "status": r.status,
+               "gap": r.gap, "primal_infeas": r.primal_infeas}
+        time_to_gap = {"seconds_incl_upload": wall, "seconds_solver_only": r.wall_s, "rel_gap": abs(r.gap),
+                       "primal_infeas": r.primal_infeas, "tol": 1e-6}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, k, dt = cpu_eval_throughput(12.0)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{k} oracle (numpy, fp64) dual evaluations of the same 1M-pool instance in {dt:.1f}s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(n_gpus, args.scaling), "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": e2e, "time_to_1e-6_gap": time_to_gap, "gpu_launches": launches, "clocks": clocks.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer solve leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 20:
+            args.steps = 5          # each reference step is seconds of CPU work
+            args.warmup = min(args.warmup, 1)
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

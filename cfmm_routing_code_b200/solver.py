@@ -82,8 +82,8 @@ def default_nu0(spec: DualSpec) -> np.ndarray:
     return np.where(c > 0, c, scale)
 
 
-def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 1e-3, max_outer: int = 40,
-               max_inner: int = 100, linear_solver: str = "auto", cg_max: int = 200, comm: Optional[Comm] = None,
+def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 0.1, eps_min: float = 1e-4,
+               eps_shrink: float = 0.25, max_outer: int = 60, max_inner: int = 100, linear_solver: str = "auto", cg_max: int = 200, comm: Optional[Comm] = None,
                verbose: bool = False, final_trades: bool = True) -> SolveInfo:
     t_start = time.perf_counter()
     comm = comm or Comm()
@@ -115,28 +115,34 @@ def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 1e-
         g = torch.dot(nu_ - c, a) + acc[n]
         return psi, g
 
+    def kkt(nu_, psi_, g_, err_prev):
+        """free set + scaled KKT residual: sum_free |nu_j (a_j+psi_j)| / |g|  (bounds gap AND infeasibility)."""
+        grad_ = a + psi_
+        thr = min(1e-2, max(err_prev if np.isfinite(err_prev) else 1e-2, 1e-14))
+        near = (nu_ <= lb * (1.0 + thr)) & ~eq
+        fr_ = (~(fixed | (near & (grad_ > 0)))).to(torch.float64)
+        pg_ = nu_ * grad_ * fr_
+        st = torch.stack([pg_.abs().sum(), g_.abs(), torch.dot(nu_, grad_.abs())]).tolist()
+        return st[0] / max(st[1], 1e-3 * st[2], 1e-300), grad_, fr_, pg_
+
     iters = 0
     status = "max_iter"
     err = float("inf")
     outer_done = 0
+    move = 1.0
     for outer in range(max_outer):
         outer_done = outer + 1
         psi, g = G(nu)
         inner_status = "max_iter"
+        # early outer passes need not be solved tightly: the multipliers are still moving
+        inner_tol = max(tol, min(1e-3, 1e-2 * move)) if has_sum else tol
+        err, grad, fr, pg = kkt(nu, psi, g, err)
         for _ in range(max_inner):
             iters += 1
-            grad = a + psi
-            near = (nu <= lb * (1.0 + min(1e-2, max(err if np.isfinite(err) else 1e-2, 1e-14)))) & ~eq
-            active = fixed | (near & (grad > 0))
-            free = ~active
-            fr = free.to(torch.float64)
-            pg = nu * grad * fr
-            stats = torch.stack([pg.abs().sum(), g.abs(), torch.dot(nu, grad.abs())]).tolist()
-            err = stats[0] / max(stats[1], 1e-3 * stats[2], 1e-300)
             history.append((time.perf_counter() - t_start, ev.evals - evals0, err))
             if verbose:
-                print(f"outer {outer} it {iters} g={float(g):.15g} err={err:.3e} free={int(free.sum())}")
-            if err <= tol:
+                print(f"outer {outer} it {iters} g={float(g):.15g} err={err:.3e} free={int(fr.sum())}")
+            if err <= inner_tol:
                 inner_status = "optimal"
                 break
             rhs = -pg
@@ -145,7 +151,7 @@ def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 1e-
                 Hs = comm.allreduce(ev.hess_dense())
                 Hm = Hs * fr[:, None] * fr[None, :]
                 dg = torch.diagonal(Hm)
-                reg = 1e-14 * float(dg.sum()) / max(int(free.sum()), 1)
+                reg = 1e-14 * float(dg.sum()) / max(int(fr.sum()), 1)
                 Hm = Hm + torch.diag((1.0 - fr) + reg * fr)
                 L, info = torch.linalg.cholesky_ex(Hm)
                 if int(info) == 0:
@@ -169,24 +175,38 @@ def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 1e-
                 psi_t, g_t = G(nu_t)
                 lin = float(torch.dot(grad, nu_t - nu))
                 gt = float(g_t)
-                if gt <= g0 + 1e-4 * lin or abs(gt - g0) <= 1e-15 * abs(g0):
+                if gt <= g0 + 1e-4 * lin:
                     ok = True
                     break
+                if abs(gt - g0) <= 1e-13 * abs(g0):
+                    # below the resolution of g in fp64: judge the step by the KKT residual instead
+                    if kkt(nu_t, psi_t, g_t, err)[0] < err:
+                        ok = True
+                        break
+                    if alpha < 1e-3:
+                        break
                 alpha *= 0.5
             if not ok:
-                inner_status = "line_search_failed"
+                inner_status = "stalled"
                 break
             nu, psi, g = nu_t, psi_t, g_t
+            err, grad, fr, pg = kkt(nu, psi, g, err)
         status = inner_status
         if not has_sum:
             break
-        # method of multipliers: theta_bar <- fills at the inner solution
-        G(nu, hess=False, trades=True)
-        move = float(comm.allreduce_max(ev.update_multipliers().clone()))
+        # method of multipliers.  The smoothed trades are pool-feasible, so (exact dual - primal) at this nu
+        # is a true optimality certificate; stop on it rather than on the multiplier step, whose floor is
+        # (fp64 resolution of the price ratio) / eps.
+        psi_s, _ = G(nu, hess=False, trades=True)
+        acc0 = comm.allreduce(ev.evaluate(nu, 0.0, trades=False, hess=False))
+        dual_now = float(torch.dot(nu - c, a) + acc0[n])
+        gap_now = (dual_now - float(torch.dot(c, psi_s))) / max(abs(dual_now), 1e-300)
         if verbose:
-            print(f"outer {outer}: multiplier move {move:.3e}")
-        if move <= tol and inner_status == "optimal":
-            break
+            print(f"outer {outer}: eps {eps_t:.1e} last move {move:.3e} gap {gap_now:.3e}")
+        if inner_status == "optimal" and err <= tol and abs(gap_now) <= tol:
+            break           # multipliers stay as they are: the read-back below reproduces psi_s
+        move = float(comm.allreduce_max(ev.update_multipliers().clone()))
+        eps_t = max(float(eps_min), eps_t * float(eps_shrink))
     # ---- final read-back + certificate: primal from the (smoothed, pool-feasible) trades, dual exact
     psi_f, _ = G(nu, hess=False, trades=final_trades)
     if has_sum:

@@ -327,7 +327,7 @@ class Result:
     nu: np.ndarray
     dual_value: float
     gap: float                   # (dual - primal)/max(|dual|, tiny)
-    primal_infeas: float         # relative to gross token flow
+    primal_infeas: float         # sum_j nu_j * violation_j / |dual value|
     iters: int
     evals: int
     status: str
@@ -342,115 +342,123 @@ def dual_value(util: Utility, nu, arb):
     return float(np.dot(nu - util.c, util.a) + arb)
 
 
-def residuals(util: Utility, nu, psi, flow_scale):
-    """primal objective, complementarity gap, infeasibility (all from one evaluation)."""
+def residuals(util: Utility, nu, psi, dual):
+    """primal objective c'psi and the value-weighted constraint violation relative to the dual value."""
     s = psi + util.a                      # must be >=0 (ineq) / ==0 (eq) / free (pinned)
     viol = np.where(util.pinned, 0.0, np.where(util.eq, np.abs(s), np.maximum(-s, 0.0)))
-    infeas = float(np.max(viol / flow_scale)) if len(viol) else 0.0
+    infeas = float(np.dot(nu, viol)) / max(abs(dual), 1e-300)
     primal = float(np.dot(util.c, psi))
     return primal, infeas
 
 
-def solve(pools: Pools, util: Utility, nu0=None, tol=1e-9, eps=1e-3, max_outer=40, max_inner=100,
-          verbose=False) -> Result:
-    """Method of multipliers on the constant-sum fills (outer) around a projected (active-set)
-    Newton method on the smooth dual g_t(nu) (inner).  Dense n x n Hessian -- fine for the
-    oracle's sizes (n <= ~1000).  With no constant-sum pool there is one outer pass."""
+def solve(pools: Pools, util: Utility, nu0=None, tol=1e-9, eps=0.1, eps_min=1e-4, eps_shrink=0.25,
+          max_outer=60, max_inner=100, verbose=False) -> Result:
+    """Method of multipliers on the constant-sum fills (outer, ramp width eps shrinking geometrically)
+    around a projected (active-set) Newton method in log-price coordinates on the smooth dual g_t(nu)
+    (inner), dense n x n Hessian -- fine for the oracle's sizes (n <= ~1000).  With no constant-sum
+    pool there is one outer pass.  Same algorithm as the product's solver.py, restated in numpy."""
     bk = Buckets(pools)
     n = pools.n_tokens
     sum_groups = [g for g in bk.groups if g["kind"] == KIND_CONST_SUM]
     for g in sum_groups:
         g["theta_bar"] = np.zeros_like(g["R"])
     scale = np.maximum(np.abs(util.c).max(), 1.0)
-    nu_floor = 1e-12 * scale
-    lb = _bounds(util, nu_floor)
+    lb = _bounds(util, 1e-12 * scale)
     fixed = util.pinned.copy()
     if nu0 is None:
-        nu = np.where(util.c > 0, util.c, scale)
-        nu = np.maximum(nu, lb)
+        pos = util.c[util.c > 0]
+        nu = np.where(util.c > 0, util.c, np.median(pos) if len(pos) else 1.0)
     else:
-        nu = np.maximum(np.asarray(nu0, float), lb)
+        nu = np.asarray(nu0, float).copy()
+    nu = np.maximum(nu, lb)
     nu[fixed] = util.c[fixed]
     evals = 0; iters = 0
     status = "max_iter"
     eps_t = eps if sum_groups else 0.0
 
-    def G(nu_, **kw):
+    def G(nu_, eps_=None, **kw):
         nonlocal evals
         evals += 1
-        ev = evaluate(bk, nu_, eps_t, **kw)
+        ev = evaluate(bk, nu_, eps_t if eps_ is None else eps_, **kw)
         ev["g"] = dual_value(util, nu_, ev["arb"])
-        ev["grad"] = util.a + ev["psi"]
         return ev
 
+    def kkt(nu_, ev_, err_prev):
+        grad = util.a + ev_["psi"]
+        thr = min(1e-2, max(err_prev if np.isfinite(err_prev) else 1e-2, 1e-14))
+        near = (nu_ <= lb * (1 + thr)) & ~util.eq
+        free = ~(fixed | (near & (grad > 0)))
+        pg = np.where(free, nu_ * grad, 0.0)
+        den = max(abs(ev_["g"]), 1e-3 * np.dot(nu_, np.abs(grad)), 1e-300)
+        return np.abs(pg).sum() / den, grad, free, pg
+
+    err = np.inf
+    move = 1.0
     for outer in range(max_outer):
         ev = G(nu, want_hess=True)
         inner_status = "max_iter"
+        inner_tol = max(tol, min(1e-3, 1e-2 * move)) if sum_groups else tol
+        err, grad, free, pg = kkt(nu, ev, err)
         for _ in range(max_inner):
             iters += 1
-            grad = ev["grad"]
-            at_lb = (nu <= lb * (1 + 1e-14)) & ~util.eq
-            active = fixed | (at_lb & (grad > 0))
-            free = ~active
-            pg = np.where(free, nu * grad, 0.0)      # value units
-            denom = max(abs(ev["g"]), 1e-3 * np.dot(nu, np.abs(grad)), 1e-300)
-            err = np.abs(pg).sum() / denom
             if verbose:
                 print(f"outer={outer} it={iters} g={ev['g']:.15g} err={err:.3e} free={free.sum()}")
-            if err <= tol:
+            if err <= inner_tol:
                 inner_status = "optimal"
                 break
             Hs = ev["hess_scaled"][np.ix_(free, free)]
-            rhs = -(nu * grad)[free]
+            rhs = -pg[free]
             reg = 1e-14 * max(np.trace(Hs) / max(free.sum(), 1), 1e-300)
             try:
-                dt = np.linalg.solve(Hs + reg * np.eye(len(rhs)), rhs)
+                dtf = np.linalg.solve(Hs + reg * np.eye(len(rhs)), rhs)
             except np.linalg.LinAlgError:
-                dt = np.linalg.lstsq(Hs, rhs, rcond=None)[0]
-            d = np.zeros(n); d[free] = nu[free] * dt
-            if not np.all(np.isfinite(d)) or np.dot(d, grad) >= 0:
-                d = np.where(free, -nu * nu * grad / max(np.abs(nu * grad).max(), 1e-300), 0.0)
+                dtf = np.linalg.lstsq(Hs, rhs, rcond=None)[0]
+            dt = np.zeros(n); dt[free] = dtf
+            if not np.all(np.isfinite(dt)) or np.dot(pg, dt) >= 0:
+                dt = -pg / max(np.abs(pg).max(), 1e-300)
             alpha = 1.0
             g0 = ev["g"]
             ok = False
-            for _ls in range(60):
-                nu_t = np.maximum(nu + alpha * d, lb)
-                nu_t = np.clip(nu_t, nu * 1e-3, nu * 1e3)     # prices stay positive
+            for _ls in range(50):
+                nu_t = np.maximum(nu * np.exp(np.clip(alpha * dt, -20, 20)), lb)
                 nu_t[fixed] = util.c[fixed]
                 ev_t = G(nu_t, want_hess=True)
-                if ev_t["g"] <= g0 + 1e-4 * np.dot(grad, nu_t - nu) or \
-                        abs(ev_t["g"] - g0) <= 1e-15 * abs(g0):
+                lin = np.dot(grad, nu_t - nu)
+                if ev_t["g"] <= g0 + 1e-4 * lin:
                     ok = True
                     break
+                if abs(ev_t["g"] - g0) <= 1e-13 * abs(g0):       # below fp64 resolution of g
+                    if kkt(nu_t, ev_t, err)[0] < err:
+                        ok = True
+                        break
+                    if alpha < 1e-3:
+                        break
                 alpha *= 0.5
             if not ok:
-                inner_status = "line_search_failed"
+                inner_status = "stalled"
                 break
             nu, ev = nu_t, ev_t
+            err, grad, free, pg = kkt(nu, ev, err)
         status = inner_status
         if not sum_groups:
             break
-        # multiplier update: theta_bar <- theta*(nu); stop when the fills are stationary
-        fin = evaluate(bk, nu, eps_t, want_trades=True)
-        evals += 1
+        fin = G(nu, want_trades=True)
+        exact = G(nu, 0.0)
+        gap_now = (exact["g"] - float(np.dot(util.c, fin["psi"]))) / max(abs(exact["g"]), 1e-300)
+        if verbose:
+            print(f"outer={outer} eps={eps_t:.1e} last move={move:.3e} gap={gap_now:.3e}")
+        if inner_status == "optimal" and err <= tol and abs(gap_now) <= tol:
+            break
         move = 0.0
         for g in sum_groups:
             th = fin["lam"][g["off"]]                     # Lambda_b IS the fill of the order paying b
             move = max(move, float(np.max(np.abs(th - g["theta_bar"]) / g["R"])))
             g["theta_bar"] = th.copy()
-        if verbose:
-            print(f"outer={outer} multiplier move={move:.3e}")
-        if move <= tol and inner_status == "optimal":
-            break
-    fin = evaluate(bk, nu, eps_t, want_trades=True)
-    exact = evaluate(bk, nu, 0.0)
-    evals += 2
-    gross = np.zeros(n)
-    np.add.at(gross, pools.tok_idx, fin["delta"] + fin["lam"])
-    flow_scale = np.maximum(gross, np.abs(util.a)) + 1e-300
-    flow_scale = np.maximum(flow_scale, 1e-9 * flow_scale.max())
-    primal, infeas = residuals(util, nu, fin["psi"], flow_scale)
-    dval = dual_value(util, nu, exact["arb"])
+        eps_t = max(eps_min, eps_t * eps_shrink)
+    fin = G(nu, want_trades=True)
+    exact = G(nu, 0.0)
+    dval = exact["g"]
+    primal, infeas = residuals(util, nu, fin["psi"], dval)
     gap = (dval - primal) / max(abs(dval), 1e-300)
     ptr = pools.pool_ptr
     deltas = [fin["delta"][ptr[i]:ptr[i + 1]].copy() for i in range(pools.m)]
