@@ -27,7 +27,7 @@ class CfmmError(RuntimeError):
 
 class Bucket(C.Structure):
     _fields_ = [
-        ("kind", C.c_int32), ("arity", C.c_int32), ("n_pools", C.c_int64),
+        ("kind", C.c_int32), ("arity", C.c_int32), ("n_pools", C.c_int64), ("stride", C.c_int64),
         ("reserves", C.c_void_p), ("tok_idx", C.c_void_p), ("gamma", C.c_void_p),
         ("weights", C.c_void_p), ("logrw", C.c_void_p), ("theta_bar", C.c_void_p),
     ]

@@ -141,7 +141,7 @@ __device__ __forceinline__ void sum_order(double Rb, double g, double na, double
 
 template <int KIND, typename Scatter, bool TRADES, bool HESS>
 __global__ void __launch_bounds__(kThreads)
-k_eval_pair(long long m, int n_tokens, const double* __restrict__ R, const int* __restrict__ idx,
+k_eval_pair(long long m, long long ld, int n_tokens, const double* __restrict__ R, const int* __restrict__ idx,
             const double* __restrict__ gamma, const double* __restrict__ thbar, double eps,
             const double* __restrict__ nu, double* psi, double* arb, double* delta, double* lambda,
             double* hcoef) {
@@ -151,8 +151,8 @@ k_eval_pair(long long m, int n_tokens, const double* __restrict__ R, const int* 
     double acc = 0.0;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
-        const double R0 = R[i], R1 = R[m + i], g = gamma[i];
-        const int i0 = idx[i], i1 = idx[m + i];
+        const double R0 = R[i], R1 = R[ld + i], g = gamma[i];
+        const int i0 = idx[i], i1 = idx[ld + i];
         const double n0 = __ldg(nu + i0), n1 = __ldg(nu + i1);
         double y0, y1, h;
         if (KIND == CFMM_KIND_PRODUCT) {
@@ -160,19 +160,19 @@ k_eval_pair(long long m, int n_tokens, const double* __restrict__ R, const int* 
         } else {
             // order A pays out token 1 (tender 0), order B pays out token 0 (tender 1)
             double thA, payA, hA, thB, payB, hB;
-            sum_order(R1, g, n0, n1, thbar ? thbar[m + i] : 0.0, eps, thA, payA, hA);
+            sum_order(R1, g, n0, n1, thbar ? thbar[ld + i] : 0.0, eps, thA, payA, hA);
             sum_order(R0, g, n1, n0, thbar ? thbar[i] : 0.0, eps, thB, payB, hB);
             y0 = thB - payA;
             y1 = thA - payB;
             h = hA + hB;
             if (TRADES) {
-                delta[i] = payA; delta[m + i] = payB;
-                lambda[i] = thB; lambda[m + i] = thA;
+                delta[i] = payA; delta[ld + i] = payB;
+                lambda[i] = thB; lambda[ld + i] = thA;
             }
         }
         if (TRADES && KIND == CFMM_KIND_PRODUCT) {
-            delta[i] = fmax(-y0, 0.0); delta[m + i] = fmax(-y1, 0.0);
-            lambda[i] = fmax(y0, 0.0); lambda[m + i] = fmax(y1, 0.0);
+            delta[i] = fmax(-y0, 0.0); delta[ld + i] = fmax(-y1, 0.0);
+            lambda[i] = fmax(y0, 0.0); lambda[ld + i] = fmax(y1, 0.0);
         }
         if (HESS) hcoef[i] = h;
         if (y0 != 0.0) sc.add(i0, y0);
@@ -184,6 +184,148 @@ k_eval_pair(long long m, int n_tokens, const double* __restrict__ R, const int* 
 }
 
 // ---------------------------------------------------------------------------------------------
+// TMA-staged variant of the 2-token kernel: persistent CTAs, each walking tiles of kTile pools.
+// One elected thread issues five 1-D bulk copies per tile (cp.async.bulk -> UBLKCP: R0, R1, gamma,
+// idx0, idx1 slabs, 32 B/pool) into a kStages-deep shared-memory ring; completion is signalled on
+// an mbarrier per stage (expect_tx), so kStages-1 tiles (~64 KB per CTA) are always in flight from
+// HBM regardless of occupancy.  A __syncthreads per tile hands the drained stage back to the
+// producer.  nu is gathered through L1 (n_tokens * 8 B stays cache resident).
+// ---------------------------------------------------------------------------------------------
+constexpr int kTile = 1024;          // pools per tile: 32 KB per stage
+constexpr int kStages = 3;
+constexpr int kTmaThreads = 512;
+constexpr int kPoolsPerThread = kTile / kTmaThreads;
+
+struct __align__(128) PairStage {
+    double R0[kTile];
+    double R1[kTile];
+    double g[kTile];
+    int i0[kTile];
+    int i1[kTile];
+};
+constexpr unsigned kStageBytes = sizeof(PairStage);
+static_assert(kStageBytes == 32u * kTile, "32 B per pool");
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void issue_pair_tile(PairStage* st, uint64_t* bar, long long tile, long long ld,
+                                                const double* R, const int* idx, const double* gamma) {
+    const long long o = tile * kTile;
+    mbar_expect_tx(bar, kStageBytes);
+    bulk_g2s(st->R0, R + o, kTile * 8, bar);
+    bulk_g2s(st->R1, R + ld + o, kTile * 8, bar);
+    bulk_g2s(st->g, gamma + o, kTile * 8, bar);
+    bulk_g2s(st->i0, idx + o, kTile * 4, bar);
+    bulk_g2s(st->i1, idx + ld + o, kTile * 4, bar);
+}
+
+template <int KIND, bool TRADES, bool HESS, bool SCATTER = true>
+__global__ void __launch_bounds__(kTmaThreads, 2)
+k_eval_pair_tma(long long m, long long ld, int n_tokens, const double* __restrict__ R, const int* __restrict__ idx,
+                const double* __restrict__ gamma, const double* __restrict__ thbar, double eps,
+                const double* __restrict__ nu, double* psi, double* arb, double* delta, double* lambda,
+                double* hcoef) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    PairStage* stages = reinterpret_cast<PairStage*>(smem_raw);
+    __shared__ uint64_t full[kStages];
+    __shared__ double part[kTmaThreads / 32];
+    const int tid = threadIdx.x;
+    const long long ntiles = (m + kTile - 1) / kTile;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
+            if (t < ntiles) issue_pair_tile(&stages[s], &full[s], t, ld, R, idx, gamma);
+        }
+    }
+    double acc = 0.0;
+    int stage = 0;
+    unsigned parity = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        mbar_wait(&full[stage], parity);
+        const PairStage& S = stages[stage];
+#pragma unroll
+        for (int u = 0; u < kPoolsPerThread; ++u) {
+            const int l = tid + u * kTmaThreads;
+            const long long i = tile * kTile + l;
+            if (i < m) {
+                const double R0 = S.R0[l], R1 = S.R1[l], g = S.g[l];
+                const int i0 = S.i0[l], i1 = S.i1[l];
+                const double n0 = __ldg(nu + i0), n1 = __ldg(nu + i1);
+                double y0, y1, h;
+                if (KIND == CFMM_KIND_PRODUCT) {
+                    product_pool(R0, R1, g, n0, n1, y0, y1, h);
+                    if (TRADES) {
+                        delta[i] = fmax(-y0, 0.0); delta[ld + i] = fmax(-y1, 0.0);
+                        lambda[i] = fmax(y0, 0.0); lambda[ld + i] = fmax(y1, 0.0);
+                    }
+                } else {
+                    double thA, payA, hA, thB, payB, hB;
+                    sum_order(R1, g, n0, n1, thbar ? thbar[ld + i] : 0.0, eps, thA, payA, hA);
+                    sum_order(R0, g, n1, n0, thbar ? thbar[i] : 0.0, eps, thB, payB, hB);
+                    y0 = thB - payA;
+                    y1 = thA - payB;
+                    h = hA + hB;
+                    if (TRADES) {
+                        delta[i] = payA; delta[ld + i] = payB;
+                        lambda[i] = thB; lambda[ld + i] = thA;
+                    }
+                }
+                if (HESS) hcoef[i] = h;
+                if (SCATTER) {
+                    if (y0 != 0.0) atomicAdd(psi + i0, y0);
+                    if (y1 != 0.0) atomicAdd(psi + i1, y1);
+                }
+                acc += n0 * y0 + n1 * y1;
+            }
+        }
+        __syncthreads();                      // every thread is done reading this stage
+        if (tid == 0) {
+            const long long nxt = tile + (long long)kStages * gridDim.x;
+            if (nxt < ntiles) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue_pair_tile(&stages[stage], &full[stage], nxt, ld, R, idx, gamma);
+            }
+        }
+        if (++stage == kStages) { stage = 0; parity ^= 1u; }
+    }
+    acc = warp_sum(acc);
+    if ((tid & 31) == 0) part[tid >> 5] = acc;
+    __syncthreads();
+    if (tid < 32) {
+        double s = (tid < kTmaThreads / 32) ? part[tid] : 0.0;
+        s = warp_sum(s);
+        if (tid == 0 && s != 0.0) atomicAdd(arb, s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // weighted geometric mean, arity K (arbitrage.py:65).  One thread per pool.
 //   tB_j = log(R_j/w_j) + log nu_j,  tA_j = tB_j - log gamma
 //   h(s) = sum_j w_j [max(s - tA_j, 0) + min(s - tB_j, 0)]  is piecewise linear, nondecreasing;
@@ -192,7 +334,7 @@ k_eval_pair(long long m, int n_tokens, const double* __restrict__ R, const int* 
 // ---------------------------------------------------------------------------------------------
 template <int K, typename Scatter, bool TRADES, bool HESS>
 __global__ void __launch_bounds__(kThreads)
-k_eval_geomean(long long m, int karity, int n_tokens, const double* __restrict__ R, const int* __restrict__ idx,
+k_eval_geomean(long long m, long long ld, int karity, int n_tokens, const double* __restrict__ R, const int* __restrict__ idx,
                const double* __restrict__ gamma, const double* __restrict__ W, const double* __restrict__ logrw,
                const double* __restrict__ nu, const double* __restrict__ lognu, double* psi, double* arb,
                double* delta, double* lambda, double* hcoef, uint32_t* hmask) {
@@ -212,9 +354,9 @@ k_eval_geomean(long long m, int karity, int n_tokens, const double* __restrict__
 #pragma unroll
         for (int j = 0; j < KMAX; ++j) {
             if (j < k) {
-                id[j] = idx[(long long)j * m + i];
-                w[j] = W[(long long)j * m + i];
-                tB[j] = logrw[(long long)j * m + i] + __ldg(lognu + id[j]);
+                id[j] = idx[(long long)j * ld + i];
+                w[j] = W[(long long)j * ld + i];
+                tB[j] = logrw[(long long)j * ld + i] + __ldg(lognu + id[j]);
                 maxB = fmax(maxB, tB[j]);
                 minA = fmin(minA, tB[j] - lg);
             }
@@ -247,12 +389,12 @@ k_eval_geomean(long long m, int karity, int n_tokens, const double* __restrict__
                 const double z = (zA > 0.0) ? zA : zB;
                 double y = 0.0;
                 if (z != 0.0 || TRADES) {
-                    const double Rj = R[(long long)j * m + i];
+                    const double Rj = R[(long long)j * ld + i];
                     const double e = expm1(z);
                     const double D = (zA > 0.0) ? Rj * e / g : 0.0;
                     const double L = (zB < 0.0) ? -Rj * e : 0.0;
                     y = L - D;
-                    if (TRADES) { delta[(long long)j * m + i] = D; lambda[(long long)j * m + i] = L; }
+                    if (TRADES) { delta[(long long)j * ld + i] = D; lambda[(long long)j * ld + i] = L; }
                 }
                 if (z != 0.0) {
                     mask |= 1u << j;
@@ -274,7 +416,7 @@ k_eval_geomean(long long m, int karity, int n_tokens, const double* __restrict__
 // ---------------------------------------------------------------------------------------------
 template <typename Scatter>
 __global__ void __launch_bounds__(kThreads)
-k_hvp_pair(long long m, int n_tokens, const int* __restrict__ idx, const double* __restrict__ hcoef,
+k_hvp_pair(long long m, long long ld, int n_tokens, const int* __restrict__ idx, const double* __restrict__ hcoef,
            const double* __restrict__ vt, double* y) {
     extern __shared__ double smem[];
     Scatter sc{y};
@@ -283,7 +425,7 @@ k_hvp_pair(long long m, int n_tokens, const int* __restrict__ idx, const double*
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
         const double h = hcoef[i];
         if (h != 0.0) {
-            const int i0 = idx[i], i1 = idx[m + i];
+            const int i0 = idx[i], i1 = idx[ld + i];
             const double c = h * (__ldg(vt + i0) - __ldg(vt + i1));
             sc.add(i0, c);
             sc.add(i1, -c);
@@ -294,7 +436,7 @@ k_hvp_pair(long long m, int n_tokens, const int* __restrict__ idx, const double*
 
 template <typename Scatter>
 __global__ void __launch_bounds__(kThreads)
-k_hvp_geomean(long long m, int k, int n_tokens, const int* __restrict__ idx, const double* __restrict__ W,
+k_hvp_geomean(long long m, long long ld, int k, int n_tokens, const int* __restrict__ idx, const double* __restrict__ W,
               const double* __restrict__ hcoef, const uint32_t* __restrict__ hmask,
               const double* __restrict__ vt, double* y) {
     extern __shared__ double smem[];
@@ -308,15 +450,15 @@ k_hvp_geomean(long long m, int k, int n_tokens, const int* __restrict__ idx, con
             double Wa = 0.0, wv = 0.0;
             for (int j = 0; j < k; ++j)
                 if (mask >> j & 1u) {
-                    const double wj = W[(long long)j * m + i];
+                    const double wj = W[(long long)j * ld + i];
                     Wa += wj;
-                    wv += wj * __ldg(vt + idx[(long long)j * m + i]);
+                    wv += wj * __ldg(vt + idx[(long long)j * ld + i]);
                 }
             const double tbar = wv / Wa;
             for (int j = 0; j < k; ++j)
                 if (mask >> j & 1u) {
-                    const int t = idx[(long long)j * m + i];
-                    sc.add(t, M * W[(long long)j * m + i] * (__ldg(vt + t) - tbar));
+                    const int t = idx[(long long)j * ld + i];
+                    sc.add(t, M * W[(long long)j * ld + i] * (__ldg(vt + t) - tbar));
                 }
         }
     }
@@ -324,16 +466,16 @@ k_hvp_geomean(long long m, int k, int n_tokens, const int* __restrict__ idx, con
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_diag_pair(long long m, const int* __restrict__ idx, const double* __restrict__ hcoef, double* diag) {
+k_diag_pair(long long m, long long ld, const int* __restrict__ idx, const double* __restrict__ hcoef, double* diag) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
         const double h = hcoef[i];
-        if (h != 0.0) { atomicAdd(diag + idx[i], h); atomicAdd(diag + idx[m + i], h); }
+        if (h != 0.0) { atomicAdd(diag + idx[i], h); atomicAdd(diag + idx[ld + i], h); }
     }
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_diag_geomean(long long m, int k, const int* __restrict__ idx, const double* __restrict__ W,
+k_diag_geomean(long long m, long long ld, int k, const int* __restrict__ idx, const double* __restrict__ W,
                const double* __restrict__ hcoef, const uint32_t* __restrict__ hmask, double* diag) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
@@ -342,23 +484,23 @@ k_diag_geomean(long long m, int k, const int* __restrict__ idx, const double* __
         if (M != 0.0 && mask) {
             double Wa = 0.0;
             for (int j = 0; j < k; ++j)
-                if (mask >> j & 1u) Wa += W[(long long)j * m + i];
+                if (mask >> j & 1u) Wa += W[(long long)j * ld + i];
             for (int j = 0; j < k; ++j)
                 if (mask >> j & 1u) {
-                    const double wj = W[(long long)j * m + i];
-                    atomicAdd(diag + idx[(long long)j * m + i], M * wj * (1.0 - wj / Wa));
+                    const double wj = W[(long long)j * ld + i];
+                    atomicAdd(diag + idx[(long long)j * ld + i], M * wj * (1.0 - wj / Wa));
                 }
         }
     }
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_dense_pair(long long m, int n, const int* __restrict__ idx, const double* __restrict__ hcoef, double* H) {
+k_dense_pair(long long m, long long ld, int n, const int* __restrict__ idx, const double* __restrict__ hcoef, double* H) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
         const double h = hcoef[i];
         if (h != 0.0) {
-            const long long a = idx[i], b = idx[m + i];
+            const long long a = idx[i], b = idx[ld + i];
             atomicAdd(H + a * n + a, h); atomicAdd(H + b * n + b, h);
             atomicAdd(H + a * n + b, -h); atomicAdd(H + b * n + a, -h);
         }
@@ -366,7 +508,7 @@ k_dense_pair(long long m, int n, const int* __restrict__ idx, const double* __re
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_dense_geomean(long long m, int k, int n, const int* __restrict__ idx, const double* __restrict__ W,
+k_dense_geomean(long long m, long long ld, int k, int n, const int* __restrict__ idx, const double* __restrict__ W,
                 const double* __restrict__ hcoef, const uint32_t* __restrict__ hmask, double* H) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
@@ -375,15 +517,15 @@ k_dense_geomean(long long m, int k, int n, const int* __restrict__ idx, const do
         if (M != 0.0 && mask) {
             double Wa = 0.0;
             for (int j = 0; j < k; ++j)
-                if (mask >> j & 1u) Wa += W[(long long)j * m + i];
+                if (mask >> j & 1u) Wa += W[(long long)j * ld + i];
             for (int j = 0; j < k; ++j) {
                 if (!(mask >> j & 1u)) continue;
-                const double wj = W[(long long)j * m + i];
-                const long long tj = idx[(long long)j * m + i];
+                const double wj = W[(long long)j * ld + i];
+                const long long tj = idx[(long long)j * ld + i];
                 for (int l = 0; l < k; ++l) {
                     if (!(mask >> l & 1u)) continue;
-                    const double wl = W[(long long)l * m + i];
-                    const long long tl = idx[(long long)l * m + i];
+                    const double wl = W[(long long)l * ld + i];
+                    const long long tl = idx[(long long)l * ld + i];
                     atomicAdd(H + tj * n + tl, M * ((j == l ? wj : 0.0) - wj * wl / Wa));
                 }
             }
@@ -392,11 +534,12 @@ k_dense_geomean(long long m, int k, int n, const int* __restrict__ idx, const do
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_sum_update(long long m, const double* __restrict__ R, const double* __restrict__ lambda,
+k_sum_update(long long m, long long ld, const double* __restrict__ R, const double* __restrict__ lambda,
              double* thbar, double* move) {
     double mx = 0.0;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * m; i += stride) {
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < 2 * m; q += stride) {
+        const long long i = (q < m) ? q : ld + (q - m);
         const double th = lambda[i];
         mx = fmax(mx, fabs(th - thbar[i]) / R[i]);
         thbar[i] = th;
@@ -419,7 +562,7 @@ inline int grid_for(long long m, int blocks_per_sm) {
 }
 
 inline bool use_shared(int n_tokens, long long m) {
-    if (g_scatter_mode == 1) return false;
+    if (g_scatter_mode == 1 || g_scatter_mode == 3) return false;
     const bool fits = (size_t)n_tokens * sizeof(double) <= 96 * 1024;
     if (g_scatter_mode == 2) return fits;
     // auto: privatise only when each CTA makes many more contributions than it has bins to flush
@@ -431,6 +574,11 @@ inline void allow_smem(K kernel, size_t bytes) {
     if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+inline bool tma_ok(const cfmm_bucket* b) {
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    return (b->stride % kTile) == 0 && al(b->reserves) && al(b->tok_idx) && al(b->gamma);
+}
+
 template <int KIND, bool TRADES, bool HESS>
 int launch_pair(const cfmm_bucket* b, int n_tokens, const double* nu, double eps, double* psi, double* arb,
                 const cfmm_eval_out* out, cudaStream_t st) {
@@ -438,15 +586,41 @@ int launch_pair(const cfmm_bucket* b, int n_tokens, const double* nu, double eps
     double* delta = out ? out->delta : nullptr;
     double* lambda = out ? out->lambda : nullptr;
     double* hcoef = out ? out->hcoef : nullptr;
+    if ((g_scatter_mode == 0 || g_scatter_mode == 3) && tma_ok(b)) {
+        auto kern = k_eval_pair_tma<KIND, TRADES, HESS>;
+        const size_t sm = (size_t)kStages * kStageBytes;
+        static bool attr_set = false;      // per instantiation
+        if (!attr_set) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            attr_set = true;
+        }
+        const long long ntiles = (m + kTile - 1) / kTile;
+        const long long cap = 2LL * num_sms();
+        const int grid = (int)(ntiles < cap ? ntiles : cap);
+        kern<<<grid, kTmaThreads, sm, st>>>(m, b->stride, n_tokens, b->reserves, b->tok_idx, b->gamma, b->theta_bar,
+                                            eps, nu, psi, arb, delta, lambda, hcoef);
+        return check_launch();
+    }
+    if (g_scatter_mode == 4 && tma_ok(b) && KIND == CFMM_KIND_PRODUCT && !TRADES && !HESS) {
+        // MEASUREMENT ONLY: the same kernel without the psi scatter (wrong results; bounds the atomics' cost)
+        auto kern = k_eval_pair_tma<CFMM_KIND_PRODUCT, false, false, false>;
+        const size_t sm = (size_t)kStages * kStageBytes;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        const long long ntiles = (m + kTile - 1) / kTile;
+        const long long cap = 2LL * num_sms();
+        kern<<<(int)(ntiles < cap ? ntiles : cap), kTmaThreads, sm, st>>>(
+            m, b->stride, n_tokens, b->reserves, b->tok_idx, b->gamma, b->theta_bar, eps, nu, psi, arb, delta, lambda, hcoef);
+        return check_launch();
+    }
     if (use_shared(n_tokens, m)) {
         const size_t sm = (size_t)n_tokens * sizeof(double);
         auto kern = k_eval_pair<KIND, SharedScatter, TRADES, HESS>;
         allow_smem(kern, sm);
-        kern<<<grid_for(m, 2), kThreads, sm, st>>>(m, n_tokens, b->reserves, b->tok_idx, b->gamma, b->theta_bar,
+        kern<<<grid_for(m, 2), kThreads, sm, st>>>(m, b->stride, n_tokens, b->reserves, b->tok_idx, b->gamma, b->theta_bar,
                                                     eps, nu, psi, arb, delta, lambda, hcoef);
     } else {
         k_eval_pair<KIND, GlobalScatter, TRADES, HESS><<<grid_for(m, 8), kThreads, 0, st>>>(
-            m, n_tokens, b->reserves, b->tok_idx, b->gamma, b->theta_bar, eps, nu, psi, arb, delta, lambda, hcoef);
+            m, b->stride, n_tokens, b->reserves, b->tok_idx, b->gamma, b->theta_bar, eps, nu, psi, arb, delta, lambda, hcoef);
     }
     return check_launch();
 }
@@ -474,12 +648,12 @@ int launch_geomean(const cfmm_bucket* b, int n_tokens, const double* nu, const d
         const size_t sm = (size_t)n_tokens * sizeof(double);
         auto kern = k_eval_geomean<K, SharedScatter, TRADES, HESS>;
         allow_smem(kern, sm);
-        kern<<<grid_for(m, 2), kThreads, sm, st>>>(m, b->arity, n_tokens, b->reserves, b->tok_idx, b->gamma,
+        kern<<<grid_for(m, 2), kThreads, sm, st>>>(m, b->stride, b->arity, n_tokens, b->reserves, b->tok_idx, b->gamma,
                                                     b->weights, b->logrw, nu, lognu, psi, arb, delta, lambda,
                                                     hcoef, hmask);
     } else {
         k_eval_geomean<K, GlobalScatter, TRADES, HESS><<<grid_for(m, 4), kThreads, 0, st>>>(
-            m, b->arity, n_tokens, b->reserves, b->tok_idx, b->gamma, b->weights, b->logrw, nu, lognu, psi, arb,
+            m, b->stride, b->arity, n_tokens, b->reserves, b->tok_idx, b->gamma, b->weights, b->logrw, nu, lognu, psi, arb,
             delta, lambda, hcoef, hmask);
     }
     return check_launch();
@@ -498,7 +672,7 @@ int dispatch_geomean_flags(const cfmm_bucket* b, int n_tokens, const double* nu,
 
 int validate(const cfmm_bucket* b, int n_tokens) {
     if (!b) return CFMM_E_NULL;
-    if (b->n_pools < 0 || n_tokens <= 0) return CFMM_E_SIZE;
+    if (b->n_pools < 0 || n_tokens <= 0 || b->stride < b->n_pools) return CFMM_E_SIZE;
     if (b->n_pools > 0 && (!b->reserves || !b->tok_idx || !b->gamma)) return CFMM_E_NULL;
     switch (b->kind) {
         case CFMM_KIND_PRODUCT:
@@ -564,18 +738,18 @@ int cfmm_hvp(const cfmm_bucket* b, int32_t n_tokens, const double* hcoef, const 
         if (!hmask) return CFMM_E_NULL;
         if (sh) {
             allow_smem(k_hvp_geomean<SharedScatter>, sm);
-            k_hvp_geomean<SharedScatter><<<grid_for(m, 2), kThreads, sm, st>>>(m, b->arity, n_tokens, b->tok_idx,
+            k_hvp_geomean<SharedScatter><<<grid_for(m, 2), kThreads, sm, st>>>(m, b->stride, b->arity, n_tokens, b->tok_idx,
                                                                                b->weights, hcoef, hmask, vt, y);
         } else {
-            k_hvp_geomean<GlobalScatter><<<grid_for(m, 8), kThreads, 0, st>>>(m, b->arity, n_tokens, b->tok_idx,
+            k_hvp_geomean<GlobalScatter><<<grid_for(m, 8), kThreads, 0, st>>>(m, b->stride, b->arity, n_tokens, b->tok_idx,
                                                                               b->weights, hcoef, hmask, vt, y);
         }
     } else {
         if (sh) {
             allow_smem(k_hvp_pair<SharedScatter>, sm);
-            k_hvp_pair<SharedScatter><<<grid_for(m, 2), kThreads, sm, st>>>(m, n_tokens, b->tok_idx, hcoef, vt, y);
+            k_hvp_pair<SharedScatter><<<grid_for(m, 2), kThreads, sm, st>>>(m, b->stride, n_tokens, b->tok_idx, hcoef, vt, y);
         } else {
-            k_hvp_pair<GlobalScatter><<<grid_for(m, 8), kThreads, 0, st>>>(m, n_tokens, b->tok_idx, hcoef, vt, y);
+            k_hvp_pair<GlobalScatter><<<grid_for(m, 8), kThreads, 0, st>>>(m, b->stride, n_tokens, b->tok_idx, hcoef, vt, y);
         }
     }
     return check_launch();
@@ -591,9 +765,9 @@ int cfmm_hess_diag(const cfmm_bucket* b, int32_t n_tokens, const double* hcoef, 
     const long long m = b->n_pools;
     if (b->kind == CFMM_KIND_GEOMEAN) {
         if (!hmask) return CFMM_E_NULL;
-        k_diag_geomean<<<grid_for(m, 8), kThreads, 0, st>>>(m, b->arity, b->tok_idx, b->weights, hcoef, hmask, diag);
+        k_diag_geomean<<<grid_for(m, 8), kThreads, 0, st>>>(m, b->stride, b->arity, b->tok_idx, b->weights, hcoef, hmask, diag);
     } else {
-        k_diag_pair<<<grid_for(m, 8), kThreads, 0, st>>>(m, b->tok_idx, hcoef, diag);
+        k_diag_pair<<<grid_for(m, 8), kThreads, 0, st>>>(m, b->stride, b->tok_idx, hcoef, diag);
     }
     return check_launch();
 }
@@ -608,10 +782,10 @@ int cfmm_hess_dense(const cfmm_bucket* b, int32_t n_tokens, const double* hcoef,
     const long long m = b->n_pools;
     if (b->kind == CFMM_KIND_GEOMEAN) {
         if (!hmask) return CFMM_E_NULL;
-        k_dense_geomean<<<grid_for(m, 8), kThreads, 0, st>>>(m, b->arity, n_tokens, b->tok_idx, b->weights, hcoef,
+        k_dense_geomean<<<grid_for(m, 8), kThreads, 0, st>>>(m, b->stride, b->arity, n_tokens, b->tok_idx, b->weights, hcoef,
                                                               hmask, H);
     } else {
-        k_dense_pair<<<grid_for(m, 8), kThreads, 0, st>>>(m, n_tokens, b->tok_idx, hcoef, H);
+        k_dense_pair<<<grid_for(m, 8), kThreads, 0, st>>>(m, b->stride, n_tokens, b->tok_idx, hcoef, H);
     }
     return check_launch();
 }
@@ -624,7 +798,7 @@ int cfmm_sum_update_multipliers(const cfmm_bucket* b, const double* lambda, doub
     if (b->n_pools == 0) return CFMM_OK;
     if (!lambda || !theta_bar_out || !move || !b->reserves) return CFMM_E_NULL;
     k_sum_update<<<grid_for(2 * b->n_pools, 8), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        b->n_pools, b->reserves, lambda, theta_bar_out, move);
+        b->n_pools, b->stride, b->reserves, lambda, theta_bar_out, move);
     return check_launch();
 }
 
@@ -637,7 +811,7 @@ int cfmm_zero(void* ptr, int64_t bytes, void* stream) {
 }
 
 int cfmm_set_scatter_mode(int32_t mode) {
-    if (mode < 0 || mode > 2) return CFMM_E_KIND;
+    if (mode < 0 || mode > 4) return CFMM_E_KIND;
     g_scatter_mode = mode;
     return CFMM_OK;
 }

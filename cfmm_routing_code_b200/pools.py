@@ -116,27 +116,40 @@ def split_buckets(hp: HostPools, rank: int = 0, world: int = 1):
     return out
 
 
+TILE = 1024     # pools per TMA tile (csrc kTile): slot stride is padded to a multiple of it
+
+
+def _padded(arr2d: np.ndarray, stride: int, fill) -> np.ndarray:
+    k, m = arr2d.shape
+    out = np.full((k, stride), fill, dtype=arr2d.dtype)
+    out[:, :m] = arr2d
+    return out
+
+
 class DeviceBucket:
     def __init__(self, hp: HostPools, spec, device):
         self.kind = spec["kind"]; self.arity = spec["arity"]
         self.sel = spec["sel"]; self.off = spec["off"]
         self.m = int(len(self.sel))
+        self.stride = max(TILE, -(-self.m // TILE) * TILE)
         f64 = dict(dtype=torch.float64, device=device)
         R = hp.reserves[self.off]
-        self.reserves = torch.as_tensor(np.ascontiguousarray(R), **f64)
-        self.tok_idx = torch.as_tensor(np.ascontiguousarray(hp.tok_idx[self.off]), dtype=torch.int32, device=device)
-        self.gamma = torch.as_tensor(np.ascontiguousarray(hp.gamma[self.sel]), **f64)
+        self.reserves = torch.as_tensor(_padded(R, self.stride, 1.0), **f64)
+        self.tok_idx = torch.as_tensor(_padded(hp.tok_idx[self.off].astype(np.int32), self.stride, 0),
+                                       dtype=torch.int32, device=device)
+        self.gamma = torch.as_tensor(_padded(hp.gamma[self.sel][None, :], self.stride, 1.0)[0], **f64)
         self.weights = self.logrw = self.theta_bar = None
         if self.kind == _lib.KIND_GEOMEAN:
             W = hp.weights[self.off]
-            self.weights = torch.as_tensor(np.ascontiguousarray(W), **f64)
-            self.logrw = torch.as_tensor(np.ascontiguousarray(np.log(R / W)), **f64)
+            self.weights = torch.as_tensor(_padded(W, self.stride, 1.0), **f64)
+            self.logrw = torch.as_tensor(_padded(np.log(R / W), self.stride, 0.0), **f64)
         if self.kind == _lib.KIND_SUM:
-            self.theta_bar = torch.zeros((2, self.m), **f64)
+            self.theta_bar = torch.zeros((2, self.stride), **f64)
         self.delta = self.lam = self.hcoef = self.hmask = None
         self._device = device
         self.c_bucket = _lib.Bucket(
-            self.kind, self.arity, self.m, self.reserves.data_ptr(), self.tok_idx.data_ptr(), self.gamma.data_ptr(),
+            self.kind, self.arity, self.m, self.stride, self.reserves.data_ptr(), self.tok_idx.data_ptr(),
+            self.gamma.data_ptr(),
             self.weights.data_ptr() if self.weights is not None else None,
             self.logrw.data_ptr() if self.logrw is not None else None,
             self.theta_bar.data_ptr() if self.theta_bar is not None else None)
@@ -151,11 +164,11 @@ class DeviceBucket:
     def out_struct(self, trades: bool, hess: bool):
         f64 = dict(dtype=torch.float64, device=self._device)
         if trades and self.delta is None:
-            self.delta = torch.empty((self.arity, self.m), **f64)
-            self.lam = torch.empty((self.arity, self.m), **f64)
+            self.delta = torch.zeros((self.arity, self.stride), **f64)
+            self.lam = torch.zeros((self.arity, self.stride), **f64)
         if hess and self.hcoef is None:
-            self.hcoef = torch.empty(self.m, **f64)
-            self.hmask = torch.empty(self.m, dtype=torch.int32, device=self._device)
+            self.hcoef = torch.zeros(self.stride, **f64)
+            self.hmask = torch.zeros(self.stride, dtype=torch.int32, device=self._device)
         return _lib.EvalOut(self.delta.data_ptr() if trades else None, self.lam.data_ptr() if trades else None,
                             self.hcoef.data_ptr() if hess else None, self.hmask.data_ptr() if hess else None)
 
@@ -267,6 +280,6 @@ class PoolStore:
         for b in self.buckets:
             if b.m == 0:
                 continue
-            delta[b.off.ravel()] = b.delta.cpu().numpy().ravel()
-            lam[b.off.ravel()] = b.lam.cpu().numpy().ravel()
+            delta[b.off.ravel()] = b.delta[:, :b.m].cpu().numpy().ravel()
+            lam[b.off.ravel()] = b.lam[:, :b.m].cpu().numpy().ravel()
         return delta, lam

@@ -7,7 +7,8 @@
  * every call is asynchronous on `stream` (a cudaStream_t passed as void*), capturable in a CUDA
  * graph, and returns 0 or a negative CFMM_E_* code.  No host threads, no CPU fallback.
  *
- * Pool storage ("bucket"): pools of one kind and one arity k, slot-major SoA, n_pools long:
+ * Pool storage ("bucket"): pools of one kind and one arity k, slot-major SoA, n_pools long, slot j of
+ * pool i at [j*stride + i] (per-pool outputs delta/lambda use the same stride):
  *   reserves[k][n_pools]  f64   R_i            arbitrage.py:14-20  (reserves)
  *   tok_idx [k][n_pools]  i32   local_indices  arbitrage.py:6-12   (replaces dense A_i, :42-48)
  *   gamma   [n_pools]     f64   fees[i]        arbitrage.py:22-28
@@ -44,6 +45,8 @@ typedef struct cfmm_bucket {
     int32_t kind;          /* CFMM_KIND_*                                                */
     int32_t arity;         /* tokens per pool: 2 for PRODUCT and SUM, 2..32 for GEOMEAN  */
     int64_t n_pools;
+    int64_t stride;        /* elements between consecutive slots (>= n_pools); the TMA-staged path needs
+                              stride % 1024 == 0 and 16-byte aligned arrays, otherwise the LDG path runs */
     const double* reserves;
     const int32_t* tok_idx;
     const double* gamma;
@@ -93,8 +96,8 @@ int cfmm_sum_update_multipliers(const cfmm_bucket* bucket, const double* lambda,
 /* cudaMemsetAsync(ptr, 0, bytes) on the stream -- lets a host language zero psi/arb without torch. */
 int cfmm_zero(void* ptr, int64_t bytes, void* stream);
 
-/* Tuning knob for experiments (scatter mode: 0 = auto, 1 = global red.add, 2 = shared-memory
- * privatised histogram).  Not part of the reference-facing surface. */
+/* Tuning knob for experiments (0 = auto: TMA-staged kernel when the layout allows; 1 = LDG kernel +
+ * global red.add; 2 = LDG kernel + shared-memory privatised histogram; 3 = TMA-staged kernel).  Not part of the reference-facing surface. */
 int cfmm_set_scatter_mode(int32_t mode);
 
 /* Introspection: number of kernel launches issued by this library since load / last reset. */

@@ -23,7 +23,7 @@ nus = [torch.as_tensor(s["prices"] * np.exp(0.01 * np.random.default_rng(k).stan
 lib = stores[0][0].lib
 
 
-def timeit(fn, iters=40, warm=5):
+def timeit(fn, iters=200, warm=16):
     for i in range(warm):
         fn(i)
     torch.cuda.synchronize()
@@ -36,7 +36,7 @@ def timeit(fn, iters=40, warm=5):
     return e0.elapsed_time(e1) / iters * 1e-3
 
 
-for mode in (1, 2):
+for mode in (1, 3, 4):
     lib.cfmm_set_scatter_mode(mode)
     for label, kw in (("eval", {}), ("eval+hess", dict(hess=True)), ("eval+trades", dict(trades=True))):
         t_rot = timeit(lambda i: stores[i % ninst][0].evaluate(nus[i % ninst], **kw))

@@ -31,7 +31,7 @@ def _check_eval(hp, nu, eps=0.0, theta=None, scatter_mode=0):
         if theta is not None:
             for b in st.buckets:
                 if b.kind == _lib.KIND_SUM:
-                    b.theta_bar.copy_(torch.as_tensor(theta[b.off], **F64))
+                    b.theta_bar[:, :b.m].copy_(torch.as_tensor(theta[b.off], **F64))
         acc = st.evaluate(torch.as_tensor(nu, **F64), eps, trades=True, hess=True).cpu().numpy()
         d, l = st.gather_trades()
     finally:
@@ -49,7 +49,7 @@ def _check_eval(hp, nu, eps=0.0, theta=None, scatter_mode=0):
     return st, ref
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_product_eval_matches_oracle(mode):
     hp, s = H.cp_host_pools(20_000, 97, seed=11)
     _check_eval(hp, H.random_prices(s["prices"], 1), scatter_mode=mode)
@@ -187,14 +187,16 @@ def test_full_size_solve_reaches_1e6_gap():
 
 def test_error_codes_and_empty_bucket():
     lib = _lib.load()
-    b = _lib.Bucket(_lib.KIND_PRODUCT, 2, 10, None, None, None, None, None, None)
+    b = _lib.Bucket(_lib.KIND_PRODUCT, 2, 10, 10, None, None, None, None, None, None)
     assert lib.cfmm_arb_eval(C.byref(b), 4, None, None, 0.0, None, None, None, None) == -1
     x = torch.zeros(8, **F64)
-    b = _lib.Bucket(7, 2, 0, x.data_ptr(), x.data_ptr(), x.data_ptr(), None, None, None)
+    b = _lib.Bucket(7, 2, 0, 0, x.data_ptr(), x.data_ptr(), x.data_ptr(), None, None, None)
     assert lib.cfmm_arb_eval(C.byref(b), 4, x.data_ptr(), None, 0.0, x.data_ptr(), x.data_ptr(), None, None) == -2
-    b = _lib.Bucket(_lib.KIND_SUM, 3, 1, x.data_ptr(), x.data_ptr(), x.data_ptr(), None, None, None)
+    b = _lib.Bucket(_lib.KIND_SUM, 3, 1, 1, x.data_ptr(), x.data_ptr(), x.data_ptr(), None, None, None)
     assert lib.cfmm_arb_eval(C.byref(b), 4, x.data_ptr(), None, 0.0, x.data_ptr(), x.data_ptr(), None, None) == -2
-    b = _lib.Bucket(_lib.KIND_PRODUCT, 2, 0, None, None, None, None, None, None)     # empty: a no-op
+    b = _lib.Bucket(_lib.KIND_PRODUCT, 2, 4, 2, x.data_ptr(), x.data_ptr(), x.data_ptr(), None, None, None)
+    assert lib.cfmm_arb_eval(C.byref(b), 4, x.data_ptr(), None, 0.0, x.data_ptr(), x.data_ptr(), None, None) == -3
+    b = _lib.Bucket(_lib.KIND_PRODUCT, 2, 0, 0, None, None, None, None, None, None)     # empty: a no-op
     assert lib.cfmm_arb_eval(C.byref(b), 4, x.data_ptr(), None, 0.0, x.data_ptr(), x.data_ptr(), None, None) == 0
     with pytest.raises(ValueError):
         cf.HostPools.from_lists(3, [[0, 1, 2]], [[1, 1, 1]], [0.99], ["sum"])
