@@ -33,6 +33,14 @@ class Bucket(C.Structure):
     ]
 
 
+class BlockedPairs(C.Structure):
+    _fields_ = [
+        ("n_pools", C.c_int64), ("n_tiles", C.c_int64), ("pools_per_tile", C.c_int32), ("reserved", C.c_int32),
+        ("r0", C.c_void_p), ("r1", C.c_void_p), ("gamma_inv", C.c_void_p), ("lid", C.c_void_p),
+        ("ent", C.c_void_p), ("rows", C.c_void_p), ("tok", C.c_void_p), ("desc", C.c_void_p),
+    ]
+
+
 class EvalOut(C.Structure):
     _fields_ = [("delta", C.c_void_p), ("lambda_", C.c_void_p), ("hcoef", C.c_void_p), ("hmask", C.c_void_p)]
 
@@ -68,6 +76,14 @@ def load(build_if_missing: bool = True):
     lib.cfmm_hvp.argtypes = [C.POINTER(Bucket), i32, vp, vp, vp, vp, vp]
     lib.cfmm_hess_diag.argtypes = [C.POINTER(Bucket), i32, vp, vp, vp, vp]
     lib.cfmm_hess_dense.argtypes = [C.POINTER(Bucket), i32, vp, vp, vp, vp]
+    lib.cfmm_blocked_layout_info.argtypes = [C.POINTER(i32)] * 4
+    lib.cfmm_blocked_layout_info.restype = C.c_int
+    lib.cfmm_blocked_eval.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp, C.POINTER(EvalOut), vp]
+    lib.cfmm_blocked_eval.restype = C.c_int
+    lib.cfmm_blocked_hvp.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp, vp]
+    lib.cfmm_blocked_hvp.restype = C.c_int
+    lib.cfmm_blocked_diag.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp]
+    lib.cfmm_blocked_diag.restype = C.c_int
     lib.cfmm_sum_update_multipliers.argtypes = [C.POINTER(Bucket), vp, vp, vp, vp]
     lib.cfmm_sum_update_multipliers.restype = C.c_int
     lib.cfmm_zero.argtypes = [vp, i64, vp]

@@ -1,0 +1,287 @@
+// cfmm_blocked.cu -- token-blocked layout for 2-token pools: evaluation, Hessian-vector product and
+// Hessian diagonal WITHOUT per-pool atomics.
+//
+// Why: psi = sum_i A_i (L_i - D_i) (arbitrage.py:54) is a scatter of 2 values per pool into n_tokens bins.
+// With red.global.add.f64 per value the L2 atomic units bound the kernel at ~8x the HBM time (measured,
+// profiles/r1b_*).  The sparsity pattern (local_indices, arbitrage.py:6-12) is static across dual
+// iterations, so it is preprocessed once into tiles of P pools whose tokens fall in two narrow token blocks:
+//   * a tile touches few distinct tokens: nu is gathered once per tile into shared memory (nu_local) and the
+//     pools address it with 16-bit local ids (4 B/pool instead of 8 B of global indices);
+//   * each pool thread writes its two net flows to a shared-memory array f[2P] (no atomics);
+//   * "rows" = (token, <=32 entries of f) listed by a per-tile CSR are summed by one thread each, in a fixed
+//     order (bit-reproducible), and only the row totals go to global memory: ~0.25 red.add per pool instead of 2.
+// HBM bytes per pool: 3 x 8 (R0, R1, 1/gamma) + 4 (local ids) + 4 (row entries) + ~1-2 (row/token tables).
+// Pool slabs and the per-tile tables are staged through a shared-memory ring by 1-D bulk TMA copies
+// (cp.async.bulk + mbarrier), several tiles in flight per CTA.
+#include <math.h>
+
+#include "cfmm_dev.cuh"
+
+using namespace cfmm;
+
+namespace {
+
+template <int P>
+struct BlockedCfg {
+    // the layout builder guarantees <= P distinct tokens per tile (tiles that would exceed it go to the
+    // plain bucket), so rows <= P + 2P/32 (every token one row, plus one extra row per 32 entries)
+    static constexpr int kTokMax = P;
+    static constexpr int kRowsMax = P + 2 * P / 32 + 8;
+};
+
+// one ring stage: NF per-pool f64 slabs + local ids + row entries + row table + token list
+template <int P, int NF>
+struct __align__(128) Stage {
+    double a[NF][P];
+    uint32_t lid[P];                              // lid0 | lid1 << 16
+    uint16_t ent[2 * P];                          // row-ordered: local_pool << 1 | slot
+    uint32_t rows[BlockedCfg<P>::kRowsMax];       // start | local_token << 16 ; sentinel row closes the last one
+    int32_t tok[BlockedCfg<P>::kTokMax];          // local token id -> global token id
+};
+
+struct BlockedArgs {
+    long long n_tiles;
+    long long M;                  // n_tiles * P (padded pool count = slab stride)
+    const double* slab[3];        // NF slabs, each [M]
+    const uint32_t* lid;          // [M]
+    const uint16_t* ent;          // [n_tiles][2P]
+    const uint32_t* rows;         // [n_tiles][kRowsMax]
+    const int32_t* tok;           // [n_tiles][kTokMax]
+    const int2* desc;             // [n_tiles] (ntok, nrow)
+    const double* vec;            // nu (eval) or vt (hvp); unused for diag
+    double* out;                  // psi / y / diag  (+=)
+    double* arb;                  // eval only
+    double* delta;                // eval, optional: [2][M] blocked order
+    double* lambda;
+    double* hcoef;                // eval, optional: [M]
+};
+
+__device__ __forceinline__ unsigned round16(unsigned bytes) { return (bytes + 15u) & ~15u; }
+
+template <int P, int NF>
+__device__ __forceinline__ void issue_tile(Stage<P, NF>* st, uint64_t* bar, const BlockedArgs& A, long long tile) {
+    const int2 d = __ldg(A.desc + tile);
+    const unsigned rows_b = round16(4u * (unsigned)(d.y + 1));
+    const unsigned tok_b = round16(4u * (unsigned)d.x);
+    mbar_expect_tx(bar, (unsigned)(NF * P * 8 + P * 4 + 2 * P * 2) + rows_b + tok_b);
+#pragma unroll
+    for (int k = 0; k < NF; ++k) bulk_g2s(st->a[k], A.slab[k] + tile * P, P * 8, bar);
+    bulk_g2s(st->lid, A.lid + tile * P, P * 4, bar);
+    bulk_g2s(st->ent, A.ent + tile * (2 * P), 2 * P * 2, bar);
+    bulk_g2s(st->rows, A.rows + tile * BlockedCfg<P>::kRowsMax, rows_b, bar);
+    bulk_g2s(st->tok, A.tok + tile * BlockedCfg<P>::kTokMax, tok_b, bar);
+}
+
+// ---- per-pool operators: produce the two values (f0, f1) that the rows sum ----------------------
+// constant product with gi = 1/gamma (arbitrage.py:68-70): trade 0->1 iff nu1 R1 > nu0 R0 / gamma.
+//   v = rsqrt(num den gi); t = num v = sqrt(gamma num/den); 1/t = den gi v; h = sqrt(p0 p1 / gamma)/2 = w v / 2
+struct EvalOp {
+    static constexpr int NF = 3;
+    static constexpr bool kNeedsVec = true;
+    template <bool TRADES, bool HESS>
+    __device__ __forceinline__ static void apply(const BlockedArgs& A, long long q, double R0, double R1, double gi,
+                                                 double n0, double n1, double& f0, double& f1, double& acc) {
+        const double p0 = n0 * R0, p1 = n1 * R1;
+        const bool fwd = p1 > p0 * gi;
+        const bool bwd = p0 > p1 * gi;
+        f0 = 0.0; f1 = 0.0;
+        double h = 0.0;
+        if (fwd || bwd) {
+            const double num = fwd ? p1 : p0, den = fwd ? p0 : p1;
+            const double w = num * den * gi;
+            const double v = rsqrt(w);
+            const double t = num * v;
+            const double u = den * gi * v;
+            const double din = (fwd ? R0 : R1) * (t - 1.0) * gi;
+            const double lout = (fwd ? R1 : R0) * (1.0 - u);
+            f0 = fwd ? -din : lout;
+            f1 = fwd ? lout : -din;
+            h = 0.5 * w * v;
+            acc += n0 * f0 + n1 * f1;
+        }
+        if (TRADES) {
+            A.delta[q] = fmax(-f0, 0.0); A.delta[A.M + q] = fmax(-f1, 0.0);
+            A.lambda[q] = fmax(f0, 0.0); A.lambda[A.M + q] = fmax(f1, 0.0);
+        }
+        if (HESS) A.hcoef[q] = h;
+    }
+};
+
+template <int P, int THREADS, int STAGES, int MODE /*0 eval, 1 hvp, 2 diag*/, bool TRADES, bool HESS>
+__global__ void __launch_bounds__(THREADS)
+k_blocked(const BlockedArgs A) {
+    constexpr int NF = (MODE == 0) ? 3 : 1;
+    using St = Stage<P, NF>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    St* stages = reinterpret_cast<St*>(smem_raw);
+    double* nul = reinterpret_cast<double*>(smem_raw + (size_t)STAGES * sizeof(St));     // [P]  nu_local
+    double* f = nul + P;                                                                  // [2P] flows
+    __shared__ uint64_t full[STAGES];
+    __shared__ double part[THREADS / 32];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
+            if (t < A.n_tiles) issue_tile<P, NF>(&stages[s], &full[s], A, t);
+        }
+    }
+    double acc = 0.0;
+    int stage = 0;
+    unsigned parity = 0;
+    for (long long tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+        const int2 d = __ldg(A.desc + tile);           // (ntok, nrow)
+        mbar_wait(&full[stage], parity);
+        St& S = stages[stage];
+        // ---- phase 1: nu_local <- vec[tok]
+        if (MODE != 2) {
+            for (int t = tid; t < d.x; t += THREADS) nul[t] = __ldg(A.vec + S.tok[t]);
+            __syncthreads();
+        }
+        // ---- phase 2: per-pool values into f
+#pragma unroll
+        for (int l = tid; l < P; l += THREADS) {
+            const uint32_t li = S.lid[l];
+            double f0, f1;
+            if (MODE == 0) {
+                EvalOp::apply<TRADES, HESS>(A, tile * P + l, S.a[0][l], S.a[1][l], S.a[2][l], nul[li & 0xffffu],
+                                            nul[li >> 16], f0, f1, acc);
+            } else if (MODE == 1) {
+                f0 = S.a[0][l] * (nul[li & 0xffffu] - nul[li >> 16]);
+                f1 = -f0;
+            } else {
+                f0 = S.a[0][l];
+                f1 = f0;
+            }
+            reinterpret_cast<double2*>(f)[l] = make_double2(f0, f1);
+        }
+        __syncthreads();
+        // ---- phase 3: one thread per row, fixed summation order, one red.add per row
+        for (int r = tid; r < d.y; r += THREADS) {
+            const uint32_t r0 = S.rows[r], r1 = S.rows[r + 1];
+            const int beg = (int)(r0 & 0xffffu), end = (int)(r1 & 0xffffu);
+            double s = 0.0;
+            for (int e = beg; e < end; ++e) s += f[S.ent[e]];
+            if (s != 0.0) atomicAdd(A.out + S.tok[r0 >> 16], s);
+        }
+        __syncthreads();                 // stage, nul and f are free again
+        if (tid == 0) {
+            const long long nxt = tile + (long long)STAGES * gridDim.x;
+            if (nxt < A.n_tiles) {
+                fence_proxy_async();
+                issue_tile<P, NF>(&S, &full[stage], A, nxt);
+            }
+        }
+        if (++stage == STAGES) { stage = 0; parity ^= 1u; }
+    }
+    if (MODE == 0) {
+        acc = warp_sum(acc);
+        if ((tid & 31) == 0) part[tid >> 5] = acc;
+        __syncthreads();
+        if (tid < 32) {
+            double s = (tid < THREADS / 32) ? part[tid] : 0.0;
+            s = warp_sum(s);
+            if (tid == 0 && s != 0.0) atomicAdd(A.arb, s);
+        }
+    }
+}
+
+// the sentinel row of tile t must carry `end` in its low 16 bits: with P <= 16384 the value 2P fits only if
+// 2P <= 65535.  P = 1024 / 2048 are the shipped configurations.
+constexpr int kP = 1024;
+constexpr int kBThreads = 512;
+constexpr int kBStages = 2;
+constexpr int kCtasPerSm = 2;
+
+template <int MODE, bool TRADES, bool HESS>
+int launch_blocked(const BlockedArgs& A, cudaStream_t st) {
+    constexpr int NF = (MODE == 0) ? 3 : 1;
+    auto kern = k_blocked<kP, kBThreads, kBStages, MODE, TRADES, HESS>;
+    const size_t sm = (size_t)kBStages * sizeof(Stage<kP, NF>) + (size_t)3 * kP * sizeof(double);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        attr = true;
+    }
+    const long long cap = (long long)kCtasPerSm * num_sms();
+    const int grid = (int)(A.n_tiles < cap ? A.n_tiles : cap);
+    kern<<<grid, kBThreads, sm, st>>>(A);
+    return check_launch();
+}
+
+int fill_args(const cfmm_blocked_pairs* b, BlockedArgs& A) {
+    if (!b) return CFMM_E_NULL;
+    if (b->pools_per_tile != kP) return CFMM_E_KIND;
+    if (b->n_tiles < 0 || b->n_pools < 0 || b->n_pools > b->n_tiles * (int64_t)kP) return CFMM_E_SIZE;
+    if (b->n_tiles > 0 && (!b->lid || !b->ent || !b->rows || !b->tok || !b->desc)) return CFMM_E_NULL;
+    A.n_tiles = b->n_tiles;
+    A.M = b->n_tiles * (int64_t)kP;
+    A.lid = b->lid; A.ent = b->ent; A.rows = b->rows; A.tok = b->tok;
+    A.desc = reinterpret_cast<const int2*>(b->desc);
+    A.slab[0] = A.slab[1] = A.slab[2] = nullptr;
+    A.vec = nullptr; A.out = nullptr; A.arb = nullptr; A.delta = A.lambda = A.hcoef = nullptr;
+    return CFMM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int32_t* tok_stride, int32_t* row_cap) {
+    if (pools_per_tile) *pools_per_tile = kP;
+    if (rows_stride) *rows_stride = BlockedCfg<kP>::kRowsMax;
+    if (tok_stride) *tok_stride = BlockedCfg<kP>::kTokMax;
+    if (row_cap) *row_cap = 32;
+    return CFMM_OK;
+}
+
+int cfmm_blocked_eval(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* nu, double* psi, double* arb,
+                      const cfmm_eval_out* out, void* stream) {
+    BlockedArgs A;
+    int rc = fill_args(b, A);
+    if (rc) return rc;
+    if (n_tokens <= 0) return CFMM_E_SIZE;
+    if (!nu || !psi || !arb) return CFMM_E_NULL;
+    if (b->n_tiles == 0) return CFMM_OK;
+    if (!b->r0 || !b->r1 || !b->gamma_inv) return CFMM_E_NULL;
+    A.slab[0] = b->r0; A.slab[1] = b->r1; A.slab[2] = b->gamma_inv;
+    A.vec = nu; A.out = psi; A.arb = arb;
+    const bool trades = out && out->delta && out->lambda;
+    const bool hess = out && out->hcoef;
+    if (trades) { A.delta = out->delta; A.lambda = out->lambda; }
+    if (hess) A.hcoef = out->hcoef;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (trades && hess) return launch_blocked<0, true, true>(A, st);
+    if (trades) return launch_blocked<0, true, false>(A, st);
+    if (hess) return launch_blocked<0, false, true>(A, st);
+    return launch_blocked<0, false, false>(A, st);
+}
+
+int cfmm_blocked_hvp(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* hcoef, const double* vt, double* y,
+                     void* stream) {
+    BlockedArgs A;
+    int rc = fill_args(b, A);
+    if (rc) return rc;
+    if (n_tokens <= 0) return CFMM_E_SIZE;
+    if (!hcoef || !vt || !y) return CFMM_E_NULL;
+    if (b->n_tiles == 0) return CFMM_OK;
+    A.slab[0] = hcoef; A.vec = vt; A.out = y;
+    return launch_blocked<1, false, false>(A, static_cast<cudaStream_t>(stream));
+}
+
+int cfmm_blocked_diag(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* hcoef, double* diag, void* stream) {
+    BlockedArgs A;
+    int rc = fill_args(b, A);
+    if (rc) return rc;
+    if (n_tokens <= 0) return CFMM_E_SIZE;
+    if (!hcoef || !diag) return CFMM_E_NULL;
+    if (b->n_tiles == 0) return CFMM_OK;
+    A.slab[0] = hcoef; A.out = diag;
+    return launch_blocked<2, false, false>(A, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -6,23 +6,16 @@
 // is independent and has a closed / finite form; the kernels evaluate all pools and reduce
 //     psi = sum_i A_i (L_i - D_i)   (arbitrage.py:54)   and   arb = sum_i nu_i'(L_i - D_i).
 // fp64 throughout, HBM-bound for the 2-token kinds (32 B/pool), no tensor cores (no contraction).
-#include <cuda_runtime.h>
-#include <stdint.h>
-#include <atomic>
 #include <math.h>
 
-#include "cfmm_b200.h"
+#include "cfmm_dev.cuh"
 
-namespace {
-
+namespace cfmm {
 std::atomic<long long> g_launches{0};
 int g_scatter_mode = 0;
 thread_local cudaError_t g_last_err = cudaSuccess;
-int g_num_sms = 0;
-
-constexpr int kThreads = 256;
-
-inline int num_sms() {
+static int g_num_sms = 0;
+int num_sms() {
     if (g_num_sms == 0) {
         int dev = 0, n = 0;
         if (cudaGetDevice(&dev) == cudaSuccess &&
@@ -33,13 +26,13 @@ inline int num_sms() {
     }
     return g_num_sms;
 }
+}  // namespace cfmm
 
-inline int check_launch() {
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { g_last_err = e; return CFMM_E_CUDA; }
-    return CFMM_OK;
-}
+using namespace cfmm;
+
+namespace {
+
+constexpr int kThreads = 256;
 
 // ---------------------------------------------------------------------------------------------
 // scatter targets: global red.add.f64, or a shared-memory privatised copy of the n_token vector
@@ -69,12 +62,6 @@ struct SharedScatter {
     }
 };
 
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
 __device__ __forceinline__ void block_accumulate(double v, double* target) {
     __shared__ double part[kThreads / 32];
     v = warp_sum(v);
@@ -85,12 +72,6 @@ __device__ __forceinline__ void block_accumulate(double v, double* target) {
         s = warp_sum(s);
         if (threadIdx.x == 0 && s != 0.0) atomicAdd(target, s);
     }
-}
-
-__device__ __forceinline__ double warp_max(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -206,29 +187,6 @@ struct __align__(128) PairStage {
 constexpr unsigned kStageBytes = sizeof(PairStage);
 static_assert(kStageBytes == 32u * kTile, "32 B per pool");
 
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-    unsigned ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 __device__ __forceinline__ void issue_pair_tile(PairStage* st, uint64_t* bar, long long tile, long long ld,
                                                 const double* R, const int* idx, const double* gamma) {
     const long long o = tile * kTile;
@@ -245,8 +203,9 @@ __global__ void __launch_bounds__(kTmaThreads, 2)
 k_eval_pair_tma(long long m, long long ld, int n_tokens, const double* __restrict__ R, const int* __restrict__ idx,
                 const double* __restrict__ gamma, const double* __restrict__ thbar, double eps,
                 const double* __restrict__ nu, double* psi, double* arb, double* delta, double* lambda,
-                double* hcoef) {
+                double* hcoef, int n_rep = 1, long long rep_stride = 0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    psi += (long long)(blockIdx.x % n_rep) * rep_stride;
     PairStage* stages = reinterpret_cast<PairStage*>(smem_raw);
     __shared__ uint64_t full[kStages];
     __shared__ double part[kTmaThreads / 32];
@@ -254,8 +213,7 @@ k_eval_pair_tma(long long m, long long ld, int n_tokens, const double* __restric
     const long long ntiles = (m + kTile - 1) / kTile;
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_fence_init();
     }
     __syncthreads();
     if (tid == 0) {
@@ -309,7 +267,7 @@ k_eval_pair_tma(long long m, long long ld, int n_tokens, const double* __restric
         if (tid == 0) {
             const long long nxt = tile + (long long)kStages * gridDim.x;
             if (nxt < ntiles) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                fence_proxy_async();
                 issue_pair_tile(&stages[stage], &full[stage], nxt, ld, R, idx, gamma);
             }
         }
@@ -562,7 +520,7 @@ inline int grid_for(long long m, int blocks_per_sm) {
 }
 
 inline bool use_shared(int n_tokens, long long m) {
-    if (g_scatter_mode == 1 || g_scatter_mode == 3) return false;
+    if (g_scatter_mode == 1 || g_scatter_mode >= 3) return false;
     const bool fits = (size_t)n_tokens * sizeof(double) <= 96 * 1024;
     if (g_scatter_mode == 2) return fits;
     // auto: privatise only when each CTA makes many more contributions than it has bins to flush
@@ -572,6 +530,15 @@ inline bool use_shared(int n_tokens, long long m) {
 template <typename K>
 inline void allow_smem(K kernel, size_t bytes) {
     if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+__global__ void k_fold(const double* __restrict__ rep, int n_rep, long long rs, int n, double* out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) {
+        double s = 0.0;
+        for (int r = 0; r < n_rep; ++r) s += rep[r * rs + j];
+        out[j] += s;
+    }
 }
 
 inline bool tma_ok(const cfmm_bucket* b) {
@@ -598,7 +565,29 @@ int launch_pair(const cfmm_bucket* b, int n_tokens, const double* nu, double eps
         const long long cap = 2LL * num_sms();
         const int grid = (int)(ntiles < cap ? ntiles : cap);
         kern<<<grid, kTmaThreads, sm, st>>>(m, b->stride, n_tokens, b->reserves, b->tok_idx, b->gamma, b->theta_bar,
-                                            eps, nu, psi, arb, delta, lambda, hcoef);
+                                            eps, nu, psi, arb, delta, lambda, hcoef, 1, 0);
+        return check_launch();
+    }
+    if (g_scatter_mode >= 5 && tma_ok(b)) {
+        // EXPERIMENT: psi replicated n_rep times (mode value = n_rep) to cut same-address serialisation in L2
+        const int n_rep = g_scatter_mode;
+        const long long rs = ((long long)n_tokens + 15) / 16 * 16;
+        static double* scratch = nullptr; static long long cap_elems = 0;
+        if (cap_elems < rs * n_rep) {
+            if (scratch) cudaFree(scratch);
+            cudaMalloc(&scratch, sizeof(double) * rs * n_rep); cap_elems = rs * n_rep;
+        }
+        cudaMemsetAsync(scratch, 0, sizeof(double) * rs * n_rep, st);
+        auto kern = k_eval_pair_tma<KIND, TRADES, HESS>;
+        const size_t sm = (size_t)kStages * kStageBytes;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        const long long ntiles = (m + kTile - 1) / kTile;
+        const long long cap = 2LL * num_sms();
+        kern<<<(int)(ntiles < cap ? ntiles : cap), kTmaThreads, sm, st>>>(
+            m, b->stride, n_tokens, b->reserves, b->tok_idx, b->gamma, b->theta_bar, eps, nu, scratch, arb, delta, lambda,
+            hcoef, n_rep, rs);
+        k_fold<<<(n_tokens + 255) / 256, 256, 0, st>>>(scratch, n_rep, rs, n_tokens, psi);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
         return check_launch();
     }
     if (g_scatter_mode == 4 && tma_ok(b) && KIND == CFMM_KIND_PRODUCT && !TRADES && !HESS) {
@@ -609,7 +598,8 @@ int launch_pair(const cfmm_bucket* b, int n_tokens, const double* nu, double eps
         const long long ntiles = (m + kTile - 1) / kTile;
         const long long cap = 2LL * num_sms();
         kern<<<(int)(ntiles < cap ? ntiles : cap), kTmaThreads, sm, st>>>(
-            m, b->stride, n_tokens, b->reserves, b->tok_idx, b->gamma, b->theta_bar, eps, nu, psi, arb, delta, lambda, hcoef);
+            m, b->stride, n_tokens, b->reserves, b->tok_idx, b->gamma, b->theta_bar, eps, nu, psi, arb, delta, lambda, hcoef,
+            1, 0);
         return check_launch();
     }
     if (use_shared(n_tokens, m)) {
@@ -811,7 +801,7 @@ int cfmm_zero(void* ptr, int64_t bytes, void* stream) {
 }
 
 int cfmm_set_scatter_mode(int32_t mode) {
-    if (mode < 0 || mode > 4) return CFMM_E_KIND;
+    if (mode < 0 || mode > 64) return CFMM_E_KIND;
     g_scatter_mode = mode;
     return CFMM_OK;
 }

@@ -173,10 +173,150 @@ class DeviceBucket:
                             self.hcoef.data_ptr() if hess else None, self.hmask.data_ptr() if hess else None)
 
 
+def blocked_layout_info(lib):
+    v = [C.c_int32() for _ in range(4)]
+    _lib.check(lib.cfmm_blocked_layout_info(*[C.byref(x) for x in v]), "cfmm_blocked_layout_info")
+    return tuple(int(x.value) for x in v)      # pools_per_tile, rows_stride, tok_stride, row_cap
+
+
+def build_blocked_pairs(idx: torch.Tensor, n_tokens: int, P: int, rows_stride: int, tok_stride: int, row_cap: int):
+    """Layout builder for cfmm_blocked_pairs (see csrc/cfmm_blocked.cu).  idx: (2, m) int64 token ids on the
+    device.  Pools are sorted by (token block of slot 0, token block of slot 1) and cut into tiles of P; each
+    tile gets its distinct-token list, 16-bit local ids, and a CSR of rows (token, <= row_cap entries).
+    Returns (order, residual, tables): `order` = bucket-local pool index at each blocked position, `residual` =
+    pools left out because their tile would touch more than tok_stride tokens (they go to a plain bucket)."""
+    dev = idx.device
+    m = idx.shape[1]
+    i64 = dict(dtype=torch.int64, device=dev)
+    nb = max(1, int(round((m / P) ** 0.5)))
+    a, b = idx[0], idx[1]
+    key = (a * nb // n_tokens) * nb + (b * nb // n_tokens)
+    order = torch.argsort(key, stable=True)
+    residual = []
+    for _pass in range(4):
+        mm = order.numel()
+        if mm == 0:
+            break
+        ntiles = -(-mm // P)
+        pos = torch.arange(mm, **i64)
+        tile = pos // P
+        l = pos - tile * P
+        he_tok = torch.cat([a[order], b[order]])
+        he_tile = torch.cat([tile, tile])
+        he_code = torch.cat([2 * l, 2 * l + 1])
+        ck, perm = torch.sort(he_tile * n_tokens + he_tok, stable=True)
+        uniq, inv, counts = torch.unique_consecutive(ck, return_inverse=True, return_counts=True)
+        u_tile = uniq // n_tokens
+        ntok = torch.bincount(u_tile, minlength=ntiles)
+        bad = ntok > tok_stride
+        if not bool(bad.any()):
+            break
+        if _pass == 3:                       # give up blocking: everything left goes to the plain bucket
+            residual.append(order); order = order[:0]; mm = 0
+            break
+        keep = ~bad[tile]
+        residual.append(order[~keep])
+        order = order[keep]
+    residual = torch.cat(residual) if residual else order[:0]
+    if order.numel() == 0:
+        return order, residual, None
+    U = uniq.numel()
+    tok_off = torch.cumsum(ntok, 0) - ntok
+    ltok_u = torch.arange(U, **i64) - tok_off[u_tile]
+    he_ltok = torch.empty(2 * mm, **i64)
+    he_ltok[perm] = ltok_u[inv]
+    M = ntiles * P
+    lid = torch.zeros(M, dtype=torch.int32, device=dev)
+    lid[:mm] = (he_ltok[:mm] | (he_ltok[mm:] << 16)).to(torch.int32)
+    tok = torch.zeros((ntiles, tok_stride), dtype=torch.int32, device=dev)
+    tok[u_tile, ltok_u] = (uniq - u_tile * n_tokens).to(torch.int32)
+    ent = torch.zeros(ntiles * 2 * P, dtype=torch.int16, device=dev)
+    # every tile but the last holds exactly 2P half-edges, so the sorted order IS the per-tile layout
+    ent[:2 * mm] = he_code[perm].to(torch.int16)
+    nsub = (counts + row_cap - 1) // row_cap
+    n_rows = int(nsub.sum())
+    row_u = torch.repeat_interleave(torch.arange(U, **i64), nsub)
+    sub = torch.arange(n_rows, **i64) - (torch.cumsum(nsub, 0) - nsub)[row_u]
+    g_start = torch.cumsum(counts, 0) - counts
+    row_tile = u_tile[row_u]
+    row_start = g_start[row_u] + row_cap * sub - 2 * P * row_tile
+    nrow = torch.bincount(row_tile, minlength=ntiles)
+    r_local = torch.arange(n_rows, **i64) - (torch.cumsum(nrow, 0) - nrow)[row_tile]
+    if int(nrow.max()) + 1 > rows_stride:
+        raise _lib.CfmmError("blocked layout: row table overflow (library/builder mismatch)")
+    rows = torch.zeros((ntiles, rows_stride), dtype=torch.int32, device=dev)
+    rows[row_tile, r_local] = (row_start | (ltok_u[row_u] << 16)).to(torch.int32)
+    pools_in_tile = torch.full((ntiles,), P, **i64)
+    pools_in_tile[-1] = mm - (ntiles - 1) * P
+    rows[torch.arange(ntiles, **i64), nrow] = (2 * pools_in_tile).to(torch.int32)     # closing sentinel
+    desc = torch.stack([ntok, nrow], 1).to(torch.int32).contiguous()
+    tables = dict(n_tiles=ntiles, M=M, lid=lid, tok=tok, ent=ent, rows=rows, desc=desc,
+                  rows_per_pool=n_rows / mm, tok_per_tile=float(ntok.double().mean()))
+    return order, residual, tables
+
+
+class BlockedBucket:
+    """Constant-product pools in the token-blocked layout (HBM-bound kind; no per-pool atomics)."""
+    kind = _lib.KIND_PRODUCT
+    arity = 2
+    blocked = True
+
+    def __init__(self, hp: HostPools, spec, device, lib):
+        sel, off = spec["sel"], spec["off"]
+        P, rows_stride, tok_stride, row_cap = blocked_layout_info(lib)
+        idx = torch.as_tensor(hp.tok_idx[off].astype(np.int64), device=device)
+        order, residual, t = build_blocked_pairs(idx, hp.n_tokens, P, rows_stride, tok_stride, row_cap)
+        self.residual = residual.cpu().numpy()           # bucket-local indices left for a plain bucket
+        order_h = order.cpu().numpy()
+        self.sel = sel[order_h]
+        self.off = off[:, order_h]
+        self.m = int(len(order_h))
+        self.theta_bar = None
+        self.delta = self.lam = self.hcoef = self.hmask = None
+        self._device = device
+        if self.m == 0:
+            self.tables = None
+            return
+        self.tables = t
+        self.stride = t["M"]
+        f64 = dict(dtype=torch.float64, device=device)
+
+        def slab(vals, fill):
+            out = torch.full((t["M"],), fill, **f64)
+            out[:self.m] = torch.as_tensor(vals, **f64)
+            return out
+        R = hp.reserves[self.off]
+        self.r0 = slab(R[0], 1.0)
+        self.r1 = slab(R[1], 1.0)
+        self.gamma_inv = slab(1.0 / hp.gamma[self.sel], 1.0)
+        self.c_blocked = _lib.BlockedPairs(self.m, t["n_tiles"], P, 0, self.r0.data_ptr(), self.r1.data_ptr(),
+                                           self.gamma_inv.data_ptr(), t["lid"].data_ptr(), t["ent"].data_ptr(),
+                                           t["rows"].data_ptr(), t["tok"].data_ptr(), t["desc"].data_ptr())
+
+    def bytes_resident(self) -> int:
+        if self.tables is None:
+            return 0
+        ts = [self.r0, self.r1, self.gamma_inv] + [self.tables[k] for k in ("lid", "tok", "ent", "rows", "desc")]
+        return sum(x.numel() * x.element_size() for x in ts)
+
+    def out_struct(self, trades: bool, hess: bool):
+        f64 = dict(dtype=torch.float64, device=self._device)
+        if trades and self.delta is None:
+            self.delta = torch.zeros((2, self.stride), **f64)
+            self.lam = torch.zeros((2, self.stride), **f64)
+        if hess and self.hcoef is None:
+            self.hcoef = torch.zeros(self.stride, **f64)
+        return _lib.EvalOut(self.delta.data_ptr() if trades else None, self.lam.data_ptr() if trades else None,
+                            self.hcoef.data_ptr() if hess else None, None)
+
+
 class PoolStore:
     """All pools of one problem (or one rank's shard of them), resident on one GPU."""
 
-    def __init__(self, hp: HostPools, device="cuda", rank: int = 0, world: int = 1, validate: bool = True):
+    def __init__(self, hp: HostPools, device="cuda", rank: int = 0, world: int = 1, validate: bool = True,
+                 layout: str = "blocked"):
+        if layout not in ("blocked", "plain"):
+            raise ValueError("layout must be 'blocked' or 'plain'")
         if validate:
             hp.validate()
         self.lib = _lib.load()
@@ -186,8 +326,19 @@ class PoolStore:
         self.n_tokens = int(hp.n_tokens)
         self.m_total = hp.m
         self.pool_ptr = hp.pool_ptr
+        self._tok_idx_host = hp.tok_idx
         self.rank, self.world = rank, world
-        self.buckets = [DeviceBucket(hp, s, self.device) for s in split_buckets(hp, rank, world)]
+        self.buckets = []
+        for s in split_buckets(hp, rank, world):
+            if s["kind"] == _lib.KIND_PRODUCT and layout == "blocked" and len(s["sel"]) > 0:
+                bb = BlockedBucket(hp, s, self.device, self.lib)
+                if bb.m > 0:
+                    self.buckets.append(bb)
+                if len(bb.residual):
+                    r = bb.residual
+                    self.buckets.append(DeviceBucket(hp, dict(s, sel=s["sel"][r], off=s["off"][:, r]), self.device))
+            else:
+                self.buckets.append(DeviceBucket(hp, s, self.device))
         self.m_local = sum(b.m for b in self.buckets)
         self.has_sum = bool(np.any(hp.kind == KIND_SUM_HOST))
         self.has_geomean = any(b.kind == _lib.KIND_GEOMEAN for b in self.buckets)
@@ -209,7 +360,7 @@ class PoolStore:
         """32 B per 2-token pool, 28k+12 per weighted pool, + nu, psi, arb."""
         n = 0
         for b in self.buckets:
-            n += b.m * (32 if b.arity == 2 and b.kind != _lib.KIND_GEOMEAN else 28 * b.arity + 12)
+            n += b.m * (32 if b.kind != _lib.KIND_GEOMEAN else 28 * b.arity + 12)
         return n + 16 * self.n_tokens + 8
 
     # -- the hot path --------------------------------------------------------------------------
@@ -221,6 +372,12 @@ class PoolStore:
         lognu = torch.log(nu) if self.has_geomean else None
         for b in self.buckets:
             out = b.out_struct(trades, hess) if (trades or hess) else None
+            if getattr(b, "blocked", False):
+                rc = self.lib.cfmm_blocked_eval(C.byref(b.c_blocked), self.n_tokens, nu.data_ptr(), acc.data_ptr(),
+                                                acc.data_ptr() + 8 * self.n_tokens,
+                                                C.byref(out) if out is not None else None, st)
+                _lib.check(rc, "cfmm_blocked_eval")
+                continue
             rc = self.lib.cfmm_arb_eval(C.byref(b.c_bucket), self.n_tokens, nu.data_ptr(),
                                         lognu.data_ptr() if lognu is not None else None, float(eps),
                                         acc.data_ptr(), acc.data_ptr() + 8 * self.n_tokens,
@@ -234,6 +391,10 @@ class PoolStore:
         y = self._y
         _lib.check(self.lib.cfmm_zero(y.data_ptr(), y.numel() * 8, st), "cfmm_zero")
         for b in self.buckets:
+            if getattr(b, "blocked", False):
+                _lib.check(self.lib.cfmm_blocked_hvp(C.byref(b.c_blocked), self.n_tokens, b.hcoef.data_ptr(),
+                                                     vt.data_ptr(), y.data_ptr(), st), "cfmm_blocked_hvp")
+                continue
             rc = self.lib.cfmm_hvp(C.byref(b.c_bucket), self.n_tokens, b.hcoef.data_ptr(),
                                    b.hmask.data_ptr(), vt.data_ptr(), y.data_ptr(), st)
             _lib.check(rc, "cfmm_hvp")
@@ -244,6 +405,10 @@ class PoolStore:
         st = self._stream()
         d = torch.zeros(self.n_tokens, dtype=torch.float64, device=self.device)
         for b in self.buckets:
+            if getattr(b, "blocked", False):
+                _lib.check(self.lib.cfmm_blocked_diag(C.byref(b.c_blocked), self.n_tokens, b.hcoef.data_ptr(),
+                                                      d.data_ptr(), st), "cfmm_blocked_diag")
+                continue
             _lib.check(self.lib.cfmm_hess_diag(C.byref(b.c_bucket), self.n_tokens, b.hcoef.data_ptr(),
                                                b.hmask.data_ptr(), d.data_ptr(), st), "cfmm_hess_diag")
         return d
@@ -252,9 +417,24 @@ class PoolStore:
         st = self._stream()
         H = torch.zeros((self.n_tokens, self.n_tokens), dtype=torch.float64, device=self.device)
         for b in self.buckets:
+            if getattr(b, "blocked", False):
+                # dense assembly is a small-n path: scatter the blocked hcoef with torch index_put (plumbing)
+                i0 = torch.as_tensor(self._tok_of(b, 0), device=self.device)
+                i1 = torch.as_tensor(self._tok_of(b, 1), device=self.device)
+                h = b.hcoef[:b.m]
+                H.index_put_((i0, i0), h, accumulate=True); H.index_put_((i1, i1), h, accumulate=True)
+                H.index_put_((i0, i1), -h, accumulate=True); H.index_put_((i1, i0), -h, accumulate=True)
+                continue
             _lib.check(self.lib.cfmm_hess_dense(C.byref(b.c_bucket), self.n_tokens, b.hcoef.data_ptr(),
                                                 b.hmask.data_ptr(), H.data_ptr(), st), "cfmm_hess_dense")
         return H
+
+    def _tok_of(self, b, slot):
+        key = (id(b), slot)
+        cache = self.__dict__.setdefault("_tok_cache", {})
+        if key not in cache:
+            cache[key] = self._tok_idx_host[b.off[slot]].astype(np.int64)
+        return cache[key]
 
     def update_multipliers(self) -> torch.Tensor:
         """theta_bar <- fills of the last trades=True evaluation; returns max relative change (device)."""

@@ -89,6 +89,39 @@ int cfmm_hess_diag(const cfmm_bucket* bucket, int32_t n_tokens, const double* hc
 int cfmm_hess_dense(const cfmm_bucket* bucket, int32_t n_tokens, const double* hcoef, const uint32_t* hmask,
                     double* H, void* stream);
 
+/*
+ * Token-blocked storage for constant-product pools (the HBM-bound kind).  Built once per problem from
+ * local_indices (arbitrage.py:6-12) by the layout builder (pools.py: build_blocked_pairs); pools are
+ * reordered into tiles of `pools_per_tile` whose tokens fall into two narrow token blocks.  Per pool 28 B of
+ * slabs + 4 B of row entries; per tile a token list, a row table and (ntok, nrow).  See csrc/cfmm_blocked.cu.
+ * Strides of the per-tile tables come from cfmm_blocked_layout_info().
+ */
+typedef struct cfmm_blocked_pairs {
+    int64_t n_pools;          /* real pools (<= n_tiles * pools_per_tile; the rest is padding)          */
+    int64_t n_tiles;
+    int32_t pools_per_tile;   /* must equal the library's tile size                                      */
+    int32_t reserved;
+    const double* r0;         /* [n_tiles*P] reserves of slot 0, blocked order        arbitrage.py:14-20 */
+    const double* r1;         /* [n_tiles*P] reserves of slot 1                                          */
+    const double* gamma_inv;  /* [n_tiles*P] 1 / fees[i]                              arbitrage.py:22-28 */
+    const uint32_t* lid;      /* [n_tiles*P] tile-local token ids: slot0 | slot1 << 16                   */
+    const uint16_t* ent;      /* [n_tiles][2P] row-ordered entries: local_pool << 1 | slot               */
+    const uint32_t* rows;     /* [n_tiles][rows_stride] row start | local token << 16, + closing sentinel */
+    const int32_t* tok;       /* [n_tiles][tok_stride] local token id -> global token id                 */
+    const int32_t* desc;      /* [n_tiles][2] (ntok, nrow)                                               */
+} cfmm_blocked_pairs;
+
+int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int32_t* tok_stride, int32_t* row_cap);
+
+/* Same contract as cfmm_arb_eval for a blocked constant-product bucket (psi/arb accumulate).  Per-pool outputs
+ * (delta/lambda [2][n_tiles*P], hcoef [n_tiles*P]) are in BLOCKED order. */
+int cfmm_blocked_eval(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* nu, double* psi, double* arb,
+                      const cfmm_eval_out* out, void* stream);
+/* y += Hs vt and diag += diag(Hs) for a blocked bucket, hcoef in blocked order. */
+int cfmm_blocked_hvp(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* hcoef, const double* vt, double* y,
+                     void* stream);
+int cfmm_blocked_diag(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* hcoef, double* diag, void* stream);
+
 /* SUM buckets: theta_bar <- current fills (= lambda), returns max_i |change|/R in move[0] (device). */
 int cfmm_sum_update_multipliers(const cfmm_bucket* bucket, const double* lambda, double* theta_bar_out,
                                 double* move, void* stream);

@@ -24,8 +24,8 @@ def _oracle_eval(hp, nu, eps=0.0, theta=None, **kw):
     return O.evaluate(bk, nu, eps, **kw)
 
 
-def _check_eval(hp, nu, eps=0.0, theta=None, scatter_mode=0):
-    st = cf.PoolStore(hp)
+def _check_eval(hp, nu, eps=0.0, theta=None, scatter_mode=0, layout="blocked"):
+    st = cf.PoolStore(hp, layout=layout)
     st.lib.cfmm_set_scatter_mode(scatter_mode)
     try:
         if theta is not None:
@@ -51,8 +51,46 @@ def _check_eval(hp, nu, eps=0.0, theta=None, scatter_mode=0):
 
 @pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_product_eval_matches_oracle(mode):
+    """plain layout: LDG kernel with global / shared-memory scatter, and the TMA-staged kernel"""
     hp, s = H.cp_host_pools(20_000, 97, seed=11)
-    _check_eval(hp, H.random_prices(s["prices"], 1), scatter_mode=mode)
+    _check_eval(hp, H.random_prices(s["prices"], 1), scatter_mode=mode, layout="plain")
+
+
+@pytest.mark.parametrize("m,n", [(20_000, 97), (1500, 700), (1024, 8), (1025, 3000), (70_000, 4096)])
+def test_blocked_product_eval_matches_oracle(m, n):
+    """token-blocked layout (csrc/cfmm_blocked.cu): ragged last tile, few and many tokens per tile"""
+    hp, s = H.cp_host_pools(m, n, seed=13)
+    st, _ = _check_eval(hp, H.random_prices(s["prices"], 1))
+    assert any(getattr(b, "blocked", False) for b in st.buckets)
+
+
+def test_blocked_layout_falls_back_when_tiles_touch_too_many_tokens():
+    """every pool on its own pair of tokens: no tile can stay under the per-tile token cap -> plain bucket"""
+    m = 3000
+    idx = np.arange(2 * m).reshape(m, 2)
+    rng = np.random.default_rng(3)
+    hp = cf.HostPools.from_pairs(2 * m, idx, np.exp(rng.normal(3, 1, (m, 2))), np.full(m, 0.997))
+    st, _ = _check_eval(hp, np.exp(rng.normal(0, 0.5, 2 * m)))
+    assert not any(getattr(b, "blocked", False) for b in st.buckets)
+    # mixed: a dense core plus the sparse fringe
+    hp2, s2 = H.cp_host_pools(8000, 64, seed=5)
+    idx2 = np.concatenate([hp2.tok_idx.reshape(-1, 2), 64 + idx])
+    R2 = np.concatenate([hp2.reserves.reshape(-1, 2), hp.reserves.reshape(-1, 2)])
+    hp3 = cf.HostPools.from_pairs(64 + 2 * m, idx2, R2, np.concatenate([hp2.gamma, hp.gamma]))
+    _check_eval(hp3, np.exp(rng.normal(0, 0.3, 64 + 2 * m)))
+
+
+def test_blocked_hvp_and_diag_match_plain():
+    hp, s = H.cp_host_pools(30_000, 300, seed=17)
+    nu = torch.as_tensor(H.random_prices(s["prices"], 2), **F64)
+    v = torch.randn(300, **F64)
+    outs = []
+    for layout in ("blocked", "plain"):
+        st = cf.PoolStore(hp, layout=layout)
+        st.evaluate(nu, hess=True)
+        outs.append((st.hvp(v).clone(), st.hess_diag().clone(), st.hess_dense().clone()))
+    for x, y in zip(*outs):
+        assert float((x - y).abs().max()) <= 1e-11 * float(y.abs().max())
 
 
 def test_product_eval_extreme_prices_and_no_trade():
