@@ -35,7 +35,7 @@ struct __align__(128) Stage {
     double a[NF][P];
     uint32_t lid[P];                              // lid0 | lid1 << 16
     uint16_t ent[2 * P];                          // row-ordered: local_pool << 1 | slot
-    uint32_t rows[BlockedCfg<P>::kRowsMax];       // start | local_token << 16 ; sentinel row closes the last one
+    uint32_t rows[BlockedCfg<P>::kRowsMax];       // start:16 | length:6 | local token:10
     int32_t tok[BlockedCfg<P>::kTokMax];          // local token id -> global token id
 };
 
@@ -49,11 +49,17 @@ struct BlockedArgs {
     const int32_t* tok;           // [n_tiles][kTokMax]
     const int2* desc;             // [n_tiles] (ntok, nrow)
     const double* vec;            // nu (eval) or vt (hvp); unused for diag
-    double* out;                  // psi / y / diag  (+=)
+    double* out;                  // psi / y / diag: zeroed by this kernel, filled by k_token_reduce
+    int n_out;                    // entries of `out` to zero (n_tokens, +1 for arb in eval mode)
+    double* partial;              // [n_tiles][rows_stride] row sums (plain stores, no atomics)
     double* arb;                  // eval only
     double* delta;                // eval, optional: [2][M] blocked order
     double* lambda;
     double* hcoef;                // eval, optional: [M]
+    int n_seg;                    // token segments for k_token_reduce
+    const int4* seg;              // [n_seg] (token, begin, end, multi)
+    const int* pos;               // [n_rows_total] positions into partial
+    int dbg;                      // MEASUREMENT ONLY: bit0 skip row phase, bit1 skip pool math, bit2 skip nu gather
 };
 
 __device__ __forceinline__ unsigned round16(unsigned bytes) { return (bytes + 15u) & ~15u; }
@@ -61,7 +67,7 @@ __device__ __forceinline__ unsigned round16(unsigned bytes) { return (bytes + 15
 template <int P, int NF>
 __device__ __forceinline__ void issue_tile(Stage<P, NF>* st, uint64_t* bar, const BlockedArgs& A, long long tile) {
     const int2 d = __ldg(A.desc + tile);
-    const unsigned rows_b = round16(4u * (unsigned)(d.y + 1));
+    const unsigned rows_b = round16(4u * (unsigned)d.y);
     const unsigned tok_b = round16(4u * (unsigned)d.x);
     mbar_expect_tx(bar, (unsigned)(NF * P * 8 + P * 4 + 2 * P * 2) + rows_b + tok_b);
 #pragma unroll
@@ -107,6 +113,12 @@ struct EvalOp {
     }
 };
 
+// row word: start (16 bits) | length (6 bits, 1..32) | local token (10 bits).  Rows of a tile are sorted by
+// decreasing length by the builder, so the 32 rows of a warp have (nearly) equal trip counts.
+__device__ __forceinline__ int row_start(uint32_t r) { return (int)(r & 0xffffu); }
+__device__ __forceinline__ int row_len(uint32_t r) { return (int)((r >> 16) & 0x3fu); }
+__device__ __forceinline__ int row_tok(uint32_t r) { return (int)(r >> 22); }
+
 template <int P, int THREADS, int STAGES, int MODE /*0 eval, 1 hvp, 2 diag*/, bool TRADES, bool HESS>
 __global__ void __launch_bounds__(THREADS)
 k_blocked(const BlockedArgs A) {
@@ -114,8 +126,8 @@ k_blocked(const BlockedArgs A) {
     using St = Stage<P, NF>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     St* stages = reinterpret_cast<St*>(smem_raw);
-    double* nul = reinterpret_cast<double*>(smem_raw + (size_t)STAGES * sizeof(St));     // [P]  nu_local
-    double* f = nul + P;                                                                  // [2P] flows
+    double* nul0 = reinterpret_cast<double*>(smem_raw + (size_t)STAGES * sizeof(St));    // [2][P]  nu_local, double buffered
+    double* f0buf = nul0 + 2 * P;                                                         // [2][2P] flows, double buffered
     __shared__ uint64_t full[STAGES];
     __shared__ double part[THREADS / 32];
     const int tid = threadIdx.x;
@@ -130,24 +142,36 @@ k_blocked(const BlockedArgs A) {
             if (t < A.n_tiles) issue_tile<P, NF>(&stages[s], &full[s], A, t);
         }
     }
+    for (int j = blockIdx.x * THREADS + tid; j < A.n_out; j += gridDim.x * THREADS) A.out[j] = 0.0;
     double acc = 0.0;
-    int stage = 0;
+    int stage = 0, pstage = 0, buf = 0;
     unsigned parity = 0;
-    for (long long tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
-        const int2 d = __ldg(A.desc + tile);           // (ntok, nrow)
-        mbar_wait(&full[stage], parity);
-        St& S = stages[stage];
-        // ---- phase 1: nu_local <- vec[tok]
+    // prologue: nu_local of the first tile
+    if ((long long)blockIdx.x < A.n_tiles) {
+        mbar_wait(&full[0], 0);
         if (MODE != 2) {
-            for (int t = tid; t < d.x; t += THREADS) nul[t] = __ldg(A.vec + S.tok[t]);
-            __syncthreads();
+            const int ntok = __ldg(A.desc + blockIdx.x).x;
+            for (int t = tid; t < ntok; t += THREADS) nul0[t] = __ldg(A.vec + stages[0].tok[t]);
         }
-        // ---- phase 2: per-pool values into f
+    }
+    __syncthreads();
+    // One barrier per tile.  Iteration k: pool phase of tile k -> f[k&1]; prefetch nu_local of tile k+1;
+    // barrier; row phase of tile k.  The row phase of tile k overlaps the pool phase of tile k+1 in other
+    // warps, and its red.adds are never followed directly by a barrier.
+    bool first = true;
+    for (long long tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+        const int nrow = __ldg(A.desc + tile).y;
+        St& S = stages[stage];
+        const double* nul = nul0 + buf * P;
+        double* f = f0buf + buf * 2 * P;
+        // ---- pool phase
 #pragma unroll
         for (int l = tid; l < P; l += THREADS) {
             const uint32_t li = S.lid[l];
             double f0, f1;
             if (MODE == 0) {
+                if (A.dbg & 2) { f0 = S.a[0][l]; f1 = S.a[1][l] + S.a[2][l] + nul[li & 0xffffu] + nul[li >> 16]; }
+                else
                 EvalOp::apply<TRADES, HESS>(A, tile * P + l, S.a[0][l], S.a[1][l], S.a[2][l], nul[li & 0xffffu],
                                             nul[li >> 16], f0, f1, acc);
             } else if (MODE == 1) {
@@ -159,71 +183,136 @@ k_blocked(const BlockedArgs A) {
             }
             reinterpret_cast<double2*>(f)[l] = make_double2(f0, f1);
         }
-        __syncthreads();
-        // ---- phase 3: one thread per row, fixed summation order, one red.add per row
-        for (int r = tid; r < d.y; r += THREADS) {
-            const uint32_t r0 = S.rows[r], r1 = S.rows[r + 1];
-            const int beg = (int)(r0 & 0xffffu), end = (int)(r1 & 0xffffu);
-            double s = 0.0;
-            for (int e = beg; e < end; ++e) s += f[S.ent[e]];
-            if (s != 0.0) atomicAdd(A.out + S.tok[r0 >> 16], s);
-        }
-        __syncthreads();                 // stage, nul and f are free again
-        if (tid == 0) {
-            const long long nxt = tile + (long long)STAGES * gridDim.x;
-            if (nxt < A.n_tiles) {
-                fence_proxy_async();
-                issue_tile<P, NF>(&S, &full[stage], A, nxt);
+        // ---- nu_local of the next tile into the other buffer
+        const long long nxt = tile + gridDim.x;
+        int nstage = stage + 1;
+        unsigned nparity = parity;
+        if (nstage == STAGES) { nstage = 0; nparity ^= 1u; }
+        if (nxt < A.n_tiles) {
+            mbar_wait(&full[nstage], nparity);
+            if (MODE != 2 && !(A.dbg & 4)) {
+                const int ntok = __ldg(A.desc + nxt).x;
+                double* nn = nul0 + (buf ^ 1) * P;
+                for (int t = tid; t < ntok; t += THREADS) nn[t] = __ldg(A.vec + stages[nstage].tok[t]);
             }
         }
-        if (++stage == STAGES) { stage = 0; parity ^= 1u; }
+        __syncthreads();          // f of this tile complete; everybody is also done with the PREVIOUS tile's rows
+        if (tid == 0 && !first) {
+            const long long far = tile + (long long)(STAGES - 1) * gridDim.x;     // (previous tile) + STAGES strides
+            if (far < A.n_tiles) {
+                fence_proxy_async();
+                issue_tile<P, NF>(&stages[pstage], &full[pstage], A, far);
+            }
+        }
+        // ---- row phase: one thread per row, fixed summation order, one red.add per row
+        for (int r = tid; r < ((A.dbg & 1) ? 0 : nrow); r += THREADS) {
+            const uint32_t rw = S.rows[r];
+            const uint16_t* e = S.ent + row_start(rw);
+            const int len = row_len(rw);
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int k = 0;
+            for (; k + 4 <= len; k += 4) {
+                s0 += f[e[k]]; s1 += f[e[k + 1]]; s2 += f[e[k + 2]]; s3 += f[e[k + 3]];
+            }
+            for (; k < len; ++k) s0 += f[e[k]];
+            A.partial[tile * BlockedCfg<P>::kRowsMax + r] = (s0 + s1) + (s2 + s3);
+        }
+        first = false;
+        pstage = stage; stage = nstage; parity = nparity; buf ^= 1;
     }
-    if (MODE == 0) {
-        acc = warp_sum(acc);
-        if ((tid & 31) == 0) part[tid >> 5] = acc;
+    (void)acc; (void)part;
+}
+
+// Second pass: psi[token] = sum of that token's row sums, in a fixed order (bit-reproducible), no atomics for
+// tokens that fit one segment.  One warp per segment (<= kSegCap rows); arb += nu[token] * sum.
+constexpr int kSegCap = 1024;
+template <bool WITH_ARB>
+__global__ void __launch_bounds__(256)
+k_token_reduce(int n_seg, const int4* __restrict__ seg, const int* __restrict__ pos, const double* __restrict__ partial,
+               const double* __restrict__ nu, double* out, double* arb) {
+    __shared__ double part[8];
+    const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    double contrib = 0.0;
+    if (warp < n_seg) {
+        const int4 sg = __ldg(seg + warp);              // (token, begin, end, multi-segment flag)
+        double s = 0.0;
+        for (int k = sg.y + lane; k < sg.z; k += 32) s += partial[__ldg(pos + k)];
+        s = warp_sum(s);
+        if (lane == 0) {
+            if (sg.w) atomicAdd(out + sg.x, s); else out[sg.x] = s;
+            if (WITH_ARB) contrib = __ldg(nu + sg.x) * s;
+        }
+    }
+    if (WITH_ARB) {
+        contrib = warp_sum(contrib);
+        if (lane == 0) part[threadIdx.x >> 5] = contrib;
         __syncthreads();
-        if (tid < 32) {
-            double s = (tid < THREADS / 32) ? part[tid] : 0.0;
-            s = warp_sum(s);
-            if (tid == 0 && s != 0.0) atomicAdd(A.arb, s);
+        if (threadIdx.x < 32) {
+            double t = (threadIdx.x < 8) ? part[threadIdx.x] : 0.0;
+            t = warp_sum(t);
+            if (threadIdx.x == 0 && t != 0.0) atomicAdd(arb, t);
         }
     }
 }
 
-// the sentinel row of tile t must carry `end` in its low 16 bits: with P <= 16384 the value 2P fits only if
-// 2P <= 65535.  P = 1024 / 2048 are the shipped configurations.
-constexpr int kP = 1024;
-constexpr int kBThreads = 512;
-constexpr int kBStages = 2;
-constexpr int kCtasPerSm = 2;
+// ---- shipped configurations (selectable at run time for tuning; the layout must be built for the same P)
+struct Cfg0 { static constexpr int P = 1024, T = 512, S = 3, CTAS = 1; };   // 121 + 48 KB smem, one CTA per SM
+struct Cfg1 { static constexpr int P = 512, T = 512, S = 4, CTAS = 2; };    // 2 x (81 + 24) KB
+struct Cfg2 { static constexpr int P = 512, T = 256, S = 3, CTAS = 2; };    // 2 x (61 + 24) KB, 2 pools per thread
+int g_cfg = 1;
+int g_dbg = 0;
 
-template <int MODE, bool TRADES, bool HESS>
-int launch_blocked(const BlockedArgs& A, cudaStream_t st) {
+template <class C, int MODE, bool TRADES, bool HESS>
+int launch_cfg(const BlockedArgs& A, cudaStream_t st) {
     constexpr int NF = (MODE == 0) ? 3 : 1;
-    auto kern = k_blocked<kP, kBThreads, kBStages, MODE, TRADES, HESS>;
-    const size_t sm = (size_t)kBStages * sizeof(Stage<kP, NF>) + (size_t)3 * kP * sizeof(double);
+    auto kern = k_blocked<C::P, C::T, C::S, MODE, TRADES, HESS>;
+    const size_t sm = (size_t)C::S * sizeof(Stage<C::P, NF>) + (size_t)6 * C::P * sizeof(double);
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         attr = true;
     }
-    const long long cap = (long long)kCtasPerSm * num_sms();
+    const long long cap = (long long)C::CTAS * num_sms();
     const int grid = (int)(A.n_tiles < cap ? A.n_tiles : cap);
-    kern<<<grid, kBThreads, sm, st>>>(A);
+    kern<<<grid, C::T, sm, st>>>(A);
+    int rc = check_launch();
+    if (rc) return rc;
+    const int blocks = (A.n_seg * 32 + 255) / 256;
+    if (MODE == 0)
+        k_token_reduce<true><<<blocks, 256, 0, st>>>(A.n_seg, A.seg, A.pos, A.partial, A.vec, A.out, A.arb);
+    else
+        k_token_reduce<false><<<blocks, 256, 0, st>>>(A.n_seg, A.seg, A.pos, A.partial, nullptr, A.out, nullptr);
     return check_launch();
 }
 
+template <int MODE, bool TRADES, bool HESS>
+int launch_blocked(const BlockedArgs& A, cudaStream_t st) {
+    switch (g_cfg) {
+        case 0: return launch_cfg<Cfg0, MODE, TRADES, HESS>(A, st);
+        case 2: return launch_cfg<Cfg2, MODE, TRADES, HESS>(A, st);
+        default: return launch_cfg<Cfg1, MODE, TRADES, HESS>(A, st);
+    }
+}
+
+int cfg_P() { return g_cfg == 0 ? Cfg0::P : Cfg1::P; }
+
 int fill_args(const cfmm_blocked_pairs* b, BlockedArgs& A) {
     if (!b) return CFMM_E_NULL;
-    if (b->pools_per_tile != kP) return CFMM_E_KIND;
-    if (b->n_tiles < 0 || b->n_pools < 0 || b->n_pools > b->n_tiles * (int64_t)kP) return CFMM_E_SIZE;
-    if (b->n_tiles > 0 && (!b->lid || !b->ent || !b->rows || !b->tok || !b->desc)) return CFMM_E_NULL;
+    if (b->pools_per_tile != cfg_P()) return CFMM_E_KIND;
+    const int64_t P = b->pools_per_tile;
+    if (b->n_tiles < 0 || b->n_pools < 0 || b->n_pools > b->n_tiles * P) return CFMM_E_SIZE;
+    if (b->n_tiles > 0 && (!b->lid || !b->ent || !b->rows || !b->tok || !b->desc || !b->partial || !b->seg ||
+                           !b->pos)) return CFMM_E_NULL;
+    if (b->n_seg < 0) return CFMM_E_SIZE;
     A.n_tiles = b->n_tiles;
-    A.M = b->n_tiles * (int64_t)kP;
+    A.M = b->n_tiles * P;
     A.lid = b->lid; A.ent = b->ent; A.rows = b->rows; A.tok = b->tok;
     A.desc = reinterpret_cast<const int2*>(b->desc);
+    A.partial = b->partial; A.n_seg = (int)b->n_seg; A.seg = reinterpret_cast<const int4*>(b->seg); A.pos = b->pos;
+    A.n_out = 0;
     A.slab[0] = A.slab[1] = A.slab[2] = nullptr;
     A.vec = nullptr; A.out = nullptr; A.arb = nullptr; A.delta = A.lambda = A.hcoef = nullptr;
+    A.dbg = g_dbg;
     return CFMM_OK;
 }
 
@@ -232,10 +321,18 @@ int fill_args(const cfmm_blocked_pairs* b, BlockedArgs& A) {
 extern "C" {
 
 int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int32_t* tok_stride, int32_t* row_cap) {
-    if (pools_per_tile) *pools_per_tile = kP;
-    if (rows_stride) *rows_stride = BlockedCfg<kP>::kRowsMax;
-    if (tok_stride) *tok_stride = BlockedCfg<kP>::kTokMax;
+    const int P = cfg_P();
+    if (pools_per_tile) *pools_per_tile = P;
+    if (rows_stride) *rows_stride = P + 2 * P / 32 + 8;
+    if (tok_stride) *tok_stride = P;
     if (row_cap) *row_cap = 32;
+    return CFMM_OK;
+}
+
+int cfmm_set_blocked_config(int32_t cfg) {
+    if (cfg >= 100) { g_dbg = cfg - 100; return CFMM_OK; }      // measurement-only phase switches
+    if (cfg < 0 || cfg > 2) return CFMM_E_KIND;
+    g_cfg = cfg;
     return CFMM_OK;
 }
 
@@ -250,6 +347,8 @@ int cfmm_blocked_eval(const cfmm_blocked_pairs* b, int32_t n_tokens, const doubl
     if (!b->r0 || !b->r1 || !b->gamma_inv) return CFMM_E_NULL;
     A.slab[0] = b->r0; A.slab[1] = b->r1; A.slab[2] = b->gamma_inv;
     A.vec = nu; A.out = psi; A.arb = arb;
+    A.n_out = (arb == psi + n_tokens) ? n_tokens + 1 : n_tokens;
+    if (A.n_out == n_tokens) cudaMemsetAsync(arb, 0, sizeof(double), static_cast<cudaStream_t>(stream));
     const bool trades = out && out->delta && out->lambda;
     const bool hess = out && out->hcoef;
     if (trades) { A.delta = out->delta; A.lambda = out->lambda; }
@@ -269,7 +368,7 @@ int cfmm_blocked_hvp(const cfmm_blocked_pairs* b, int32_t n_tokens, const double
     if (n_tokens <= 0) return CFMM_E_SIZE;
     if (!hcoef || !vt || !y) return CFMM_E_NULL;
     if (b->n_tiles == 0) return CFMM_OK;
-    A.slab[0] = hcoef; A.vec = vt; A.out = y;
+    A.slab[0] = hcoef; A.vec = vt; A.out = y; A.n_out = n_tokens;
     return launch_blocked<1, false, false>(A, static_cast<cudaStream_t>(stream));
 }
 
@@ -280,7 +379,7 @@ int cfmm_blocked_diag(const cfmm_blocked_pairs* b, int32_t n_tokens, const doubl
     if (n_tokens <= 0) return CFMM_E_SIZE;
     if (!hcoef || !diag) return CFMM_E_NULL;
     if (b->n_tiles == 0) return CFMM_OK;
-    A.slab[0] = hcoef; A.out = diag;
+    A.slab[0] = hcoef; A.out = diag; A.n_out = n_tokens;
     return launch_blocked<2, false, false>(A, static_cast<cudaStream_t>(stream));
 }
 

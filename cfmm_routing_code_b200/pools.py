@@ -240,17 +240,37 @@ def build_blocked_pairs(idx: torch.Tensor, n_tokens: int, P: int, rows_stride: i
     g_start = torch.cumsum(counts, 0) - counts
     row_tile = u_tile[row_u]
     row_start = g_start[row_u] + row_cap * sub - 2 * P * row_tile
+    row_len = torch.clamp(counts[row_u] - row_cap * sub, max=row_cap)
+    # longest rows first inside each tile: the 32 rows a warp sums have (nearly) equal trip counts
+    srt = torch.argsort(row_tile * 64 + (63 - row_len), stable=True)
+    row_tile, row_start, row_len, row_ltok = row_tile[srt], row_start[srt], row_len[srt], ltok_u[row_u][srt]
     nrow = torch.bincount(row_tile, minlength=ntiles)
     r_local = torch.arange(n_rows, **i64) - (torch.cumsum(nrow, 0) - nrow)[row_tile]
-    if int(nrow.max()) + 1 > rows_stride:
+    if int(nrow.max()) > rows_stride:
         raise _lib.CfmmError("blocked layout: row table overflow (library/builder mismatch)")
     rows = torch.zeros((ntiles, rows_stride), dtype=torch.int32, device=dev)
-    rows[row_tile, r_local] = (row_start | (ltok_u[row_u] << 16)).to(torch.int32)
-    pools_in_tile = torch.full((ntiles,), P, **i64)
-    pools_in_tile[-1] = mm - (ntiles - 1) * P
-    rows[torch.arange(ntiles, **i64), nrow] = (2 * pools_in_tile).to(torch.int32)     # closing sentinel
+    word = row_start | (row_len << 16) | (row_ltok << 22)          # start:16 | len:6 | ltok:10 (may set bit 31)
+    rows[row_tile, r_local] = torch.where(word >= 2 ** 31, word - 2 ** 32, word).to(torch.int32)
     desc = torch.stack([ntok, nrow], 1).to(torch.int32).contiguous()
-    tables = dict(n_tiles=ntiles, M=M, lid=lid, tok=tok, ent=ent, rows=rows, desc=desc,
+    # second pass (k_token_reduce): rows grouped by global token, cut into segments of <= seg_cap rows
+    seg_cap = 1024
+    row_gtok = (uniq - u_tile * n_tokens)[row_u][srt]
+    by_tok = torch.argsort(row_gtok, stable=True)
+    pos = (row_tile * rows_stride + r_local)[by_tok].to(torch.int32).contiguous()
+    tcount = torch.bincount(row_gtok, minlength=n_tokens)
+    tbegin = torch.cumsum(tcount, 0) - tcount
+    toks = torch.nonzero(tcount, as_tuple=False)[:, 0]
+    nseg_t = (tcount[toks] + seg_cap - 1) // seg_cap
+    seg_tok = torch.repeat_interleave(toks, nseg_t)
+    ssub = torch.arange(seg_tok.numel(), **i64) - (torch.cumsum(nseg_t, 0) - nseg_t)[
+        torch.repeat_interleave(torch.arange(toks.numel(), **i64), nseg_t)]
+    sbeg = tbegin[seg_tok] + seg_cap * ssub
+    send = torch.minimum(sbeg + seg_cap, tbegin[seg_tok] + tcount[seg_tok])
+    smulti = (torch.repeat_interleave(nseg_t, nseg_t) > 1).to(torch.int64)
+    seg = torch.stack([seg_tok, sbeg, send, smulti], 1).to(torch.int32).contiguous()
+    partial = torch.zeros(ntiles * rows_stride, dtype=torch.float64, device=dev)
+    tables = dict(n_tiles=ntiles, M=M, lid=lid, tok=tok, ent=ent, rows=rows, desc=desc, pos=pos, seg=seg,
+                  partial=partial, n_seg=int(seg.shape[0]),
                   rows_per_pool=n_rows / mm, tok_per_tile=float(ntok.double().mean()))
     return order, residual, tables
 
@@ -291,7 +311,9 @@ class BlockedBucket:
         self.gamma_inv = slab(1.0 / hp.gamma[self.sel], 1.0)
         self.c_blocked = _lib.BlockedPairs(self.m, t["n_tiles"], P, 0, self.r0.data_ptr(), self.r1.data_ptr(),
                                            self.gamma_inv.data_ptr(), t["lid"].data_ptr(), t["ent"].data_ptr(),
-                                           t["rows"].data_ptr(), t["tok"].data_ptr(), t["desc"].data_ptr())
+                                           t["rows"].data_ptr(), t["tok"].data_ptr(), t["desc"].data_ptr(),
+                                           t["partial"].data_ptr(), t["n_seg"], t["seg"].data_ptr(),
+                                           t["pos"].data_ptr())
 
     def bytes_resident(self) -> int:
         if self.tables is None:
@@ -339,6 +361,10 @@ class PoolStore:
                     self.buckets.append(DeviceBucket(hp, dict(s, sel=s["sel"][r], off=s["off"][:, r]), self.device))
             else:
                 self.buckets.append(DeviceBucket(hp, s, self.device))
+        # blocked buckets OVERWRITE their output vector, so they must come first (at most one per store)
+        self.buckets.sort(key=lambda b: 0 if getattr(b, "blocked", False) else 1)
+        self._blocked_first = bool(self.buckets) and getattr(self.buckets[0], "blocked", False)
+        assert sum(1 for b in self.buckets if getattr(b, "blocked", False)) <= 1
         self.m_local = sum(b.m for b in self.buckets)
         self.has_sum = bool(np.any(hp.kind == KIND_SUM_HOST))
         self.has_geomean = any(b.kind == _lib.KIND_GEOMEAN for b in self.buckets)
@@ -368,7 +394,8 @@ class PoolStore:
         """psi(nu) (n_tokens) and arb(nu) (1) for this rank's pools, as views into one (n+1) buffer."""
         st = self._stream()
         acc = self._acc
-        _lib.check(self.lib.cfmm_zero(acc.data_ptr(), acc.numel() * 8, st), "cfmm_zero")
+        if not self._blocked_first:       # a blocked bucket zeroes and overwrites [psi | arb] itself
+            _lib.check(self.lib.cfmm_zero(acc.data_ptr(), acc.numel() * 8, st), "cfmm_zero")
         lognu = torch.log(nu) if self.has_geomean else None
         for b in self.buckets:
             out = b.out_struct(trades, hess) if (trades or hess) else None
@@ -389,7 +416,8 @@ class PoolStore:
     def hvp(self, vt: torch.Tensor) -> torch.Tensor:
         st = self._stream()
         y = self._y
-        _lib.check(self.lib.cfmm_zero(y.data_ptr(), y.numel() * 8, st), "cfmm_zero")
+        if not self._blocked_first:
+            _lib.check(self.lib.cfmm_zero(y.data_ptr(), y.numel() * 8, st), "cfmm_zero")
         for b in self.buckets:
             if getattr(b, "blocked", False):
                 _lib.check(self.lib.cfmm_blocked_hvp(C.byref(b.c_blocked), self.n_tokens, b.hcoef.data_ptr(),

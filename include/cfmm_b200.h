@@ -106,18 +106,28 @@ typedef struct cfmm_blocked_pairs {
     const double* gamma_inv;  /* [n_tiles*P] 1 / fees[i]                              arbitrage.py:22-28 */
     const uint32_t* lid;      /* [n_tiles*P] tile-local token ids: slot0 | slot1 << 16                   */
     const uint16_t* ent;      /* [n_tiles][2P] row-ordered entries: local_pool << 1 | slot               */
-    const uint32_t* rows;     /* [n_tiles][rows_stride] row start | local token << 16, + closing sentinel */
+    const uint32_t* rows;     /* [n_tiles][rows_stride] start:16 | length:6 | local token:10, longest rows first */
     const int32_t* tok;       /* [n_tiles][tok_stride] local token id -> global token id                 */
     const int32_t* desc;      /* [n_tiles][2] (ntok, nrow)                                               */
+    double* partial;          /* [n_tiles][rows_stride] scratch: row sums of the last call               */
+    int64_t n_seg;            /* token segments of the second (per-token) reduction pass                 */
+    const int32_t* seg;       /* [n_seg][4] (token, begin, end, multi) into pos                          */
+    const int32_t* pos;       /* [total rows] positions into partial, grouped by token                   */
 } cfmm_blocked_pairs;
 
 int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int32_t* tok_stride, int32_t* row_cap);
+/* tuning: 0 = 1024-pool tiles / 2-stage ring, 1 = 512-pool tiles / 4-stage ring (default), 2 = 512 / 2-stage / 4 CTAs per SM.
+ * Layouts must be (re)built after changing it. */
+int cfmm_set_blocked_config(int32_t cfg);
 
-/* Same contract as cfmm_arb_eval for a blocked constant-product bucket (psi/arb accumulate).  Per-pool outputs
+/* Evaluation of a blocked constant-product bucket.  UNLIKE cfmm_arb_eval this call OVERWRITES psi[0..n_tokens) and
+ * arb[0] (it zeroes them itself, then fills them by a deterministic two-pass reduction: per-tile row sums, then
+ * per-token sums; no floating-point atomics unless a token has more than 1024 rows), so it must be the FIRST bucket
+ * evaluated into a psi buffer; cfmm_arb_eval calls for other buckets then accumulate on top.  Per-pool outputs
  * (delta/lambda [2][n_tiles*P], hcoef [n_tiles*P]) are in BLOCKED order. */
 int cfmm_blocked_eval(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* nu, double* psi, double* arb,
                       const cfmm_eval_out* out, void* stream);
-/* y += Hs vt and diag += diag(Hs) for a blocked bucket, hcoef in blocked order. */
+/* y = Hs vt and diag = diag(Hs) for a blocked bucket (OVERWRITE, same two-pass reduction), hcoef in blocked order. */
 int cfmm_blocked_hvp(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* hcoef, const double* vt, double* y,
                      void* stream);
 int cfmm_blocked_diag(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* hcoef, double* diag, void* stream);

@@ -11,10 +11,12 @@ import cfmm_routing_code_b200 as cf
 from cfmm_routing_code_b200 import instances as I
 
 dev = "cuda"
-m, n = 1_000_000, 4096
+m, n = int(os.environ.get('M_POOLS', 1_000_000)), 4096
 ninst = 8
 stores = []
 LAYOUT = os.environ.get("LAYOUT", "blocked")
+from cfmm_routing_code_b200 import _lib as _L
+_L.load().cfmm_set_blocked_config(int(os.environ.get("BLOCKED_CFG", "1")))
 for k in range(ninst):
     s = I.synth_const_product(m, n, seed=3 + k)
     hp = cf.HostPools.from_pairs(n, s["idx"], s["reserves"], s["gamma"])
@@ -55,13 +57,14 @@ def graph_time(fn, reps=64, replays=5):
 
 modes = [int(x) for x in sys.argv[1:]] or [0]
 for mode in modes:
-    lib.cfmm_set_scatter_mode(mode)
+    lib.cfmm_set_scatter_mode(0)
+    lib.cfmm_set_blocked_config(100 + mode)      # mode = debug phase mask here
     for label, kw in (("eval", {}), ("eval+hess", dict(hess=True))):
         t_rot = graph_time(lambda i: stores[i % ninst][0].evaluate(nus[i % ninst], **kw))
         t_hot = graph_time(lambda i: stores[0][0].evaluate(nus[0], **kw))
         print(f"mode {mode:2d} {label:12s} rotating {t_rot*1e6:8.1f} us  {m/t_rot/1e9:7.2f} Gpool/s  "
               f"{32*m/t_rot/1e9:7.0f} GB/s | L2-hot {t_hot*1e6:8.1f} us {32*m/t_hot/1e9:7.0f} GB/s", flush=True)
-lib.cfmm_set_scatter_mode(0)
+lib.cfmm_set_blocked_config(100)
 st = stores[0][0]
 st.evaluate(nus[0], hess=True)
 v = torch.randn(n, dtype=torch.float64, device=dev)
