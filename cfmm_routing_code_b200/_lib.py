@@ -77,7 +77,7 @@ def load(build_if_missing: bool = True):
     lib.cfmm_hvp.argtypes = [C.POINTER(Bucket), i32, vp, vp, vp, vp, vp]
     lib.cfmm_hess_diag.argtypes = [C.POINTER(Bucket), i32, vp, vp, vp, vp]
     lib.cfmm_hess_dense.argtypes = [C.POINTER(Bucket), i32, vp, vp, vp, vp]
-    lib.cfmm_blocked_layout_info.argtypes = [C.POINTER(i32)] * 4
+    lib.cfmm_blocked_layout_info.argtypes = [C.POINTER(i32)] * 5
     lib.cfmm_blocked_layout_info.restype = C.c_int
     lib.cfmm_set_blocked_config.argtypes = [i32]
     lib.cfmm_set_blocked_config.restype = C.c_int

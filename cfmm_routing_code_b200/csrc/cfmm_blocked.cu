@@ -27,6 +27,9 @@ struct BlockedCfg {
     // plain bucket), so rows <= P + 2P/32 (every token one row, plus one extra row per 32 entries)
     static constexpr int kTokMax = P;
     static constexpr int kRowsMax = P + 2 * P / 32 + 8;
+    // rows are padded to multiples of 4 entries (pad code kZeroSlot reads a 0.0), so <= 2P + 3 per row
+    static constexpr int kEntMax = (2 * P + 3 * kRowsMax + 7) / 8 * 8;
+    static constexpr int kZeroSlot = 2 * P;
 };
 
 // one ring stage: NF per-pool f64 slabs + local ids + row entries + row table + token list
@@ -34,8 +37,8 @@ template <int P, int NF>
 struct __align__(128) Stage {
     double a[NF][P];
     uint32_t lid[P];                              // lid0 | lid1 << 16
-    uint16_t ent[2 * P];                          // row-ordered: local_pool << 1 | slot
-    uint32_t rows[BlockedCfg<P>::kRowsMax];       // start:16 | length:6 | local token:10
+    uint16_t ent[BlockedCfg<P>::kEntMax];         // row-ordered, rows padded to 4: local_pool << 1 | slot
+    uint32_t rows[BlockedCfg<P>::kRowsMax];       // start/4 :16 | groups of 4 entries :6 | local token :10
     int32_t tok[BlockedCfg<P>::kTokMax];          // local token id -> global token id
 };
 
@@ -47,7 +50,7 @@ struct BlockedArgs {
     const uint16_t* ent;          // [n_tiles][2P]
     const uint32_t* rows;         // [n_tiles][kRowsMax]
     const int32_t* tok;           // [n_tiles][kTokMax]
-    const int2* desc;             // [n_tiles] (ntok, nrow)
+    const int4* desc;             // [n_tiles] (ntok, nrow, entry groups of 4, 0)
     const double* vec;            // nu (eval) or vt (hvp); unused for diag
     double* out;                  // psi / y / diag: zeroed by this kernel, filled by k_token_reduce
     int n_out;                    // entries of `out` to zero (n_tokens, +1 for arb in eval mode)
@@ -66,14 +69,15 @@ __device__ __forceinline__ unsigned round16(unsigned bytes) { return (bytes + 15
 
 template <int P, int NF>
 __device__ __forceinline__ void issue_tile(Stage<P, NF>* st, uint64_t* bar, const BlockedArgs& A, long long tile) {
-    const int2 d = __ldg(A.desc + tile);
+    const int4 d = __ldg(A.desc + tile);
     const unsigned rows_b = round16(4u * (unsigned)d.y);
     const unsigned tok_b = round16(4u * (unsigned)d.x);
-    mbar_expect_tx(bar, (unsigned)(NF * P * 8 + P * 4 + 2 * P * 2) + rows_b + tok_b);
+    const unsigned ent_b = round16(8u * (unsigned)d.z);
+    mbar_expect_tx(bar, (unsigned)(NF * P * 8 + P * 4) + ent_b + rows_b + tok_b);
 #pragma unroll
     for (int k = 0; k < NF; ++k) bulk_g2s(st->a[k], A.slab[k] + tile * P, P * 8, bar);
     bulk_g2s(st->lid, A.lid + tile * P, P * 4, bar);
-    bulk_g2s(st->ent, A.ent + tile * (2 * P), 2 * P * 2, bar);
+    bulk_g2s(st->ent, A.ent + tile * BlockedCfg<P>::kEntMax, ent_b, bar);
     bulk_g2s(st->rows, A.rows + tile * BlockedCfg<P>::kRowsMax, rows_b, bar);
     bulk_g2s(st->tok, A.tok + tile * BlockedCfg<P>::kTokMax, tok_b, bar);
 }
@@ -115,8 +119,8 @@ struct EvalOp {
 
 // row word: start (16 bits) | length (6 bits, 1..32) | local token (10 bits).  Rows of a tile are sorted by
 // decreasing length by the builder, so the 32 rows of a warp have (nearly) equal trip counts.
-__device__ __forceinline__ int row_start(uint32_t r) { return (int)(r & 0xffffu); }
-__device__ __forceinline__ int row_len(uint32_t r) { return (int)((r >> 16) & 0x3fu); }
+__device__ __forceinline__ int row_start4(uint32_t r) { return (int)(r & 0xffffu); }
+__device__ __forceinline__ int row_groups(uint32_t r) { return (int)((r >> 16) & 0x3fu); }
 __device__ __forceinline__ int row_tok(uint32_t r) { return (int)(r >> 22); }
 
 template <int P, int THREADS, int STAGES, int MODE /*0 eval, 1 hvp, 2 diag*/, bool TRADES, bool HESS>
@@ -127,7 +131,8 @@ k_blocked(const BlockedArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     St* stages = reinterpret_cast<St*>(smem_raw);
     double* nul0 = reinterpret_cast<double*>(smem_raw + (size_t)STAGES * sizeof(St));    // [2][P]  nu_local, double buffered
-    double* f0buf = nul0 + 2 * P;                                                         // [2][2P] flows, double buffered
+    double* f0buf = nul0 + 2 * P;                                                         // [2][2P+4] flows (+ zero slot)
+    constexpr int FS = 2 * P + 4;
     __shared__ uint64_t full[STAGES];
     __shared__ double part[THREADS / 32];
     const int tid = threadIdx.x;
@@ -143,6 +148,7 @@ k_blocked(const BlockedArgs A) {
         }
     }
     for (int j = blockIdx.x * THREADS + tid; j < A.n_out; j += gridDim.x * THREADS) A.out[j] = 0.0;
+    if (tid < 8) f0buf[(tid >> 2) * FS + 2 * P + (tid & 3)] = 0.0;       // the zero slots padding entries point at
     double acc = 0.0;
     int stage = 0, pstage = 0, buf = 0;
     unsigned parity = 0;
@@ -150,7 +156,7 @@ k_blocked(const BlockedArgs A) {
     if ((long long)blockIdx.x < A.n_tiles) {
         mbar_wait(&full[0], 0);
         if (MODE != 2) {
-            const int ntok = __ldg(A.desc + blockIdx.x).x;
+            const int ntok = __ldg(A.desc + blockIdx.x).x;   
             for (int t = tid; t < ntok; t += THREADS) nul0[t] = __ldg(A.vec + stages[0].tok[t]);
         }
     }
@@ -163,7 +169,7 @@ k_blocked(const BlockedArgs A) {
         const int nrow = __ldg(A.desc + tile).y;
         St& S = stages[stage];
         const double* nul = nul0 + buf * P;
-        double* f = f0buf + buf * 2 * P;
+        double* f = f0buf + buf * FS;
         // ---- pool phase
 #pragma unroll
         for (int l = tid; l < P; l += THREADS) {
@@ -207,14 +213,21 @@ k_blocked(const BlockedArgs A) {
         // ---- row phase: one thread per row, fixed summation order, one red.add per row
         for (int r = tid; r < ((A.dbg & 1) ? 0 : nrow); r += THREADS) {
             const uint32_t rw = S.rows[r];
-            const uint16_t* e = S.ent + row_start(rw);
-            const int len = row_len(rw);
+            const uint2* e4 = reinterpret_cast<const uint2*>(S.ent) + row_start4(rw);
+            const int ng = row_groups(rw);
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            int k = 0;
-            for (; k + 4 <= len; k += 4) {
-                s0 += f[e[k]]; s1 += f[e[k + 1]]; s2 += f[e[k + 2]]; s3 += f[e[k + 3]];
+            int g = 0;
+            for (; g + 2 <= ng; g += 2) {          // 8 independent shared-memory loads in flight
+                const uint2 a = e4[g], b = e4[g + 1];
+                const double v0 = f[a.x & 0xffffu], v1 = f[a.x >> 16], v2 = f[a.y & 0xffffu], v3 = f[a.y >> 16];
+                const double v4 = f[b.x & 0xffffu], v5 = f[b.x >> 16], v6 = f[b.y & 0xffffu], v7 = f[b.y >> 16];
+                s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+                s0 += v4; s1 += v5; s2 += v6; s3 += v7;
             }
-            for (; k < len; ++k) s0 += f[e[k]];
+            if (g < ng) {
+                const uint2 a = e4[g];
+                s0 += f[a.x & 0xffffu]; s1 += f[a.x >> 16]; s2 += f[a.y & 0xffffu]; s3 += f[a.y >> 16];
+            }
             A.partial[tile * BlockedCfg<P>::kRowsMax + r] = (s0 + s1) + (s2 + s3);
         }
         first = false;
@@ -266,7 +279,7 @@ template <class C, int MODE, bool TRADES, bool HESS>
 int launch_cfg(const BlockedArgs& A, cudaStream_t st) {
     constexpr int NF = (MODE == 0) ? 3 : 1;
     auto kern = k_blocked<C::P, C::T, C::S, MODE, TRADES, HESS>;
-    const size_t sm = (size_t)C::S * sizeof(Stage<C::P, NF>) + (size_t)6 * C::P * sizeof(double);
+    const size_t sm = (size_t)C::S * sizeof(Stage<C::P, NF>) + (size_t)(6 * C::P + 8) * sizeof(double);
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -307,7 +320,7 @@ int fill_args(const cfmm_blocked_pairs* b, BlockedArgs& A) {
     A.n_tiles = b->n_tiles;
     A.M = b->n_tiles * P;
     A.lid = b->lid; A.ent = b->ent; A.rows = b->rows; A.tok = b->tok;
-    A.desc = reinterpret_cast<const int2*>(b->desc);
+    A.desc = reinterpret_cast<const int4*>(b->desc);
     A.partial = b->partial; A.n_seg = (int)b->n_seg; A.seg = reinterpret_cast<const int4*>(b->seg); A.pos = b->pos;
     A.n_out = 0;
     A.slab[0] = A.slab[1] = A.slab[2] = nullptr;
@@ -320,12 +333,15 @@ int fill_args(const cfmm_blocked_pairs* b, BlockedArgs& A) {
 
 extern "C" {
 
-int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int32_t* tok_stride, int32_t* row_cap) {
+int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int32_t* tok_stride, int32_t* row_cap,
+                             int32_t* ent_stride) {
     const int P = cfg_P();
+    const int rows = P + 2 * P / 32 + 8;
     if (pools_per_tile) *pools_per_tile = P;
-    if (rows_stride) *rows_stride = P + 2 * P / 32 + 8;
+    if (rows_stride) *rows_stride = rows;
     if (tok_stride) *tok_stride = P;
     if (row_cap) *row_cap = 32;
+    if (ent_stride) *ent_stride = (2 * P + 3 * rows + 7) / 8 * 8;
     return CFMM_OK;
 }
 

@@ -174,12 +174,13 @@ class DeviceBucket:
 
 
 def blocked_layout_info(lib):
-    v = [C.c_int32() for _ in range(4)]
+    v = [C.c_int32() for _ in range(5)]
     _lib.check(lib.cfmm_blocked_layout_info(*[C.byref(x) for x in v]), "cfmm_blocked_layout_info")
-    return tuple(int(x.value) for x in v)      # pools_per_tile, rows_stride, tok_stride, row_cap
+    return tuple(int(x.value) for x in v)      # pools_per_tile, rows_stride, tok_stride, row_cap, ent_stride
 
 
-def build_blocked_pairs(idx: torch.Tensor, n_tokens: int, P: int, rows_stride: int, tok_stride: int, row_cap: int):
+def build_blocked_pairs(idx: torch.Tensor, n_tokens: int, P: int, rows_stride: int, tok_stride: int, row_cap: int,
+                        ent_stride: int):
     """Layout builder for cfmm_blocked_pairs (see csrc/cfmm_blocked.cu).  idx: (2, m) int64 token ids on the
     device.  Pools are sorted by (token block of slot 0, token block of slot 1) and cut into tiles of P; each
     tile gets its distinct-token list, 16-bit local ids, and a CSR of rows (token, <= row_cap entries).
@@ -230,28 +231,39 @@ def build_blocked_pairs(idx: torch.Tensor, n_tokens: int, P: int, rows_stride: i
     lid[:mm] = (he_ltok[:mm] | (he_ltok[mm:] << 16)).to(torch.int32)
     tok = torch.zeros((ntiles, tok_stride), dtype=torch.int32, device=dev)
     tok[u_tile, ltok_u] = (uniq - u_tile * n_tokens).to(torch.int32)
-    ent = torch.zeros(ntiles * 2 * P, dtype=torch.int16, device=dev)
-    # every tile but the last holds exactly 2P half-edges, so the sorted order IS the per-tile layout
-    ent[:2 * mm] = he_code[perm].to(torch.int16)
     nsub = (counts + row_cap - 1) // row_cap
     n_rows = int(nsub.sum())
+    first_row_u = torch.cumsum(nsub, 0) - nsub
     row_u = torch.repeat_interleave(torch.arange(U, **i64), nsub)
-    sub = torch.arange(n_rows, **i64) - (torch.cumsum(nsub, 0) - nsub)[row_u]
+    sub = torch.arange(n_rows, **i64) - first_row_u[row_u]
     g_start = torch.cumsum(counts, 0) - counts
-    row_tile = u_tile[row_u]
-    row_start = g_start[row_u] + row_cap * sub - 2 * P * row_tile
-    row_len = torch.clamp(counts[row_u] - row_cap * sub, max=row_cap)
+    row_tile0 = u_tile[row_u]
+    row_len0 = torch.clamp(counts[row_u] - row_cap * sub, max=row_cap)
     # longest rows first inside each tile: the 32 rows a warp sums have (nearly) equal trip counts
-    srt = torch.argsort(row_tile * 64 + (63 - row_len), stable=True)
-    row_tile, row_start, row_len, row_ltok = row_tile[srt], row_start[srt], row_len[srt], ltok_u[row_u][srt]
+    srt = torch.argsort(row_tile0 * 64 + (63 - row_len0), stable=True)
+    rank = torch.empty_like(srt); rank[srt] = torch.arange(n_rows, **i64)     # old row id -> sorted position
+    row_tile, row_len, row_ltok = row_tile0[srt], row_len0[srt], ltok_u[row_u][srt]
     nrow = torch.bincount(row_tile, minlength=ntiles)
-    r_local = torch.arange(n_rows, **i64) - (torch.cumsum(nrow, 0) - nrow)[row_tile]
+    row_first = torch.cumsum(nrow, 0) - nrow
+    r_local = torch.arange(n_rows, **i64) - row_first[row_tile]
     if int(nrow.max()) > rows_stride:
         raise _lib.CfmmError("blocked layout: row table overflow (library/builder mismatch)")
+    # entries: every row padded to a multiple of 4 (pad code 2P -> a shared-memory zero slot)
+    row_ng = (row_len + 3) // 4
+    cs = torch.cumsum(row_ng, 0) - row_ng
+    row_start4 = cs - cs[row_first][row_tile]                                   # in groups of 4, per tile
+    ngroups = torch.zeros(ntiles, **i64).index_add_(0, row_tile, row_ng)
+    if int(ngroups.max()) * 4 > ent_stride:
+        raise _lib.CfmmError("blocked layout: entry table overflow (library/builder mismatch)")
+    ent = torch.full((ntiles * ent_stride,), 2 * P, dtype=torch.int16, device=dev)
+    he_o = torch.arange(2 * mm, **i64) - g_start[inv]                           # offset inside its token group
+    he_row = rank[first_row_u[inv] + he_o // row_cap]                           # sorted row id of each half-edge
+    dest = row_tile[he_row] * ent_stride + 4 * row_start4[he_row] + he_o % row_cap
+    ent[dest] = he_code[perm].to(torch.int16)
     rows = torch.zeros((ntiles, rows_stride), dtype=torch.int32, device=dev)
-    word = row_start | (row_len << 16) | (row_ltok << 22)          # start:16 | len:6 | ltok:10 (may set bit 31)
+    word = row_start4 | (row_ng << 16) | (row_ltok << 22)          # start/4:16 | groups:6 | ltok:10 (may set bit 31)
     rows[row_tile, r_local] = torch.where(word >= 2 ** 31, word - 2 ** 32, word).to(torch.int32)
-    desc = torch.stack([ntok, nrow], 1).to(torch.int32).contiguous()
+    desc = torch.stack([ntok, nrow, ngroups, torch.zeros_like(ntok)], 1).to(torch.int32).contiguous()
     # second pass (k_token_reduce): rows grouped by global token, cut into segments of <= seg_cap rows
     seg_cap = 1024
     row_gtok = (uniq - u_tile * n_tokens)[row_u][srt]
@@ -283,9 +295,9 @@ class BlockedBucket:
 
     def __init__(self, hp: HostPools, spec, device, lib):
         sel, off = spec["sel"], spec["off"]
-        P, rows_stride, tok_stride, row_cap = blocked_layout_info(lib)
+        P, rows_stride, tok_stride, row_cap, ent_stride = blocked_layout_info(lib)
         idx = torch.as_tensor(hp.tok_idx[off].astype(np.int64), device=device)
-        order, residual, t = build_blocked_pairs(idx, hp.n_tokens, P, rows_stride, tok_stride, row_cap)
+        order, residual, t = build_blocked_pairs(idx, hp.n_tokens, P, rows_stride, tok_stride, row_cap, ent_stride)
         self.residual = residual.cpu().numpy()           # bucket-local indices left for a plain bucket
         order_h = order.cpu().numpy()
         self.sel = sel[order_h]

@@ -105,17 +105,19 @@ typedef struct cfmm_blocked_pairs {
     const double* r1;         /* [n_tiles*P] reserves of slot 1                                          */
     const double* gamma_inv;  /* [n_tiles*P] 1 / fees[i]                              arbitrage.py:22-28 */
     const uint32_t* lid;      /* [n_tiles*P] tile-local token ids: slot0 | slot1 << 16                   */
-    const uint16_t* ent;      /* [n_tiles][2P] row-ordered entries: local_pool << 1 | slot               */
-    const uint32_t* rows;     /* [n_tiles][rows_stride] start:16 | length:6 | local token:10, longest rows first */
+    const uint16_t* ent;      /* [n_tiles][ent_stride] row-ordered entries (local_pool << 1 | slot), each row
+                                 padded to a multiple of 4 with the zero-slot code 2P                     */
+    const uint32_t* rows;     /* [n_tiles][rows_stride] start/4 :16 | 4-entry groups :6 | local token :10, longest first */
     const int32_t* tok;       /* [n_tiles][tok_stride] local token id -> global token id                 */
-    const int32_t* desc;      /* [n_tiles][2] (ntok, nrow)                                               */
+    const int32_t* desc;      /* [n_tiles][4] (ntok, nrow, 4-entry groups, 0)                            */
     double* partial;          /* [n_tiles][rows_stride] scratch: row sums of the last call               */
     int64_t n_seg;            /* token segments of the second (per-token) reduction pass                 */
     const int32_t* seg;       /* [n_seg][4] (token, begin, end, multi) into pos                          */
     const int32_t* pos;       /* [total rows] positions into partial, grouped by token                   */
 } cfmm_blocked_pairs;
 
-int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int32_t* tok_stride, int32_t* row_cap);
+int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int32_t* tok_stride, int32_t* row_cap,
+                             int32_t* ent_stride);
 /* tuning: 0 = 1024-pool tiles / 2-stage ring, 1 = 512-pool tiles / 4-stage ring (default), 2 = 512 / 2-stage / 4 CTAs per SM.
  * Layouts must be (re)built after changing it. */
 int cfmm_set_blocked_config(int32_t cfg);
