@@ -38,7 +38,6 @@ class BlockedPairs(C.Structure):
         ("n_pools", C.c_int64), ("n_tiles", C.c_int64), ("pools_per_tile", C.c_int32), ("reserved", C.c_int32),
         ("r0", C.c_void_p), ("r1", C.c_void_p), ("gamma_inv", C.c_void_p), ("lid", C.c_void_p),
         ("ent", C.c_void_p), ("rows", C.c_void_p), ("tok", C.c_void_p), ("desc", C.c_void_p),
-        ("partial", C.c_void_p), ("n_seg", C.c_int64), ("seg", C.c_void_p), ("pos", C.c_void_p),
     ]
 
 
@@ -81,9 +80,9 @@ def load(build_if_missing: bool = True):
     lib.cfmm_blocked_layout_info.restype = C.c_int
     lib.cfmm_set_blocked_config.argtypes = [i32]
     lib.cfmm_set_blocked_config.restype = C.c_int
-    lib.cfmm_blocked_eval.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp, C.POINTER(EvalOut), vp]
+    lib.cfmm_blocked_eval.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp, C.POINTER(EvalOut), vp, i64, vp]
     lib.cfmm_blocked_eval.restype = C.c_int
-    lib.cfmm_blocked_hvp.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp, vp]
+    lib.cfmm_blocked_hvp.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp, vp, vp]
     lib.cfmm_blocked_hvp.restype = C.c_int
     lib.cfmm_blocked_diag.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp]
     lib.cfmm_blocked_diag.restype = C.c_int

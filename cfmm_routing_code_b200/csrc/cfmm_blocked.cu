@@ -27,8 +27,9 @@ struct BlockedCfg {
     // plain bucket), so rows <= P + 2P/32 (every token one row, plus one extra row per 32 entries)
     static constexpr int kTokMax = P;
     static constexpr int kRowsMax = P + 2 * P / 32 + 8;
-    // rows are padded to multiples of 4 entries (pad code kZeroSlot reads a 0.0), so <= 2P + 3 per row
-    static constexpr int kEntMax = (2 * P + 3 * kRowsMax + 7) / 8 * 8;
+    // rows are padded to multiples of 4 entries (pad code kZeroSlot reads a 0.0); the builder sends tiles whose
+    // padded entry list would exceed 3P to the plain bucket (typical: 2.5P)
+    static constexpr int kEntMax = 3 * P;
     static constexpr int kZeroSlot = 2 * P;
 };
 
@@ -52,16 +53,13 @@ struct BlockedArgs {
     const int32_t* tok;           // [n_tiles][kTokMax]
     const int4* desc;             // [n_tiles] (ntok, nrow, entry groups of 4, 0)
     const double* vec;            // nu (eval) or vt (hvp); unused for diag
-    double* out;                  // psi / y / diag: zeroed by this kernel, filled by k_token_reduce
-    int n_out;                    // entries of `out` to zero (n_tokens, +1 for arb in eval mode)
-    double* partial;              // [n_tiles][rows_stride] row sums (plain stores, no atomics)
+    double* out;                  // psi / y / diag (+= via one red.add per row)
+    double* zero_next;            // optional: buffer of n_zero doubles this launch clears for the NEXT call
+    int n_zero;
     double* arb;                  // eval only
     double* delta;                // eval, optional: [2][M] blocked order
     double* lambda;
     double* hcoef;                // eval, optional: [M]
-    int n_seg;                    // token segments for k_token_reduce
-    const int4* seg;              // [n_seg] (token, begin, end, multi)
-    const int* pos;               // [n_rows_total] positions into partial
     int dbg;                      // MEASUREMENT ONLY: bit0 skip row phase, bit1 skip pool math, bit2 skip nu gather
 };
 
@@ -130,16 +128,16 @@ k_blocked(const BlockedArgs A) {
     using St = Stage<P, NF>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     St* stages = reinterpret_cast<St*>(smem_raw);
-    double* nul0 = reinterpret_cast<double*>(smem_raw + (size_t)STAGES * sizeof(St));    // [2][P]  nu_local, double buffered
-    double* f0buf = nul0 + 2 * P;                                                         // [2][2P+4] flows (+ zero slot)
-    constexpr int FS = 2 * P + 4;
+    double* nul = reinterpret_cast<double*>(smem_raw + (size_t)STAGES * sizeof(St));      // [P]    nu_local
+    double* f = nul + P;                                                                   // [2P+4] flows + zero slot
     __shared__ uint64_t full[STAGES];
     __shared__ double part[THREADS / 32];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
         mbar_fence_init();
     }
+    if (tid < 4) f[2 * P + tid] = 0.0;
     __syncthreads();
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -147,37 +145,26 @@ k_blocked(const BlockedArgs A) {
             if (t < A.n_tiles) issue_tile<P, NF>(&stages[s], &full[s], A, t);
         }
     }
-    for (int j = blockIdx.x * THREADS + tid; j < A.n_out; j += gridDim.x * THREADS) A.out[j] = 0.0;
-    if (tid < 8) f0buf[(tid >> 2) * FS + 2 * P + (tid & 3)] = 0.0;       // the zero slots padding entries point at
+    // clear the buffer the NEXT call accumulates into (nobody touches it during this launch)
+    for (int j = blockIdx.x * THREADS + tid; j < A.n_zero; j += gridDim.x * THREADS) A.zero_next[j] = 0.0;
     double acc = 0.0;
-    int stage = 0, pstage = 0, buf = 0;
+    int stage = 0;
     unsigned parity = 0;
-    // prologue: nu_local of the first tile
-    if ((long long)blockIdx.x < A.n_tiles) {
-        mbar_wait(&full[0], 0);
-        if (MODE != 2) {
-            const int ntok = __ldg(A.desc + blockIdx.x).x;   
-            for (int t = tid; t < ntok; t += THREADS) nul0[t] = __ldg(A.vec + stages[0].tok[t]);
-        }
-    }
-    __syncthreads();
-    // One barrier per tile.  Iteration k: pool phase of tile k -> f[k&1]; prefetch nu_local of tile k+1;
-    // barrier; row phase of tile k.  The row phase of tile k overlaps the pool phase of tile k+1 in other
-    // warps, and its red.adds are never followed directly by a barrier.
-    bool first = true;
     for (long long tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
-        const int nrow = __ldg(A.desc + tile).y;
+        const int4 d = __ldg(A.desc + tile);           // (ntok, nrow, groups, -)
+        mbar_wait(&full[stage], parity);
         St& S = stages[stage];
-        const double* nul = nul0 + buf * P;
-        double* f = f0buf + buf * FS;
-        // ---- pool phase
+        // ---- phase 1: nu_local <- vec[tok]
+        if (MODE != 2) {
+            for (int t = tid; t < d.x; t += THREADS) nul[t] = __ldg(A.vec + S.tok[t]);
+            __syncthreads();
+        }
+        // ---- phase 2: per-pool values into f
 #pragma unroll
         for (int l = tid; l < P; l += THREADS) {
             const uint32_t li = S.lid[l];
             double f0, f1;
             if (MODE == 0) {
-                if (A.dbg & 2) { f0 = S.a[0][l]; f1 = S.a[1][l] + S.a[2][l] + nul[li & 0xffffu] + nul[li >> 16]; }
-                else
                 EvalOp::apply<TRADES, HESS>(A, tile * P + l, S.a[0][l], S.a[1][l], S.a[2][l], nul[li & 0xffffu],
                                             nul[li >> 16], f0, f1, acc);
             } else if (MODE == 1) {
@@ -189,97 +176,64 @@ k_blocked(const BlockedArgs A) {
             }
             reinterpret_cast<double2*>(f)[l] = make_double2(f0, f1);
         }
-        // ---- nu_local of the next tile into the other buffer
-        const long long nxt = tile + gridDim.x;
-        int nstage = stage + 1;
-        unsigned nparity = parity;
-        if (nstage == STAGES) { nstage = 0; nparity ^= 1u; }
-        if (nxt < A.n_tiles) {
-            mbar_wait(&full[nstage], nparity);
-            if (MODE != 2 && !(A.dbg & 4)) {
-                const int ntok = __ldg(A.desc + nxt).x;
-                double* nn = nul0 + (buf ^ 1) * P;
-                for (int t = tid; t < ntok; t += THREADS) nn[t] = __ldg(A.vec + stages[nstage].tok[t]);
-            }
-        }
-        __syncthreads();          // f of this tile complete; everybody is also done with the PREVIOUS tile's rows
-        if (tid == 0 && !first) {
-            const long long far = tile + (long long)(STAGES - 1) * gridDim.x;     // (previous tile) + STAGES strides
-            if (far < A.n_tiles) {
-                fence_proxy_async();
-                issue_tile<P, NF>(&stages[pstage], &full[pstage], A, far);
-            }
-        }
-        // ---- row phase: one thread per row, fixed summation order, one red.add per row
-        for (int r = tid; r < ((A.dbg & 1) ? 0 : nrow); r += THREADS) {
-            const uint32_t rw = S.rows[r];
-            const uint2* e4 = reinterpret_cast<const uint2*>(S.ent) + row_start4(rw);
-            const int ng = row_groups(rw);
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            int g = 0;
-            for (; g + 2 <= ng; g += 2) {          // 8 independent shared-memory loads in flight
-                const uint2 a = e4[g], b = e4[g + 1];
-                const double v0 = f[a.x & 0xffffu], v1 = f[a.x >> 16], v2 = f[a.y & 0xffffu], v3 = f[a.y >> 16];
-                const double v4 = f[b.x & 0xffffu], v5 = f[b.x >> 16], v6 = f[b.y & 0xffffu], v7 = f[b.y >> 16];
-                s0 += v0; s1 += v1; s2 += v2; s3 += v3;
-                s0 += v4; s1 += v5; s2 += v6; s3 += v7;
-            }
-            if (g < ng) {
-                const uint2 a = e4[g];
-                s0 += f[a.x & 0xffffu]; s1 += f[a.x >> 16]; s2 += f[a.y & 0xffffu]; s3 += f[a.y >> 16];
-            }
-            A.partial[tile * BlockedCfg<P>::kRowsMax + r] = (s0 + s1) + (s2 + s3);
-        }
-        first = false;
-        pstage = stage; stage = nstage; parity = nparity; buf ^= 1;
-    }
-    (void)acc; (void)part;
-}
-
-// Second pass: psi[token] = sum of that token's row sums, in a fixed order (bit-reproducible), no atomics for
-// tokens that fit one segment.  One warp per segment (<= kSegCap rows); arb += nu[token] * sum.
-constexpr int kSegCap = 1024;
-template <bool WITH_ARB>
-__global__ void __launch_bounds__(256)
-k_token_reduce(int n_seg, const int4* __restrict__ seg, const int* __restrict__ pos, const double* __restrict__ partial,
-               const double* __restrict__ nu, double* out, double* arb) {
-    __shared__ double part[8];
-    const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    double contrib = 0.0;
-    if (warp < n_seg) {
-        const int4 sg = __ldg(seg + warp);              // (token, begin, end, multi-segment flag)
-        double s = 0.0;
-        for (int k = sg.y + lane; k < sg.z; k += 32) s += partial[__ldg(pos + k)];
-        s = warp_sum(s);
-        if (lane == 0) {
-            if (sg.w) atomicAdd(out + sg.x, s); else out[sg.x] = s;
-            if (WITH_ARB) contrib = __ldg(nu + sg.x) * s;
-        }
-    }
-    if (WITH_ARB) {
-        contrib = warp_sum(contrib);
-        if (lane == 0) part[threadIdx.x >> 5] = contrib;
         __syncthreads();
-        if (threadIdx.x < 32) {
-            double t = (threadIdx.x < 8) ? part[threadIdx.x] : 0.0;
-            t = warp_sum(t);
-            if (threadIdx.x == 0 && t != 0.0) atomicAdd(arb, t);
+        // ---- phase 3, warp-autonomous: a warp owns 32 consecutive rows and the contiguous span of their
+        // 4-entry groups.  Level 1: lanes sum groups in parallel, overwriting each 8-byte group with its sum;
+        // level 2: each lane adds up the group sums of its row (fixed order) and issues one red.add.
+        if (!(A.dbg & 1))
+        for (int r0 = warp * 32; r0 < d.y; r0 += THREADS) {
+            const int r = r0 + lane;
+            const uint32_t rw = (r < d.y) ? S.rows[r] : 0u;
+            const uint32_t rwl = S.rows[min(r0 + 31, d.y - 1)];
+            const int gbeg = row_start4(S.rows[r0]), gend = row_start4(rwl) + row_groups(rwl);
+            uint2* e4 = reinterpret_cast<uint2*>(S.ent);
+            double* gs = reinterpret_cast<double*>(S.ent);
+            for (int g = gbeg + lane; g < gend; g += 32) {
+                const uint2 a = e4[g];
+                gs[g] = (f[a.x & 0xffffu] + f[a.x >> 16]) + (f[a.y & 0xffffu] + f[a.y >> 16]);
+            }
+            __syncwarp();
+            if (r < d.y) {
+                const int g0 = row_start4(rw), ng = row_groups(rw);
+                double s = gs[g0];
+                for (int k = 1; k < ng; ++k) s += gs[g0 + k];
+                if (s != 0.0) atomicAdd(A.out + S.tok[row_tok(rw)], s);
+            }
+        }
+        __syncthreads();                 // stage, nul and f are free again
+        if (tid == 0) {
+            const long long nxt = tile + (long long)STAGES * gridDim.x;
+            if (nxt < A.n_tiles) {
+                fence_proxy_async();
+                issue_tile<P, NF>(&S, &full[stage], A, nxt);
+            }
+        }
+        if (++stage == STAGES) { stage = 0; parity ^= 1u; }
+    }
+    if (MODE == 0) {
+        acc = warp_sum(acc);
+        if (lane == 0) part[warp] = acc;
+        __syncthreads();
+        if (tid < 32) {
+            double s = (tid < THREADS / 32) ? part[tid] : 0.0;
+            s = warp_sum(s);
+            if (tid == 0 && s != 0.0) atomicAdd(A.arb, s);
         }
     }
 }
 
 // ---- shipped configurations (selectable at run time for tuning; the layout must be built for the same P)
-struct Cfg0 { static constexpr int P = 1024, T = 512, S = 3, CTAS = 1; };   // 121 + 48 KB smem, one CTA per SM
-struct Cfg1 { static constexpr int P = 512, T = 512, S = 4, CTAS = 2; };    // 2 x (81 + 24) KB
-struct Cfg2 { static constexpr int P = 512, T = 256, S = 3, CTAS = 2; };    // 2 x (61 + 24) KB, 2 pools per thread
-int g_cfg = 1;
+struct Cfg0 { static constexpr int P = 1024, T = 512, S = 2, CTAS = 2; };   // 2 x (85 + 24) KB smem per SM
+struct Cfg1 { static constexpr int P = 512, T = 512, S = 3, CTAS = 2; };    // 2 x (64 + 12) KB, deeper ring
+struct Cfg2 { static constexpr int P = 512, T = 256, S = 2, CTAS = 4; };    // 4 x (43 + 12) KB
+int g_cfg = 0;
 int g_dbg = 0;
 
 template <class C, int MODE, bool TRADES, bool HESS>
 int launch_cfg(const BlockedArgs& A, cudaStream_t st) {
     constexpr int NF = (MODE == 0) ? 3 : 1;
     auto kern = k_blocked<C::P, C::T, C::S, MODE, TRADES, HESS>;
-    const size_t sm = (size_t)C::S * sizeof(Stage<C::P, NF>) + (size_t)(6 * C::P + 8) * sizeof(double);
+    const size_t sm = (size_t)C::S * sizeof(Stage<C::P, NF>) + (size_t)(3 * C::P + 4) * sizeof(double);
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -288,13 +242,6 @@ int launch_cfg(const BlockedArgs& A, cudaStream_t st) {
     const long long cap = (long long)C::CTAS * num_sms();
     const int grid = (int)(A.n_tiles < cap ? A.n_tiles : cap);
     kern<<<grid, C::T, sm, st>>>(A);
-    int rc = check_launch();
-    if (rc) return rc;
-    const int blocks = (A.n_seg * 32 + 255) / 256;
-    if (MODE == 0)
-        k_token_reduce<true><<<blocks, 256, 0, st>>>(A.n_seg, A.seg, A.pos, A.partial, A.vec, A.out, A.arb);
-    else
-        k_token_reduce<false><<<blocks, 256, 0, st>>>(A.n_seg, A.seg, A.pos, A.partial, nullptr, A.out, nullptr);
     return check_launch();
 }
 
@@ -314,15 +261,12 @@ int fill_args(const cfmm_blocked_pairs* b, BlockedArgs& A) {
     if (b->pools_per_tile != cfg_P()) return CFMM_E_KIND;
     const int64_t P = b->pools_per_tile;
     if (b->n_tiles < 0 || b->n_pools < 0 || b->n_pools > b->n_tiles * P) return CFMM_E_SIZE;
-    if (b->n_tiles > 0 && (!b->lid || !b->ent || !b->rows || !b->tok || !b->desc || !b->partial || !b->seg ||
-                           !b->pos)) return CFMM_E_NULL;
-    if (b->n_seg < 0) return CFMM_E_SIZE;
+    if (b->n_tiles > 0 && (!b->lid || !b->ent || !b->rows || !b->tok || !b->desc)) return CFMM_E_NULL;
     A.n_tiles = b->n_tiles;
     A.M = b->n_tiles * P;
     A.lid = b->lid; A.ent = b->ent; A.rows = b->rows; A.tok = b->tok;
     A.desc = reinterpret_cast<const int4*>(b->desc);
-    A.partial = b->partial; A.n_seg = (int)b->n_seg; A.seg = reinterpret_cast<const int4*>(b->seg); A.pos = b->pos;
-    A.n_out = 0;
+    A.zero_next = nullptr; A.n_zero = 0;
     A.slab[0] = A.slab[1] = A.slab[2] = nullptr;
     A.vec = nullptr; A.out = nullptr; A.arb = nullptr; A.delta = A.lambda = A.hcoef = nullptr;
     A.dbg = g_dbg;
@@ -341,7 +285,7 @@ int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int3
     if (rows_stride) *rows_stride = rows;
     if (tok_stride) *tok_stride = P;
     if (row_cap) *row_cap = 32;
-    if (ent_stride) *ent_stride = (2 * P + 3 * rows + 7) / 8 * 8;
+    if (ent_stride) *ent_stride = 3 * P;
     return CFMM_OK;
 }
 
@@ -353,7 +297,7 @@ int cfmm_set_blocked_config(int32_t cfg) {
 }
 
 int cfmm_blocked_eval(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* nu, double* psi, double* arb,
-                      const cfmm_eval_out* out, void* stream) {
+                      const cfmm_eval_out* out, double* zero_next, int64_t n_zero, void* stream) {
     BlockedArgs A;
     int rc = fill_args(b, A);
     if (rc) return rc;
@@ -363,8 +307,7 @@ int cfmm_blocked_eval(const cfmm_blocked_pairs* b, int32_t n_tokens, const doubl
     if (!b->r0 || !b->r1 || !b->gamma_inv) return CFMM_E_NULL;
     A.slab[0] = b->r0; A.slab[1] = b->r1; A.slab[2] = b->gamma_inv;
     A.vec = nu; A.out = psi; A.arb = arb;
-    A.n_out = (arb == psi + n_tokens) ? n_tokens + 1 : n_tokens;
-    if (A.n_out == n_tokens) cudaMemsetAsync(arb, 0, sizeof(double), static_cast<cudaStream_t>(stream));
+    A.zero_next = zero_next; A.n_zero = zero_next ? (int)n_zero : 0;
     const bool trades = out && out->delta && out->lambda;
     const bool hess = out && out->hcoef;
     if (trades) { A.delta = out->delta; A.lambda = out->lambda; }
@@ -377,14 +320,15 @@ int cfmm_blocked_eval(const cfmm_blocked_pairs* b, int32_t n_tokens, const doubl
 }
 
 int cfmm_blocked_hvp(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* hcoef, const double* vt, double* y,
-                     void* stream) {
+                     double* zero_next, void* stream) {
     BlockedArgs A;
     int rc = fill_args(b, A);
     if (rc) return rc;
     if (n_tokens <= 0) return CFMM_E_SIZE;
     if (!hcoef || !vt || !y) return CFMM_E_NULL;
     if (b->n_tiles == 0) return CFMM_OK;
-    A.slab[0] = hcoef; A.vec = vt; A.out = y; A.n_out = n_tokens;
+    A.slab[0] = hcoef; A.vec = vt; A.out = y;
+    A.zero_next = zero_next; A.n_zero = zero_next ? n_tokens : 0;
     return launch_blocked<1, false, false>(A, static_cast<cudaStream_t>(stream));
 }
 
@@ -395,7 +339,7 @@ int cfmm_blocked_diag(const cfmm_blocked_pairs* b, int32_t n_tokens, const doubl
     if (n_tokens <= 0) return CFMM_E_SIZE;
     if (!hcoef || !diag) return CFMM_E_NULL;
     if (b->n_tiles == 0) return CFMM_OK;
-    A.slab[0] = hcoef; A.out = diag; A.n_out = n_tokens;
+    A.slab[0] = hcoef; A.out = diag;
     return launch_blocked<2, false, false>(A, static_cast<cudaStream_t>(stream));
 }
 

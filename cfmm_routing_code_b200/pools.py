@@ -209,7 +209,10 @@ def build_blocked_pairs(idx: torch.Tensor, n_tokens: int, P: int, rows_stride: i
         uniq, inv, counts = torch.unique_consecutive(ck, return_inverse=True, return_counts=True)
         u_tile = uniq // n_tokens
         ntok = torch.bincount(u_tile, minlength=ntiles)
-        bad = ntok > tok_stride
+        rem = counts % row_cap
+        padded = (counts // row_cap) * row_cap + (rem + 3) // 4 * 4        # entries after padding rows to 4
+        nent = torch.zeros(ntiles, **i64).index_add_(0, u_tile, padded)
+        bad = (ntok > tok_stride) | (nent > ent_stride)
         if not bool(bad.any()):
             break
         if _pass == 3:                       # give up blocking: everything left goes to the plain bucket
@@ -264,25 +267,7 @@ def build_blocked_pairs(idx: torch.Tensor, n_tokens: int, P: int, rows_stride: i
     word = row_start4 | (row_ng << 16) | (row_ltok << 22)          # start/4:16 | groups:6 | ltok:10 (may set bit 31)
     rows[row_tile, r_local] = torch.where(word >= 2 ** 31, word - 2 ** 32, word).to(torch.int32)
     desc = torch.stack([ntok, nrow, ngroups, torch.zeros_like(ntok)], 1).to(torch.int32).contiguous()
-    # second pass (k_token_reduce): rows grouped by global token, cut into segments of <= seg_cap rows
-    seg_cap = 1024
-    row_gtok = (uniq - u_tile * n_tokens)[row_u][srt]
-    by_tok = torch.argsort(row_gtok, stable=True)
-    pos = (row_tile * rows_stride + r_local)[by_tok].to(torch.int32).contiguous()
-    tcount = torch.bincount(row_gtok, minlength=n_tokens)
-    tbegin = torch.cumsum(tcount, 0) - tcount
-    toks = torch.nonzero(tcount, as_tuple=False)[:, 0]
-    nseg_t = (tcount[toks] + seg_cap - 1) // seg_cap
-    seg_tok = torch.repeat_interleave(toks, nseg_t)
-    ssub = torch.arange(seg_tok.numel(), **i64) - (torch.cumsum(nseg_t, 0) - nseg_t)[
-        torch.repeat_interleave(torch.arange(toks.numel(), **i64), nseg_t)]
-    sbeg = tbegin[seg_tok] + seg_cap * ssub
-    send = torch.minimum(sbeg + seg_cap, tbegin[seg_tok] + tcount[seg_tok])
-    smulti = (torch.repeat_interleave(nseg_t, nseg_t) > 1).to(torch.int64)
-    seg = torch.stack([seg_tok, sbeg, send, smulti], 1).to(torch.int32).contiguous()
-    partial = torch.zeros(ntiles * rows_stride, dtype=torch.float64, device=dev)
-    tables = dict(n_tiles=ntiles, M=M, lid=lid, tok=tok, ent=ent, rows=rows, desc=desc, pos=pos, seg=seg,
-                  partial=partial, n_seg=int(seg.shape[0]),
+    tables = dict(n_tiles=ntiles, M=M, lid=lid, tok=tok, ent=ent, rows=rows, desc=desc,
                   rows_per_pool=n_rows / mm, tok_per_tile=float(ntok.double().mean()))
     return order, residual, tables
 
@@ -323,9 +308,7 @@ class BlockedBucket:
         self.gamma_inv = slab(1.0 / hp.gamma[self.sel], 1.0)
         self.c_blocked = _lib.BlockedPairs(self.m, t["n_tiles"], P, 0, self.r0.data_ptr(), self.r1.data_ptr(),
                                            self.gamma_inv.data_ptr(), t["lid"].data_ptr(), t["ent"].data_ptr(),
-                                           t["rows"].data_ptr(), t["tok"].data_ptr(), t["desc"].data_ptr(),
-                                           t["partial"].data_ptr(), t["n_seg"], t["seg"].data_ptr(),
-                                           t["pos"].data_ptr())
+                                           t["rows"].data_ptr(), t["tok"].data_ptr(), t["desc"].data_ptr())
 
     def bytes_resident(self) -> int:
         if self.tables is None:
@@ -373,7 +356,7 @@ class PoolStore:
                     self.buckets.append(DeviceBucket(hp, dict(s, sel=s["sel"][r], off=s["off"][:, r]), self.device))
             else:
                 self.buckets.append(DeviceBucket(hp, s, self.device))
-        # blocked buckets OVERWRITE their output vector, so they must come first (at most one per store)
+        # the blocked bucket (at most one per store) goes first: its launch clears the ping-pong partner buffer
         self.buckets.sort(key=lambda b: 0 if getattr(b, "blocked", False) else 1)
         self._blocked_first = bool(self.buckets) and getattr(self.buckets[0], "blocked", False)
         assert sum(1 for b in self.buckets if getattr(b, "blocked", False)) <= 1
@@ -381,8 +364,12 @@ class PoolStore:
         self.has_sum = bool(np.any(hp.kind == KIND_SUM_HOST))
         self.has_geomean = any(b.kind == _lib.KIND_GEOMEAN for b in self.buckets)
         f64 = dict(dtype=torch.float64, device=self.device)
-        self._acc = torch.zeros(self.n_tokens + 1, **f64)      # [psi | arb], the one all-reduced buffer
-        self._y = torch.zeros(self.n_tokens, **f64)
+        # [psi | arb] (the one all-reduced buffer) and y are ping-ponged: a blocked launch clears the buffer of the
+        # NEXT call, so steady-state evaluations need no memset node
+        self._acc2 = torch.zeros((2, self.n_tokens + 1), **f64)
+        self._y2 = torch.zeros((2, self.n_tokens), **f64)
+        self._acc_i = 0
+        self._y_i = 0
         self._move = torch.zeros(1, **f64)
         self.evals = 0
         self.hvps = 0
@@ -405,8 +392,10 @@ class PoolStore:
     def evaluate(self, nu: torch.Tensor, eps: float = 0.0, trades: bool = False, hess: bool = False):
         """psi(nu) (n_tokens) and arb(nu) (1) for this rank's pools, as views into one (n+1) buffer."""
         st = self._stream()
-        acc = self._acc
-        if not self._blocked_first:       # a blocked bucket zeroes and overwrites [psi | arb] itself
+        acc = self._acc2[self._acc_i]
+        nxt = self._acc2[self._acc_i ^ 1]
+        self._acc_i ^= 1
+        if not self._blocked_first:       # otherwise the previous blocked launch already cleared `acc`
             _lib.check(self.lib.cfmm_zero(acc.data_ptr(), acc.numel() * 8, st), "cfmm_zero")
         lognu = torch.log(nu) if self.has_geomean else None
         for b in self.buckets:
@@ -414,7 +403,8 @@ class PoolStore:
             if getattr(b, "blocked", False):
                 rc = self.lib.cfmm_blocked_eval(C.byref(b.c_blocked), self.n_tokens, nu.data_ptr(), acc.data_ptr(),
                                                 acc.data_ptr() + 8 * self.n_tokens,
-                                                C.byref(out) if out is not None else None, st)
+                                                C.byref(out) if out is not None else None,
+                                                nxt.data_ptr(), nxt.numel(), st)
                 _lib.check(rc, "cfmm_blocked_eval")
                 continue
             rc = self.lib.cfmm_arb_eval(C.byref(b.c_bucket), self.n_tokens, nu.data_ptr(),
@@ -427,13 +417,16 @@ class PoolStore:
 
     def hvp(self, vt: torch.Tensor) -> torch.Tensor:
         st = self._stream()
-        y = self._y
+        y = self._y2[self._y_i]
+        ynxt = self._y2[self._y_i ^ 1]
+        self._y_i ^= 1
         if not self._blocked_first:
             _lib.check(self.lib.cfmm_zero(y.data_ptr(), y.numel() * 8, st), "cfmm_zero")
         for b in self.buckets:
             if getattr(b, "blocked", False):
                 _lib.check(self.lib.cfmm_blocked_hvp(C.byref(b.c_blocked), self.n_tokens, b.hcoef.data_ptr(),
-                                                     vt.data_ptr(), y.data_ptr(), st), "cfmm_blocked_hvp")
+                                                     vt.data_ptr(), y.data_ptr(), ynxt.data_ptr(), st),
+                           "cfmm_blocked_hvp")
                 continue
             rc = self.lib.cfmm_hvp(C.byref(b.c_bucket), self.n_tokens, b.hcoef.data_ptr(),
                                    b.hmask.data_ptr(), vt.data_ptr(), y.data_ptr(), st)

@@ -110,10 +110,6 @@ typedef struct cfmm_blocked_pairs {
     const uint32_t* rows;     /* [n_tiles][rows_stride] start/4 :16 | 4-entry groups :6 | local token :10, longest first */
     const int32_t* tok;       /* [n_tiles][tok_stride] local token id -> global token id                 */
     const int32_t* desc;      /* [n_tiles][4] (ntok, nrow, 4-entry groups, 0)                            */
-    double* partial;          /* [n_tiles][rows_stride] scratch: row sums of the last call               */
-    int64_t n_seg;            /* token segments of the second (per-token) reduction pass                 */
-    const int32_t* seg;       /* [n_seg][4] (token, begin, end, multi) into pos                          */
-    const int32_t* pos;       /* [total rows] positions into partial, grouped by token                   */
 } cfmm_blocked_pairs;
 
 int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int32_t* tok_stride, int32_t* row_cap,
@@ -122,16 +118,15 @@ int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int3
  * Layouts must be (re)built after changing it. */
 int cfmm_set_blocked_config(int32_t cfg);
 
-/* Evaluation of a blocked constant-product bucket.  UNLIKE cfmm_arb_eval this call OVERWRITES psi[0..n_tokens) and
- * arb[0] (it zeroes them itself, then fills them by a deterministic two-pass reduction: per-tile row sums, then
- * per-token sums; no floating-point atomics unless a token has more than 1024 rows), so it must be the FIRST bucket
- * evaluated into a psi buffer; cfmm_arb_eval calls for other buckets then accumulate on top.  Per-pool outputs
- * (delta/lambda [2][n_tiles*P], hcoef [n_tiles*P]) are in BLOCKED order. */
+/* Same contract as cfmm_arb_eval for a blocked constant-product bucket: psi/arb ACCUMULATE (one red.add per row
+ * of <= 32 entries, ~0.35 per pool, instead of 2 per pool).  Per-pool outputs (delta/lambda [2][n_tiles*P], hcoef
+ * [n_tiles*P]) are in BLOCKED order.  If zero_next != NULL the launch also clears zero_next[0..n_zero): callers that
+ * ping-pong two [psi | arb] buffers never need a separate memset node between evaluations. */
 int cfmm_blocked_eval(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* nu, double* psi, double* arb,
-                      const cfmm_eval_out* out, void* stream);
-/* y = Hs vt and diag = diag(Hs) for a blocked bucket (OVERWRITE, same two-pass reduction), hcoef in blocked order. */
+                      const cfmm_eval_out* out, double* zero_next, int64_t n_zero, void* stream);
+/* y += Hs vt (optionally clearing zero_next[0..n_tokens) for the next call) and diag += diag(Hs), hcoef in blocked order. */
 int cfmm_blocked_hvp(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* hcoef, const double* vt, double* y,
-                     void* stream);
+                     double* zero_next, void* stream);
 int cfmm_blocked_diag(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* hcoef, double* diag, void* stream);
 
 /* SUM buckets: theta_bar <- current fills (= lambda), returns max_i |change|/R in move[0] (device). */
