@@ -41,6 +41,7 @@ struct __align__(128) Stage {
     uint16_t ent[BlockedCfg<P>::kEntMax];         // row-ordered, rows padded to 4: local_pool << 1 | slot
     uint32_t rows[BlockedCfg<P>::kRowsMax];       // start/4 :16 | groups of 4 entries :6 | local token :10
     int32_t tok[BlockedCfg<P>::kTokMax];          // local token id -> global token id
+    int4 desc;                                    // (ntok, nrow, groups, 0) of the tile in this stage
 };
 
 struct BlockedArgs {
@@ -66,12 +67,13 @@ struct BlockedArgs {
 __device__ __forceinline__ unsigned round16(unsigned bytes) { return (bytes + 15u) & ~15u; }
 
 template <int P, int NF>
-__device__ __forceinline__ void issue_tile(Stage<P, NF>* st, uint64_t* bar, const BlockedArgs& A, long long tile) {
-    const int4 d = __ldg(A.desc + tile);
+__device__ __forceinline__ void issue_tile(Stage<P, NF>* st, uint64_t* bar, const BlockedArgs& A, long long tile,
+                                           const int4 d) {
     const unsigned rows_b = round16(4u * (unsigned)d.y);
     const unsigned tok_b = round16(4u * (unsigned)d.x);
     const unsigned ent_b = round16(8u * (unsigned)d.z);
-    mbar_expect_tx(bar, (unsigned)(NF * P * 8 + P * 4) + ent_b + rows_b + tok_b);
+    mbar_expect_tx(bar, (unsigned)(NF * P * 8 + P * 4 + 16) + ent_b + rows_b + tok_b);
+    bulk_g2s(&st->desc, A.desc + tile, 16, bar);
 #pragma unroll
     for (int k = 0; k < NF; ++k) bulk_g2s(st->a[k], A.slab[k] + tile * P, P * 8, bar);
     bulk_g2s(st->lid, A.lid + tile * P, P * 4, bar);
@@ -142,7 +144,7 @@ k_blocked(const BlockedArgs A) {
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
-            if (t < A.n_tiles) issue_tile<P, NF>(&stages[s], &full[s], A, t);
+            if (t < A.n_tiles) issue_tile<P, NF>(&stages[s], &full[s], A, t, __ldg(A.desc + t));
         }
     }
     // clear the buffer the NEXT call accumulates into (nobody touches it during this launch)
@@ -150,15 +152,23 @@ k_blocked(const BlockedArgs A) {
     double acc = 0.0;
     int stage = 0;
     unsigned parity = 0;
-    for (long long tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
-        const int4 d = __ldg(A.desc + tile);           // (ntok, nrow, groups, -)
-        mbar_wait(&full[stage], parity);
-        St& S = stages[stage];
-        // ---- phase 1: nu_local <- vec[tok]
+    constexpr int NPRE = (P + THREADS - 1) / THREADS;       // nu_local values each thread prefetches
+    // prologue: nu_local of this CTA's first tile
+    if ((long long)blockIdx.x < A.n_tiles) {
+        mbar_wait(&full[0], 0);
         if (MODE != 2) {
-            for (int t = tid; t < d.x; t += THREADS) nul[t] = __ldg(A.vec + S.tok[t]);
-            __syncthreads();
+            const int ntok = stages[0].desc.x;
+            for (int t = tid; t < ntok; t += THREADS) nul[t] = __ldg(A.vec + stages[0].tok[t]);
         }
+    }
+    __syncthreads();
+    for (long long tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+        St& S = stages[stage];                          // full (waited for when its nu_local was fetched)
+        const int4 d = S.desc;                          // (ntok, nrow, groups, -)
+        // the producer thread fetches the descriptor of the tile it will issue at the end of this iteration
+        const long long far = tile + (long long)STAGES * gridDim.x;
+        int4 dfar = make_int4(0, 0, 0, 0);
+        if (tid == 0 && far < A.n_tiles) dfar = __ldg(A.desc + far);
         // ---- phase 2: per-pool values into f
 #pragma unroll
         for (int l = tid; l < P; l += THREADS) {
@@ -176,7 +186,25 @@ k_blocked(const BlockedArgs A) {
             }
             reinterpret_cast<double2*>(f)[l] = make_double2(f0, f1);
         }
-        __syncthreads();
+        __syncthreads();                 // f complete; nu_local of this tile is dead from here on
+        // ---- prefetch nu_local of the NEXT tile into registers: the L2 latency hides behind the row phase
+        const long long nxt = tile + gridDim.x;
+        int nstage = stage + 1;
+        unsigned nparity = parity;
+        if (nstage == STAGES) { nstage = 0; nparity ^= 1u; }
+        double pre[NPRE];
+        int ntok_n = 0;
+        if (nxt < A.n_tiles) {
+            mbar_wait(&full[nstage], nparity);           // also makes the next iteration's stage reads safe
+            if (MODE != 2) {
+                ntok_n = stages[nstage].desc.x;
+#pragma unroll
+                for (int k = 0; k < NPRE; ++k) {
+                    const int t = tid + k * THREADS;
+                    pre[k] = (t < ntok_n) ? __ldg(A.vec + stages[nstage].tok[t]) : 0.0;
+                }
+            }
+        }
         // ---- phase 3, warp-autonomous: a warp owns 32 consecutive rows and the contiguous span of their
         // 4-entry groups.  Level 1: lanes sum groups in parallel, overwriting each 8-byte group with its sum;
         // level 2: each lane adds up the group sums of its row (fixed order) and issues one red.add.
@@ -197,18 +225,23 @@ k_blocked(const BlockedArgs A) {
                 const int g0 = row_start4(rw), ng = row_groups(rw);
                 double s = gs[g0];
                 for (int k = 1; k < ng; ++k) s += gs[g0 + k];
-                if (s != 0.0) atomicAdd(A.out + S.tok[row_tok(rw)], s);
+                if (s != 0.0 && !(A.dbg & 8)) atomicAdd(A.out + S.tok[row_tok(rw)], s);
+                if (A.dbg & 8) acc += s;
             }
         }
-        __syncthreads();                 // stage, nul and f are free again
-        if (tid == 0) {
-            const long long nxt = tile + (long long)STAGES * gridDim.x;
-            if (nxt < A.n_tiles) {
-                fence_proxy_async();
-                issue_tile<P, NF>(&S, &full[stage], A, nxt);
+        if (MODE != 2 && nxt < A.n_tiles) {
+#pragma unroll
+            for (int k = 0; k < NPRE; ++k) {
+                const int t = tid + k * THREADS;
+                if (t < ntok_n) nul[t] = pre[k];
             }
         }
-        if (++stage == STAGES) { stage = 0; parity ^= 1u; }
+        __syncthreads();                 // stage and f are free again; nu_local of the next tile is in place
+        if (tid == 0 && far < A.n_tiles) {
+            fence_proxy_async();
+            issue_tile<P, NF>(&S, &full[stage], A, far, dfar);
+        }
+        stage = nstage; parity = nparity;
     }
     if (MODE == 0) {
         acc = warp_sum(acc);

@@ -85,14 +85,59 @@ class HostPools:
             raise ValueError("token index out of range")
 
 
-def split_buckets(hp: HostPools, rank: int = 0, world: int = 1):
+class BucketSpec:
+    """Which pools of a HostPools form one bucket.  `sel` = global pool indices (None = all pools, in order,
+    the fast path for constant-product-only problems: no host-side gathers at all)."""
+
+    def __init__(self, hp: HostPools, kind: int, arity: int, sel: Optional[np.ndarray]):
+        self.hp, self.kind, self.arity, self._sel = hp, kind, arity, sel
+        self.m = hp.m if sel is None else int(len(sel))
+        self._off = None
+
+    @property
+    def identity(self) -> bool:
+        return self._sel is None
+
+    @property
+    def sel(self) -> np.ndarray:
+        if self._sel is None:
+            self._sel = np.arange(self.hp.m, dtype=np.int64)
+        return self._sel
+
+    @property
+    def off(self) -> np.ndarray:
+        """(arity, m) CSR offsets of every slot of every pool of the bucket"""
+        if self._off is None:
+            self._off = self.hp.pool_ptr[self.sel][None, :] + np.arange(self.arity)[:, None]
+        return self._off
+
+    def subset(self, local_idx: np.ndarray) -> "BucketSpec":
+        return BucketSpec(self.hp, self.kind, self.arity, self.sel[local_idx])
+
+    # backwards-compatible dict-style access used by older call sites / tests
+    def __getitem__(self, k):
+        return getattr(self, k)
+
+
+def split_buckets(hp: HostPools, rank: int = 0, world: int = 1) -> List["BucketSpec"]:
     """Group pools by (kind, arity); with world>1 keep this rank's contiguous block of each group."""
+    m = hp.m
+    if m == 0:
+        return []
+    uniform_pairs = int(hp.pool_ptr[-1]) == 2 * m and (hp.pool_ptr[1] - hp.pool_ptr[0]) == 2 and \
+        bool(np.all(np.diff(hp.pool_ptr[::max(1, m // 64)]) == 2 * max(1, m // 64))) and \
+        bool(np.array_equal(hp.pool_ptr[:3], np.arange(0, 2 * min(m, 2) + 1, 2)[:3]))
+    if uniform_pairs:
+        uniform_pairs = bool(np.all(np.diff(hp.pool_ptr) == 2))
+    if uniform_pairs and not hp.kind.any() and bool(np.all(hp.weights == 0.5)):
+        if world == 1:
+            return [BucketSpec(hp, _lib.KIND_PRODUCT, 2, None)]
+        lo, hi = (m * rank) // world, (m * (rank + 1)) // world
+        return [BucketSpec(hp, _lib.KIND_PRODUCT, 2, np.arange(lo, hi, dtype=np.int64))]
     ar = np.diff(hp.pool_ptr)
-    out = []
-    w2 = hp.weights[hp.pool_ptr[:-1]] if hp.m else np.zeros(0)
+    first = hp.pool_ptr[:-1]
     is_cp = (hp.kind == KIND_GEOMEAN_HOST) & (ar == 2)
-    if hp.m:
-        is_cp &= (w2 == 0.5) & (hp.weights[np.minimum(hp.pool_ptr[:-1] + 1, len(hp.weights) - 1)] == 0.5)
+    is_cp &= (hp.weights[first] == 0.5) & (hp.weights[np.minimum(first + 1, len(hp.weights) - 1)] == 0.5)
     keys = []
     if is_cp.any():
         keys.append((_lib.KIND_PRODUCT, 2, np.nonzero(is_cp)[0]))
@@ -102,17 +147,17 @@ def split_buckets(hp: HostPools, rank: int = 0, world: int = 1):
             raise ValueError("constant-sum pools must have 2 tokens")
         keys.append((_lib.KIND_SUM, 2, np.nonzero(cs)[0]))
     gm = (hp.kind == KIND_GEOMEAN_HOST) & ~is_cp
-    for k in sorted(set(ar[gm].tolist())):
+    for k in np.unique(ar[gm]).tolist():
         if k < 2 or k > 32:
             raise ValueError(f"weighted pools support 2..32 tokens, got {k}")
         keys.append((_lib.KIND_GEOMEAN, int(k), np.nonzero(gm & (ar == k))[0]))
+    out = []
     for kind, k, sel in keys:
         if world > 1:
             lo = (len(sel) * rank) // world
             hi = (len(sel) * (rank + 1)) // world
             sel = sel[lo:hi]
-        off = hp.pool_ptr[sel][None, :] + np.arange(k)[:, None]        # (k, m_b) slot-major
-        out.append(dict(kind=kind, arity=k, sel=sel, off=off))
+        out.append(BucketSpec(hp, kind, k, sel))
     return out
 
 
@@ -128,19 +173,29 @@ def _padded(arr2d: np.ndarray, stride: int, fill) -> np.ndarray:
 
 class DeviceBucket:
     def __init__(self, hp: HostPools, spec, device):
-        self.kind = spec["kind"]; self.arity = spec["arity"]
-        self.sel = spec["sel"]; self.off = spec["off"]
-        self.m = int(len(self.sel))
+        self.kind = spec.kind; self.arity = spec.arity
+        self.spec = spec
+        self.m = spec.m
         self.stride = max(TILE, -(-self.m // TILE) * TILE)
         f64 = dict(dtype=torch.float64, device=device)
-        R = hp.reserves[self.off]
-        self.reserves = torch.as_tensor(_padded(R, self.stride, 1.0), **f64)
-        self.tok_idx = torch.as_tensor(_padded(hp.tok_idx[self.off].astype(np.int32), self.stride, 0),
-                                       dtype=torch.int32, device=device)
-        self.gamma = torch.as_tensor(_padded(hp.gamma[self.sel][None, :], self.stride, 1.0)[0], **f64)
         self.weights = self.logrw = self.theta_bar = None
+        if spec.identity and self.arity == 2:          # uniform pairs, all pools in order: transpose on the GPU
+            m = self.m
+            self.reserves = torch.ones((2, self.stride), **f64)
+            self.reserves[:, :m] = torch.from_numpy(hp.reserves).to(device).view(m, 2).t()
+            self.tok_idx = torch.zeros((2, self.stride), dtype=torch.int32, device=device)
+            self.tok_idx[:, :m] = torch.from_numpy(hp.tok_idx).to(device).view(m, 2).t()
+            self.gamma = torch.ones(self.stride, **f64)
+            self.gamma[:m] = torch.from_numpy(hp.gamma).to(device)
+            R = W = None
+        else:
+            R = hp.reserves[spec.off]
+            self.reserves = torch.as_tensor(_padded(R, self.stride, 1.0), **f64)
+            self.tok_idx = torch.as_tensor(_padded(hp.tok_idx[spec.off].astype(np.int32), self.stride, 0),
+                                           dtype=torch.int32, device=device)
+            self.gamma = torch.as_tensor(_padded(hp.gamma[spec.sel][None, :], self.stride, 1.0)[0], **f64)
         if self.kind == _lib.KIND_GEOMEAN:
-            W = hp.weights[self.off]
+            W = hp.weights[spec.off]
             self.weights = torch.as_tensor(_padded(W, self.stride, 1.0), **f64)
             self.logrw = torch.as_tensor(_padded(np.log(R / W), self.stride, 0.0), **f64)
         if self.kind == _lib.KIND_SUM:
@@ -153,6 +208,14 @@ class DeviceBucket:
             self.weights.data_ptr() if self.weights is not None else None,
             self.logrw.data_ptr() if self.logrw is not None else None,
             self.theta_bar.data_ptr() if self.theta_bar is not None else None)
+
+    @property
+    def sel(self) -> np.ndarray:
+        return self.spec.sel
+
+    @property
+    def off(self) -> np.ndarray:
+        return self.spec.off
 
     def bytes_resident(self) -> int:
         n = 0
@@ -279,36 +342,54 @@ class BlockedBucket:
     blocked = True
 
     def __init__(self, hp: HostPools, spec, device, lib):
-        sel, off = spec["sel"], spec["off"]
+        self.spec = spec
         P, rows_stride, tok_stride, row_cap, ent_stride = blocked_layout_info(lib)
-        idx = torch.as_tensor(hp.tok_idx[off].astype(np.int64), device=device)
-        order, residual, t = build_blocked_pairs(idx, hp.n_tokens, P, rows_stride, tok_stride, row_cap, ent_stride)
-        self.residual = residual.cpu().numpy()           # bucket-local indices left for a plain bucket
-        order_h = order.cpu().numpy()
-        self.sel = sel[order_h]
-        self.off = off[:, order_h]
-        self.m = int(len(order_h))
+        f64 = dict(dtype=torch.float64, device=device)
+        if spec.identity:                       # raw arrays go up as they are; all reordering happens on the GPU
+            R = torch.from_numpy(hp.reserves).to(device, non_blocking=True).view(-1, 2)
+            idx = torch.from_numpy(hp.tok_idx).to(device, non_blocking=True).view(-1, 2).to(torch.int64)
+            gam = torch.from_numpy(hp.gamma).to(device, non_blocking=True)
+        else:
+            R = torch.as_tensor(np.ascontiguousarray(hp.reserves[spec.off].T), **f64)
+            idx = torch.as_tensor(np.ascontiguousarray(hp.tok_idx[spec.off].T).astype(np.int64), device=device)
+            gam = torch.as_tensor(np.ascontiguousarray(hp.gamma[spec.sel]), **f64)
+        order, residual, t = build_blocked_pairs(idx.t(), hp.n_tokens, P, rows_stride, tok_stride, row_cap, ent_stride)
+        self.order = order                               # blocked position -> bucket-local pool index (device)
+        self.residual = residual.cpu().numpy() if residual.numel() else np.zeros(0, np.int64)
+        self.m = int(order.numel())
         self.theta_bar = None
         self.delta = self.lam = self.hcoef = self.hmask = None
         self._device = device
+        self._sel = self._off = None
         if self.m == 0:
             self.tables = None
             return
         self.tables = t
         self.stride = t["M"]
-        f64 = dict(dtype=torch.float64, device=device)
 
         def slab(vals, fill):
             out = torch.full((t["M"],), fill, **f64)
-            out[:self.m] = torch.as_tensor(vals, **f64)
+            out[:self.m] = vals
             return out
-        R = hp.reserves[self.off]
-        self.r0 = slab(R[0], 1.0)
-        self.r1 = slab(R[1], 1.0)
-        self.gamma_inv = slab(1.0 / hp.gamma[self.sel], 1.0)
+        self.r0 = slab(R[order, 0], 1.0)
+        self.r1 = slab(R[order, 1], 1.0)
+        self.gamma_inv = slab(1.0 / gam[order], 1.0)
         self.c_blocked = _lib.BlockedPairs(self.m, t["n_tiles"], P, 0, self.r0.data_ptr(), self.r1.data_ptr(),
                                            self.gamma_inv.data_ptr(), t["lid"].data_ptr(), t["ent"].data_ptr(),
                                            t["rows"].data_ptr(), t["tok"].data_ptr(), t["desc"].data_ptr())
+
+    # host-side index maps are only needed for read-back / dense assembly: built on first use
+    @property
+    def sel(self) -> np.ndarray:
+        if self._sel is None:
+            self._sel = self.spec.sel[self.order.cpu().numpy()]
+        return self._sel
+
+    @property
+    def off(self) -> np.ndarray:
+        if self._off is None:
+            self._off = self.spec.hp.pool_ptr[self.sel][None, :] + np.arange(2)[:, None]
+        return self._off
 
     def bytes_resident(self) -> int:
         if self.tables is None:
@@ -347,13 +428,12 @@ class PoolStore:
         self.rank, self.world = rank, world
         self.buckets = []
         for s in split_buckets(hp, rank, world):
-            if s["kind"] == _lib.KIND_PRODUCT and layout == "blocked" and len(s["sel"]) > 0:
+            if s.kind == _lib.KIND_PRODUCT and layout == "blocked" and s.m > 0:
                 bb = BlockedBucket(hp, s, self.device, self.lib)
                 if bb.m > 0:
                     self.buckets.append(bb)
                 if len(bb.residual):
-                    r = bb.residual
-                    self.buckets.append(DeviceBucket(hp, dict(s, sel=s["sel"][r], off=s["off"][:, r]), self.device))
+                    self.buckets.append(DeviceBucket(hp, s.subset(bb.residual), self.device))
             else:
                 self.buckets.append(DeviceBucket(hp, s, self.device))
         # the blocked bucket (at most one per store) goes first: its launch clears the ping-pong partner buffer
