@@ -421,6 +421,8 @@ class PoolStore:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.CfmmError("PoolStore needs a CUDA device: there is no CPU path in this package")
+        if not torch.cuda.is_available():
+            raise _lib.CfmmError("no CUDA device visible: the routing kernels have no CPU fallback")
         self.n_tokens = int(hp.n_tokens)
         self.m_total = hp.m
         self.pool_ptr = hp.pool_ptr

@@ -1,0 +1,188 @@
+"""Host-side logic of the product, on CPU: solver.py driven by the oracle-backed evaluator, pool bucketing
+and sharding, the C ABI's symbol table, loud failure without a GPU, and the world_size=2 all-reduce path (gloo)."""
+import ctypes
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import cfmm_routing_code_b200 as cf
+from cfmm_routing_code_b200 import _lib, instances as I, pools as PL
+from cfmm_routing_code_b200.solver import Comm, solve_dual
+from cpu_evaluator import OracleEvaluator
+import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c_abi_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    text = ""
+    for fn in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        if fn.endswith(".h"):
+            text += open(os.path.join(ROOT, "include", fn)).read()
+    names = set(re.findall(r"\b(cfmm_[a-z0-9_]+)\s*\(", text))
+    assert len(names) >= 12
+    for n in sorted(names):
+        assert hasattr(lib, n), f"{n} declared in include/ but not exported by libcfmm_b200.so"
+    assert b"sm_100a" in lib.cfmm_version()
+    # argument validation happens before any CUDA call, so it is testable without a GPU
+    b = _lib.Bucket(_lib.KIND_PRODUCT, 2, 10, 10, None, None, None, None, None, None)
+    assert lib.cfmm_arb_eval(ctypes.byref(b), 4, None, None, 0.0, None, None, None, None) == -1
+    b = _lib.Bucket(9, 2, 0, 0, 1, 1, 1, None, None, None)
+    assert lib.cfmm_arb_eval(ctypes.byref(b), 4, None, None, 0.0, None, None, None, None) == -2
+    assert lib.cfmm_blocked_eval(None, 4, None, None, None, None, None, 0, None) == -1
+
+
+def test_product_path_fails_loudly_without_a_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    d = I.arbitrage_instance()
+    with pytest.raises(cf.CfmmError):
+        cf.solve(d["local_indices"], d["reserves"], d["fees"], d["kinds"], d["weights"],
+                 utility=cf.Arbitrage(d["market_value"]))
+    with pytest.raises(cf.CfmmError):
+        cf.PoolStore(H.host_pools(d), device="cpu")
+
+
+@pytest.mark.parametrize("linear_solver", ["dense", "cg"])
+def test_solver_logic_reproduces_the_reference_instances(golden, linear_solver):
+    d = I.arbitrage_instance()
+    r = solve_dual(OracleEvaluator(H.host_pools(d)), cf.Arbitrage(d["market_value"]).spec(4), tol=1e-9,
+                   linear_solver=linear_solver)
+    assert r.status == "optimal" and abs(r.primal_value - golden["arbitrage"]["value"]) <= 1e-7
+    np.testing.assert_allclose(r.psi.numpy(), golden["arbitrage"]["psi"], atol=2e-6)
+    d = I.liquidation_instance()
+    r = solve_dual(OracleEvaluator(H.host_pools(d)), cf.Liquidate(4, d["current_assets"]).spec(5), tol=1e-9,
+                   linear_solver=linear_solver)
+    assert r.status == "optimal" and abs(r.primal_value - golden["liquidation"]["value"]) <= 1e-7
+    d = I.two_asset_instance()
+    hp = H.host_pools(d)
+    for j in (0, 10, 20, 35, 49):
+        r = solve_dual(OracleEvaluator(hp), cf.Swap(0, 2, d["amounts"][j]).spec(3), tol=1e-9,
+                       linear_solver=linear_solver)
+        assert abs(r.primal_value - golden["two_asset"][j]["value"]) <= 2e-7 * max(1, golden["two_asset"][j]["value"])
+
+
+def test_solver_logic_on_synthetic_mixed_pools_certifies_its_answer():
+    hp, s = H.mixed_host_pools(3000, 60, seed=4)
+    r = solve_dual(OracleEvaluator(hp), cf.Arbitrage(s["prices"]).spec(60), tol=1e-8)
+    assert r.status == "optimal" and abs(r.gap) <= 1e-7 and r.primal_infeas <= 1e-7
+
+
+def test_utilities_and_input_validation():
+    assert cf.Liquidate(4, [2, 1, 3, 5, 10]).spec(5).pinned.tolist() == [False] * 4 + [True]
+    sp = cf.Swap(0, 2, 7.5).spec(3)
+    assert sp.a.tolist() == [7.5, 0, 0] and sp.c.tolist() == [0, 0, 1]
+    with pytest.raises(ValueError):
+        cf.Arbitrage([1.0, -2.0])
+    with pytest.raises(ValueError):
+        cf.HostPools.from_lists(3, [[0, 1, 2]], [[1, 1, 1]], [0.99], ["sum"])
+    with pytest.raises(ValueError):
+        cf.HostPools.from_lists(3, [[0, 0]], [[1, 1]], [0.99], ["product"])
+    with pytest.raises(ValueError):
+        cf.HostPools.from_lists(3, [[0, 1]], [[1, 1, 1]], [0.99], ["product"])
+    with pytest.raises(ValueError):
+        cf.HostPools.from_pairs(2, [[0, 1]], [[1.0, -1.0]], [0.99]).validate()
+    with pytest.raises(ValueError):
+        cf.HostPools.from_pairs(2, [[0, 5]], [[1.0, 1.0]], [0.99]).validate()
+    with pytest.raises(ValueError):
+        cf.solve([[0, 1]], [[1, 1]], [0.99], ["product"])          # utility is required
+
+
+def test_bucketing_and_pool_sharding_partition_the_problem():
+    hp, _ = H.mixed_host_pools(5000, 80, seed=9)
+    whole = PL.split_buckets(hp)
+    assert sum(b.m for b in whole) == hp.m
+    kinds = {(b.kind, b.arity) for b in whole}
+    assert (_lib.KIND_PRODUCT, 2) in kinds and (_lib.KIND_SUM, 2) in kinds and (_lib.KIND_GEOMEAN, 5) in kinds
+    for world in (2, 3, 8):
+        seen = []
+        for rank in range(world):
+            seen += [b.sel for b in PL.split_buckets(hp, rank, world)]
+        allsel = np.sort(np.concatenate(seen))
+        assert np.array_equal(allsel, np.arange(hp.m))          # every pool on exactly one rank
+    # constant-product-only problems take the no-gather fast path
+    hp2, _ = H.cp_host_pools(1000, 16, seed=1)
+    (b,) = PL.split_buckets(hp2)
+    assert b.identity and b.kind == _lib.KIND_PRODUCT and np.array_equal(b.off[:, 3], [6, 7])
+
+
+def test_blocked_layout_builder_tables_reproduce_the_scatter():
+    """build_blocked_pairs on CPU tensors: emulate the kernel's row sums and compare with index_add."""
+    lib = _lib.load()
+    P, rs, ts, cap, es = PL.blocked_layout_info(lib)
+    for m, n in ((5000, 300), (700, 3), (40_000, 2000)):
+        s = I.synth_const_product(m, n, 0)
+        idx = torch.as_tensor(s["idx"].T.astype(np.int64).copy())
+        order, res, t = PL.build_blocked_pairs(idx, n, P, rs, ts, cap, es)
+        assert len(order) + len(res) == m and t is not None
+        f = torch.randn(t["n_tiles"], 2 * P + 4, dtype=torch.float64)
+        f[:, 2 * P:] = 0
+        rows = t["rows"].to(torch.int64) & 0xffffffff
+        ent = (t["ent"].to(torch.int64) & 0xffff).view(t["n_tiles"], es)
+        out = torch.zeros(n, dtype=torch.float64)
+        for tile in range(t["n_tiles"]):
+            ntok, nrow, ng, _ = t["desc"][tile].tolist()
+            assert ntok <= ts and nrow <= rs and 4 * ng <= es
+            w = rows[tile, :nrow]
+            st4, g, lt = w & 0xffff, (w >> 16) & 0x3f, w >> 22
+            assert bool((g[:-1] >= g[1:]).all())                     # longest rows first
+            for r in range(nrow):
+                e = ent[tile, 4 * st4[r]:4 * (st4[r] + g[r])]
+                out[t["tok"][tile, lt[r]]] += f[tile][e].sum()
+        a, b = idx[0][order], idx[1][order]
+        q = torch.arange(len(order)); tl, l = q // P, q % P
+        ref = torch.zeros(n, dtype=torch.float64)
+        ref.index_add_(0, a, f[tl, 2 * l]); ref.index_add_(0, b, f[tl, 2 * l + 1])
+        assert float((out - ref).abs().max()) <= 1e-12 * float(ref.abs().max())
+        lid = t["lid"].to(torch.int64)[:len(order)]
+        assert bool((t["tok"][tl, lid & 0xffff] == a).all() and (t["tok"][tl, lid >> 16] == b).all())
+
+
+# ---------------------------------------------------------------------------------------------------------
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _rank_main(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        hp, s = H.mixed_host_pools(2000, 40, seed=6)
+        comm = Comm()
+        assert comm.dist is not None
+        r = solve_dual(OracleEvaluator(hp, rank, world), cf.Arbitrage(s["prices"]).spec(40), tol=1e-9, comm=comm)
+        q.put((rank, r.primal_value, r.psi.numpy(), r.nu.numpy(), r.status, comm.calls, r.evals))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_pool_sharded_solve_over_gloo_world2_matches_single_process():
+    """pools shard across ranks, nu is replicated, ONE all-reduce of [psi | arb] per evaluation."""
+    hp, s = H.mixed_host_pools(2000, 40, seed=6)
+    single = solve_dual(OracleEvaluator(hp), cf.Arbitrage(s["prices"]).spec(40), tol=1e-9)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=240) for _ in procs], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, val, psi, nu, status, calls, evals in outs:
+        assert status == "optimal"
+        assert abs(val - single.primal_value) <= 1e-8 * abs(single.primal_value)
+        assert calls >= evals                      # at least one all-reduce per dual evaluation
+    # every rank applied the same update: prices are bit-identical across ranks
+    assert np.array_equal(outs[0][3], outs[1][3])
+    np.testing.assert_allclose(outs[0][2], single.psi.numpy(), atol=1e-7 * np.abs(single.psi.numpy()).max())
