@@ -249,6 +249,7 @@ def run_b200(args):
     lib.cfmm_reset_launch_count()
     with ClockSampler(local) as clocks:
         barrier()
+        torch.cuda.profiler.start()
         e0.record()
         if use_graph:
             for _ in range(steps // CHUNK):
@@ -258,6 +259,7 @@ def run_b200(args):
                 step(i)
         e1.record()
         barrier()
+        torch.cuda.profiler.stop()
     launches = int(lib.cfmm_launch_count()) if not use_graph else steps * sum(len(st.buckets) for st in stores[:1])
     ms = torch.tensor([e0.elapsed_time(e1)], **f64)
     if world > 1:
