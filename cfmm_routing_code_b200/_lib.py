@@ -41,6 +41,16 @@ class BlockedPairs(C.Structure):
     ]
 
 
+class SolveParams(C.Structure):
+    _fields_ = [("tol", C.c_double), ("nu_floor", C.c_double), ("max_iter", C.c_int32), ("cg_max", C.c_int32)]
+
+
+class SolveResult(C.Structure):
+    _fields_ = [("dual_value", C.c_double), ("primal_value", C.c_double), ("gap", C.c_double),
+                ("primal_infeas", C.c_double), ("err", C.c_double), ("iters", C.c_int32), ("evals", C.c_int32),
+                ("hvps", C.c_int32), ("status", C.c_int32)]
+
+
 class EvalOut(C.Structure):
     _fields_ = [("delta", C.c_void_p), ("lambda_", C.c_void_p), ("hcoef", C.c_void_p), ("hmask", C.c_void_p)]
 
@@ -86,6 +96,11 @@ def load(build_if_missing: bool = True):
     lib.cfmm_blocked_hvp.restype = C.c_int
     lib.cfmm_blocked_diag.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp]
     lib.cfmm_blocked_diag.restype = C.c_int
+    lib.cfmm_blocked_solve_work_bytes.argtypes = [C.POINTER(BlockedPairs), i32]
+    lib.cfmm_blocked_solve_work_bytes.restype = i64
+    lib.cfmm_blocked_solve.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp, vp, vp, vp, vp,
+                                       C.POINTER(SolveParams), C.POINTER(SolveResult), vp]
+    lib.cfmm_blocked_solve.restype = C.c_int
     lib.cfmm_sum_update_multipliers.argtypes = [C.POINTER(Bucket), vp, vp, vp, vp]
     lib.cfmm_sum_update_multipliers.restype = C.c_int
     lib.cfmm_zero.argtypes = [vp, i64, vp]

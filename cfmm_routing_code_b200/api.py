@@ -97,9 +97,50 @@ def solve(local_indices, reserves, fees, kinds, weights=None, utility=None, n_to
                        **solver_kw)
 
 
+def _native_applicable(store: PoolStore, comm: Comm, solver_kw) -> bool:
+    return (comm.dist is None and len(store.buckets) == 1 and getattr(store.buckets[0], "blocked", False)
+            and solver_kw.get("linear_solver", "auto") in ("auto", "cg") and not solver_kw.get("verbose"))
+
+
+def _solve_native(store: PoolStore, spec, nu0, tol, max_iter, cg_max=200) -> SolveInfo:
+    """cfmm_blocked_solve (csrc/cfmm_solver.cu): the whole outer loop in one C call."""
+    import ctypes as C
+    import time
+    from .solver import default_nu0
+    t0 = time.perf_counter()
+    b = store.buckets[0]
+    n, dev = store.n_tokens, store.device
+    f64 = dict(dtype=torch.float64, device=dev)
+    c = torch.as_tensor(np.asarray(spec.c, float), **f64)
+    a = torch.as_tensor(np.asarray(spec.a, float), **f64)
+    eq = torch.as_tensor(np.asarray(spec.eq, np.uint8), device=dev)
+    pinned = torch.as_tensor(np.asarray(spec.pinned, np.uint8), device=dev)
+    nu = torch.as_tensor(default_nu0(spec) if nu0 is None else np.asarray(nu0, float), **f64).clone()
+    psi = torch.empty(n, **f64)
+    nbytes = store.lib.cfmm_blocked_solve_work_bytes(C.byref(b.c_blocked), n)
+    if nbytes <= 0:
+        raise _lib.CfmmError("cfmm_blocked_solve_work_bytes failed")
+    if getattr(store, "_solve_work", None) is None or store._solve_work.numel() < nbytes:
+        store._solve_work = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    scale = max(float(np.abs(spec.c).max()), 1.0)
+    prm = _lib.SolveParams(float(tol), 1e-12 * scale, int(max_iter), int(cg_max))
+    res = _lib.SolveResult()
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    rc = store.lib.cfmm_blocked_solve(C.byref(b.c_blocked), n, c.data_ptr(), a.data_ptr(), eq.data_ptr(),
+                                      pinned.data_ptr(), nu.data_ptr(), psi.data_ptr(), store._solve_work.data_ptr(),
+                                      C.byref(prm), C.byref(res), st)
+    _lib.check(rc, "cfmm_blocked_solve")
+    store.evals += res.evals
+    store.hvps += res.hvps
+    status = {0: "optimal", 1: "max_iter", 2: "stalled"}[res.status]
+    return SolveInfo(nu=nu, psi=psi, dual_value=res.dual_value, primal_value=res.primal_value, gap=res.gap,
+                     primal_infeas=res.primal_infeas, err=res.err, iters=res.iters, outer=1, evals=res.evals,
+                     hvps=res.hvps, status=status, wall_s=time.perf_counter() - t0, history=[])
+
+
 def solve_pools(hp: HostPools, utility, nu0=None, tol: float = 1e-8, max_iter: int = 100, device="cuda",
                 verbose: bool = False, store: Optional[PoolStore] = None, want_trades: bool = True,
-                **solver_kw) -> Result:
+                native: bool = True, **solver_kw) -> Result:
     """Same as solve() on CSR host arrays.  Under torch.distributed (world_size > 1) every rank passes the
     full problem and keeps its contiguous shard; psi/value are global, deltas/lambdas are this rank's."""
     comm = Comm()
@@ -108,8 +149,13 @@ def solve_pools(hp: HostPools, utility, nu0=None, tol: float = 1e-8, max_iter: i
         world = comm.dist.get_world_size() if comm.dist is not None else 1
         store = PoolStore(hp, device=device, rank=rank, world=world)
     spec = utility.spec(hp.n_tokens)
-    info = solve_dual(store, spec, nu0=nu0, tol=tol, max_inner=max_iter, comm=comm, verbose=verbose,
-                      final_trades=want_trades, **solver_kw)
+    if native and not verbose and _native_applicable(store, comm, solver_kw):
+        info = _solve_native(store, spec, nu0, tol, max_iter, solver_kw.get("cg_max", 200))
+        if want_trades:          # one more pass of the eval kernel to emit Delta / Lambda at the solution
+            store.evaluate(info.nu, 0.0, trades=True, hess=False)
+    else:
+        info = solve_dual(store, spec, nu0=nu0, tol=tol, max_inner=max_iter, comm=comm, verbose=verbose,
+                          final_trades=want_trades, **solver_kw)
     deltas: List[np.ndarray] = []
     lambdas: List[np.ndarray] = []
     if want_trades:

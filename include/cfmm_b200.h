@@ -129,6 +129,31 @@ int cfmm_blocked_hvp(const cfmm_blocked_pairs* b, int32_t n_tokens, const double
                      double* zero_next, void* stream);
 int cfmm_blocked_diag(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* hcoef, double* diag, void* stream);
 
+/*
+ * Native outer loop (csrc/cfmm_solver.cu) for problems whose pools are ONE blocked constant-product bucket: the
+ * whole of `prob.solve()` (arbitrage.py:81-82) in one call -- projected Newton-CG on the dual, all vectors on the
+ * device, host loop in C++.  Utility in "linear + box" form: maximise c'psi s.t. psi_j + a_j >= 0 (eq[j]=0),
+ * == 0 (eq[j]=1), unconstrained with nu_j = c_j (pinned[j]=1)  [arbitrage.py:57,77; liquidation.py:57,77-80;
+ * two-asset.py:66,86].  c, a, eq, pinned, nu (in: start, out: solution), psi_out: device, n_tokens long.
+ * work: device scratch of cfmm_blocked_solve_work_bytes() bytes.  res: host.  Synchronous on `stream`.
+ */
+typedef struct cfmm_solve_params {
+    double tol;        /* stop when sum_free |nu_j (a_j + psi_j)| / |g| <= tol (bounds gap and infeasibility) */
+    double nu_floor;   /* positivity floor for free prices                                                    */
+    int32_t max_iter;  /* Newton iterations                                                                    */
+    int32_t cg_max;    /* PCG iterations per Newton step                                                       */
+} cfmm_solve_params;
+
+typedef struct cfmm_solve_result {
+    double dual_value, primal_value, gap, primal_infeas, err;
+    int32_t iters, evals, hvps, status;   /* status: 0 optimal, 1 max_iter, 2 stalled */
+} cfmm_solve_result;
+
+int64_t cfmm_blocked_solve_work_bytes(const cfmm_blocked_pairs* b, int32_t n_tokens);
+int cfmm_blocked_solve(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* c, const double* a,
+                       const uint8_t* eq, const uint8_t* pinned, double* nu, double* psi_out, void* work,
+                       const cfmm_solve_params* prm, cfmm_solve_result* res, void* stream);
+
 /* SUM buckets: theta_bar <- current fills (= lambda), returns max_i |change|/R in move[0] (device). */
 int cfmm_sum_update_multipliers(const cfmm_bucket* bucket, const double* lambda, double* theta_bar_out,
                                 double* move, void* stream);

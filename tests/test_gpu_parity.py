@@ -174,6 +174,29 @@ def test_cfg2_solve_matches_oracle(linear_solver):
     assert np.max(np.abs(r.psi - ro.psi) / gross.max()) <= 1e-7
 
 
+def test_native_solver_matches_python_solver_and_oracle():
+    """cfmm_blocked_solve (C++ host loop) vs solver.py on the same store, cfg2 size, arbitrage and liquidation"""
+    hp, s = H.cp_host_pools(10_000, 256, seed=0)
+    st = cf.PoolStore(hp)
+    r_nat = cf.solve_pools(hp, cf.Arbitrage(s["prices"]), tol=1e-9, store=st, native=True)
+    r_py = cf.solve_pools(hp, cf.Arbitrage(s["prices"]), tol=1e-9, store=st, native=False)
+    ro = O.solve(H.oracle_pools(hp), O.Utility.arbitrage(s["prices"]), tol=1e-10)
+    assert r_nat.status == "optimal" and r_py.status == "optimal"
+    assert r_nat.info.history == [] and len(r_py.info.history) > 0          # really two different host loops
+    for r in (r_nat, r_py):
+        assert abs(r.value - ro.value) <= 1e-8 * abs(ro.value)
+        assert abs(r.gap) <= 1e-8 and r.primal_infeas <= 1e-8
+    np.testing.assert_allclose(r_nat.nu, r_py.nu, rtol=1e-7)
+    d_ref = np.concatenate(ro.deltas)
+    np.testing.assert_allclose(np.concatenate(r_nat.deltas), d_ref, atol=1e-6 * np.abs(d_ref).max())
+    basket = I.synth_basket(256, s["prices"], seed=2)
+    nu0 = s["prices"] / s["prices"][0]
+    r_nat = cf.solve_pools(hp, cf.Liquidate(0, basket), nu0=nu0, tol=1e-9, store=st)
+    ro = O.solve(H.oracle_pools(hp), O.Utility.liquidate(256, 0, basket), nu0=nu0, tol=1e-10)
+    assert r_nat.status == "optimal" and abs(r_nat.value - ro.value) <= 1e-7 * abs(ro.value)
+    np.testing.assert_allclose(r_nat.psi[1:], -basket[1:], atol=1e-7 * basket.max())
+
+
 def test_cfg3_small_mixed_solve_matches_oracle():
     hp, s = H.mixed_host_pools(8000, 150, seed=1)
     r = cf.solve_pools(hp, cf.Arbitrage(s["prices"]), tol=1e-8)
