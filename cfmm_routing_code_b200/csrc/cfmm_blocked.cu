@@ -27,10 +27,7 @@ struct BlockedCfg {
     // plain bucket), so rows <= P + 2P/32 (every token one row, plus one extra row per 32 entries)
     static constexpr int kTokMax = P;
     static constexpr int kRowsMax = P + 2 * P / 32 + 8;
-    // rows are padded to multiples of 4 entries (pad code kZeroSlot reads a 0.0); the builder sends tiles whose
-    // padded entry list would exceed 3P to the plain bucket (typical: 2.5P)
-    static constexpr int kEntMax = 3 * P;
-    static constexpr int kZeroSlot = 2 * P;
+
 };
 
 // one ring stage: NF per-pool f64 slabs + local ids + row entries + row table + token list
@@ -38,8 +35,8 @@ template <int P, int NF>
 struct __align__(128) Stage {
     double a[NF][P];
     uint32_t lid[P];                              // lid0 | lid1 << 16
-    uint16_t ent[BlockedCfg<P>::kEntMax];         // row-ordered, rows padded to 4: local_pool << 1 | slot
-    uint32_t rows[BlockedCfg<P>::kRowsMax];       // start/4 :16 | groups of 4 entries :6 | local token :10
+    uint32_t pos[P];                              // where this pool's two flows go in the row-ordered array g: pos0 | pos1 << 16
+    uint32_t rows[BlockedCfg<P>::kRowsMax];       // start :16 | length (1..32) :6 | local token :10, longest first
     int32_t tok[BlockedCfg<P>::kTokMax];          // local token id -> global token id
     int4 desc;                                    // (ntok, nrow, groups, 0) of the tile in this stage
 };
@@ -49,10 +46,10 @@ struct BlockedArgs {
     long long M;                  // n_tiles * P (padded pool count = slab stride)
     const double* slab[3];        // NF slabs, each [M]
     const uint32_t* lid;          // [M]
-    const uint16_t* ent;          // [n_tiles][2P]
+    const uint32_t* pos;          // [M]
     const uint32_t* rows;         // [n_tiles][kRowsMax]
     const int32_t* tok;           // [n_tiles][kTokMax]
-    const int4* desc;             // [n_tiles] (ntok, nrow, entry groups of 4, 0)
+    const int4* desc;             // [n_tiles] (ntok, nrow, 0, 0)
     const double* vec;            // nu (eval) or vt (hvp); unused for diag
     double* out;                  // psi / y / diag (+= via one red.add per row)
     double* zero_next;            // optional: buffer of n_zero doubles this launch clears for the NEXT call
@@ -71,13 +68,12 @@ __device__ __forceinline__ void issue_tile(Stage<P, NF>* st, uint64_t* bar, cons
                                            const int4 d) {
     const unsigned rows_b = round16(4u * (unsigned)d.y);
     const unsigned tok_b = round16(4u * (unsigned)d.x);
-    const unsigned ent_b = round16(8u * (unsigned)d.z);
-    mbar_expect_tx(bar, (unsigned)(NF * P * 8 + P * 4 + 16) + ent_b + rows_b + tok_b);
+    mbar_expect_tx(bar, (unsigned)(NF * P * 8 + P * 4 + P * 4 + 16) + rows_b + tok_b);
     bulk_g2s(&st->desc, A.desc + tile, 16, bar);
 #pragma unroll
     for (int k = 0; k < NF; ++k) bulk_g2s(st->a[k], A.slab[k] + tile * P, P * 8, bar);
     bulk_g2s(st->lid, A.lid + tile * P, P * 4, bar);
-    bulk_g2s(st->ent, A.ent + tile * BlockedCfg<P>::kEntMax, ent_b, bar);
+    bulk_g2s(st->pos, A.pos + tile * P, P * 4, bar);
     bulk_g2s(st->rows, A.rows + tile * BlockedCfg<P>::kRowsMax, rows_b, bar);
     bulk_g2s(st->tok, A.tok + tile * BlockedCfg<P>::kTokMax, tok_b, bar);
 }
@@ -119,8 +115,8 @@ struct EvalOp {
 
 // row word: start (16 bits) | length (6 bits, 1..32) | local token (10 bits).  Rows of a tile are sorted by
 // decreasing length by the builder, so the 32 rows of a warp have (nearly) equal trip counts.
-__device__ __forceinline__ int row_start4(uint32_t r) { return (int)(r & 0xffffu); }
-__device__ __forceinline__ int row_groups(uint32_t r) { return (int)((r >> 16) & 0x3fu); }
+__device__ __forceinline__ int row_start(uint32_t r) { return (int)(r & 0xffffu); }
+__device__ __forceinline__ int row_len(uint32_t r) { return (int)((r >> 16) & 0x3fu); }
 __device__ __forceinline__ int row_tok(uint32_t r) { return (int)(r >> 22); }
 
 template <int P, int THREADS, int STAGES, int MODE /*0 eval, 1 hvp, 2 diag*/, bool TRADES, bool HESS>
@@ -131,7 +127,7 @@ k_blocked(const BlockedArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     St* stages = reinterpret_cast<St*>(smem_raw);
     double* nul = reinterpret_cast<double*>(smem_raw + (size_t)STAGES * sizeof(St));      // [P]    nu_local
-    double* f = nul + P;                                                                   // [2P+4] flows + zero slot
+    double* g = nul + P;                                                                   // [2P] flows in ROW order
     __shared__ uint64_t full[STAGES];
     __shared__ double part[THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -139,7 +135,6 @@ k_blocked(const BlockedArgs A) {
         for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
         mbar_fence_init();
     }
-    if (tid < 4) f[2 * P + tid] = 0.0;
     __syncthreads();
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -147,6 +142,11 @@ k_blocked(const BlockedArgs A) {
             if (t < A.n_tiles) issue_tile<P, NF>(&stages[s], &full[s], A, t, __ldg(A.desc + t));
         }
     }
+    // Programmatic dependent launch: everything above touches only this launch's own shared memory and the
+    // constant pool tables, so it may run while the previous kernel on the stream is still draining.  From here
+    // on we read vec / write out, zero_next -- wait for the previous grid, then let the next one start its ramp.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // clear the buffer the NEXT call accumulates into (nobody touches it during this launch)
     for (int j = blockIdx.x * THREADS + tid; j < A.n_zero; j += gridDim.x * THREADS) A.zero_next[j] = 0.0;
     double acc = 0.0;
@@ -184,9 +184,11 @@ k_blocked(const BlockedArgs A) {
                 f0 = S.a[0][l];
                 f1 = f0;
             }
-            reinterpret_cast<double2*>(f)[l] = make_double2(f0, f1);
+            const uint32_t ps = S.pos[l];
+            g[ps & 0xffffu] = f0;
+            g[ps >> 16] = f1;
         }
-        __syncthreads();                 // f complete; nu_local of this tile is dead from here on
+        __syncthreads();                 // g complete; nu_local of this tile is dead from here on
         // ---- prefetch nu_local of the NEXT tile into registers: the L2 latency hides behind the row phase
         const long long nxt = tile + gridDim.x;
         int nstage = stage + 1;
@@ -205,29 +207,20 @@ k_blocked(const BlockedArgs A) {
                 }
             }
         }
-        // ---- phase 3, warp-autonomous: a warp owns 32 consecutive rows and the contiguous span of their
-        // 4-entry groups.  Level 1: lanes sum groups in parallel, overwriting each 8-byte group with its sum;
-        // level 2: each lane adds up the group sums of its row (fixed order) and issues one red.add.
+        // ---- phase 3: one thread per row; a row is a CONTIGUOUS run of g (the pool phase scattered the flows
+        // into row order), rows are sorted by length so a warp's 32 rows have (nearly) equal trip counts.
+        // Fixed summation order; one red.add per row.
         if (!(A.dbg & 1))
-        for (int r0 = warp * 32; r0 < d.y; r0 += THREADS) {
-            const int r = r0 + lane;
-            const uint32_t rw = (r < d.y) ? S.rows[r] : 0u;
-            const uint32_t rwl = S.rows[min(r0 + 31, d.y - 1)];
-            const int gbeg = row_start4(S.rows[r0]), gend = row_start4(rwl) + row_groups(rwl);
-            uint2* e4 = reinterpret_cast<uint2*>(S.ent);
-            double* gs = reinterpret_cast<double*>(S.ent);
-            for (int g = gbeg + lane; g < gend; g += 32) {
-                const uint2 a = e4[g];
-                gs[g] = (f[a.x & 0xffffu] + f[a.x >> 16]) + (f[a.y & 0xffffu] + f[a.y >> 16]);
-            }
-            __syncwarp();
-            if (r < d.y) {
-                const int g0 = row_start4(rw), ng = row_groups(rw);
-                double s = gs[g0];
-                for (int k = 1; k < ng; ++k) s += gs[g0 + k];
-                if (s != 0.0 && !(A.dbg & 8)) atomicAdd(A.out + S.tok[row_tok(rw)], s);
-                if (A.dbg & 8) acc += s;
-            }
+        for (int r = tid; r < d.y; r += THREADS) {
+            const uint32_t rw = S.rows[r];
+            const double* q = g + row_start(rw);
+            const int len = row_len(rw);
+            double s0 = 0.0, s1 = 0.0;
+            int k = 0;
+            for (; k + 4 <= len; k += 4) { s0 += q[k] + q[k + 2]; s1 += q[k + 1] + q[k + 3]; }
+            for (; k < len; ++k) s0 += q[k];
+            const double s = s0 + s1;
+            if (s != 0.0) atomicAdd(A.out + S.tok[row_tok(rw)], s);
         }
         if (MODE != 2 && nxt < A.n_tiles) {
 #pragma unroll
@@ -261,12 +254,13 @@ struct Cfg1 { static constexpr int P = 512, T = 512, S = 3, CTAS = 2; };    // 2
 struct Cfg2 { static constexpr int P = 512, T = 256, S = 2, CTAS = 4; };    // 4 x (43 + 12) KB
 int g_cfg = 0;
 int g_dbg = 0;
+int g_pdl = 1;
 
 template <class C, int MODE, bool TRADES, bool HESS>
 int launch_cfg(const BlockedArgs& A, cudaStream_t st) {
     constexpr int NF = (MODE == 0) ? 3 : 1;
     auto kern = k_blocked<C::P, C::T, C::S, MODE, TRADES, HESS>;
-    const size_t sm = (size_t)C::S * sizeof(Stage<C::P, NF>) + (size_t)(3 * C::P + 4) * sizeof(double);
+    const size_t sm = (size_t)C::S * sizeof(Stage<C::P, NF>) + (size_t)(3 * C::P) * sizeof(double);
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -274,7 +268,17 @@ int launch_cfg(const BlockedArgs& A, cudaStream_t st) {
     }
     const long long cap = (long long)C::CTAS * num_sms();
     const int grid = (int)(A.n_tiles < cap ? A.n_tiles : cap);
-    kern<<<grid, C::T, sm, st>>>(A);
+    if (g_pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(C::T); cfg.dynamicSmemBytes = sm; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, kern, A);
+    } else {
+        kern<<<grid, C::T, sm, st>>>(A);
+    }
     return check_launch();
 }
 
@@ -294,10 +298,10 @@ int fill_args(const cfmm_blocked_pairs* b, BlockedArgs& A) {
     if (b->pools_per_tile != cfg_P()) return CFMM_E_KIND;
     const int64_t P = b->pools_per_tile;
     if (b->n_tiles < 0 || b->n_pools < 0 || b->n_pools > b->n_tiles * P) return CFMM_E_SIZE;
-    if (b->n_tiles > 0 && (!b->lid || !b->ent || !b->rows || !b->tok || !b->desc)) return CFMM_E_NULL;
+    if (b->n_tiles > 0 && (!b->lid || !b->pos || !b->rows || !b->tok || !b->desc)) return CFMM_E_NULL;
     A.n_tiles = b->n_tiles;
     A.M = b->n_tiles * P;
-    A.lid = b->lid; A.ent = b->ent; A.rows = b->rows; A.tok = b->tok;
+    A.lid = b->lid; A.pos = b->pos; A.rows = b->rows; A.tok = b->tok;
     A.desc = reinterpret_cast<const int4*>(b->desc);
     A.zero_next = nullptr; A.n_zero = 0;
     A.slab[0] = A.slab[1] = A.slab[2] = nullptr;
@@ -318,11 +322,12 @@ int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int3
     if (rows_stride) *rows_stride = rows;
     if (tok_stride) *tok_stride = P;
     if (row_cap) *row_cap = 32;
-    if (ent_stride) *ent_stride = 3 * P;
+    if (ent_stride) *ent_stride = 0;          /* unused since the row-ordered scatter (kept for ABI stability) */
     return CFMM_OK;
 }
 
 int cfmm_set_blocked_config(int32_t cfg) {
+    if (cfg >= 200) { g_pdl = cfg - 200; return CFMM_OK; }      // 200 / 201: programmatic dependent launch off / on
     if (cfg >= 100) { g_dbg = cfg - 100; return CFMM_OK; }      // measurement-only phase switches
     if (cfg < 0 || cfg > 2) return CFMM_E_KIND;
     g_cfg = cfg;

@@ -272,10 +272,7 @@ def build_blocked_pairs(idx: torch.Tensor, n_tokens: int, P: int, rows_stride: i
         uniq, inv, counts = torch.unique_consecutive(ck, return_inverse=True, return_counts=True)
         u_tile = uniq // n_tokens
         ntok = torch.bincount(u_tile, minlength=ntiles)
-        rem = counts % row_cap
-        padded = (counts // row_cap) * row_cap + (rem + 3) // 4 * 4        # entries after padding rows to 4
-        nent = torch.zeros(ntiles, **i64).index_add_(0, u_tile, padded)
-        bad = (ntok > tok_stride) | (nent > ent_stride)
+        bad = ntok > tok_stride
         if not bool(bad.any()):
             break
         if _pass == 3:                       # give up blocking: everything left goes to the plain bucket
@@ -314,23 +311,25 @@ def build_blocked_pairs(idx: torch.Tensor, n_tokens: int, P: int, rows_stride: i
     r_local = torch.arange(n_rows, **i64) - row_first[row_tile]
     if int(nrow.max()) > rows_stride:
         raise _lib.CfmmError("blocked layout: row table overflow (library/builder mismatch)")
-    # entries: every row padded to a multiple of 4 (pad code 2P -> a shared-memory zero slot)
-    row_ng = (row_len + 3) // 4
-    cs = torch.cumsum(row_ng, 0) - row_ng
-    row_start4 = cs - cs[row_first][row_tile]                                   # in groups of 4, per tile
-    ngroups = torch.zeros(ntiles, **i64).index_add_(0, row_tile, row_ng)
-    if int(ngroups.max()) * 4 > ent_stride:
-        raise _lib.CfmmError("blocked layout: entry table overflow (library/builder mismatch)")
-    ent = torch.full((ntiles * ent_stride,), 2 * P, dtype=torch.int16, device=dev)
+    # g positions: rows are contiguous runs of the tile's row-ordered array, in sorted-row order
+    cs = torch.cumsum(row_len, 0) - row_len
+    row_start = cs - cs[row_first][row_tile]                                    # per tile
     he_o = torch.arange(2 * mm, **i64) - g_start[inv]                           # offset inside its token group
     he_row = rank[first_row_u[inv] + he_o // row_cap]                           # sorted row id of each half-edge
-    dest = row_tile[he_row] * ent_stride + 4 * row_start4[he_row] + he_o % row_cap
-    ent[dest] = he_code[perm].to(torch.int16)
+    he_pos = torch.empty(2 * mm, **i64)
+    he_pos[perm] = row_start[he_row] + he_o % row_cap                           # back to (pool, slot) order
+    pos = torch.zeros(M, dtype=torch.int32, device=dev)
+    # padding pools (last tile) write their zero flows to slots past the real entries of that tile
+    pad_base = 2 * (mm - (ntiles - 1) * P)
+    if M > mm:
+        padl = torch.arange(M - mm, **i64)
+        pos[mm:] = ((pad_base + 2 * padl) | ((pad_base + 2 * padl + 1) << 16)).to(torch.int32)
+    pos[:mm] = (he_pos[:mm] | (he_pos[mm:] << 16)).to(torch.int32)
     rows = torch.zeros((ntiles, rows_stride), dtype=torch.int32, device=dev)
-    word = row_start4 | (row_ng << 16) | (row_ltok << 22)          # start/4:16 | groups:6 | ltok:10 (may set bit 31)
+    word = row_start | (row_len << 16) | (row_ltok << 22)          # start:16 | len:6 | ltok:10 (may set bit 31)
     rows[row_tile, r_local] = torch.where(word >= 2 ** 31, word - 2 ** 32, word).to(torch.int32)
-    desc = torch.stack([ntok, nrow, ngroups, torch.zeros_like(ntok)], 1).to(torch.int32).contiguous()
-    tables = dict(n_tiles=ntiles, M=M, lid=lid, tok=tok, ent=ent, rows=rows, desc=desc,
+    desc = torch.stack([ntok, nrow, torch.zeros_like(ntok), torch.zeros_like(ntok)], 1).to(torch.int32).contiguous()
+    tables = dict(n_tiles=ntiles, M=M, lid=lid, tok=tok, pos=pos, rows=rows, desc=desc,
                   rows_per_pool=n_rows / mm, tok_per_tile=float(ntok.double().mean()))
     return order, residual, tables
 
@@ -375,7 +374,7 @@ class BlockedBucket:
         self.r1 = slab(R[order, 1], 1.0)
         self.gamma_inv = slab(1.0 / gam[order], 1.0)
         self.c_blocked = _lib.BlockedPairs(self.m, t["n_tiles"], P, 0, self.r0.data_ptr(), self.r1.data_ptr(),
-                                           self.gamma_inv.data_ptr(), t["lid"].data_ptr(), t["ent"].data_ptr(),
+                                           self.gamma_inv.data_ptr(), t["lid"].data_ptr(), t["pos"].data_ptr(),
                                            t["rows"].data_ptr(), t["tok"].data_ptr(), t["desc"].data_ptr())
 
     # host-side index maps are only needed for read-back / dense assembly: built on first use
@@ -394,7 +393,7 @@ class BlockedBucket:
     def bytes_resident(self) -> int:
         if self.tables is None:
             return 0
-        ts = [self.r0, self.r1, self.gamma_inv] + [self.tables[k] for k in ("lid", "tok", "ent", "rows", "desc")]
+        ts = [self.r0, self.r1, self.gamma_inv] + [self.tables[k] for k in ("lid", "tok", "pos", "rows", "desc")]
         return sum(x.numel() * x.element_size() for x in ts)
 
     def out_struct(self, trades: bool, hess: bool):

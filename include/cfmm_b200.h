@@ -93,7 +93,7 @@ int cfmm_hess_dense(const cfmm_bucket* bucket, int32_t n_tokens, const double* h
  * Token-blocked storage for constant-product pools (the HBM-bound kind).  Built once per problem from
  * local_indices (arbitrage.py:6-12) by the layout builder (pools.py: build_blocked_pairs); pools are
  * reordered into tiles of `pools_per_tile` whose tokens fall into two narrow token blocks.  Per pool 28 B of
- * slabs + 4 B of row entries; per tile a token list, a row table and (ntok, nrow).  See csrc/cfmm_blocked.cu.
+ * slabs + 4 B of local ids + 4 B of row positions; per tile a token list, a row table and (ntok, nrow).  See csrc/cfmm_blocked.cu.
  * Strides of the per-tile tables come from cfmm_blocked_layout_info().
  */
 typedef struct cfmm_blocked_pairs {
@@ -105,11 +105,11 @@ typedef struct cfmm_blocked_pairs {
     const double* r1;         /* [n_tiles*P] reserves of slot 1                                          */
     const double* gamma_inv;  /* [n_tiles*P] 1 / fees[i]                              arbitrage.py:22-28 */
     const uint32_t* lid;      /* [n_tiles*P] tile-local token ids: slot0 | slot1 << 16                   */
-    const uint16_t* ent;      /* [n_tiles][ent_stride] row-ordered entries (local_pool << 1 | slot), each row
-                                 padded to a multiple of 4 with the zero-slot code 2P                     */
-    const uint32_t* rows;     /* [n_tiles][rows_stride] start/4 :16 | 4-entry groups :6 | local token :10, longest first */
+    const uint32_t* pos;      /* [n_tiles*P] where the pool's two flows go in the tile's row-ordered array:
+                                 pos(slot 0) | pos(slot 1) << 16, each < 2P                              */
+    const uint32_t* rows;     /* [n_tiles][rows_stride] start :16 | length 1..32 :6 | local token :10, longest first */
     const int32_t* tok;       /* [n_tiles][tok_stride] local token id -> global token id                 */
-    const int32_t* desc;      /* [n_tiles][4] (ntok, nrow, 4-entry groups, 0)                            */
+    const int32_t* desc;      /* [n_tiles][4] (ntok, nrow, 0, 0)                                         */
 } cfmm_blocked_pairs;
 
 int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int32_t* tok_stride, int32_t* row_cap,

@@ -122,24 +122,28 @@ def test_blocked_layout_builder_tables_reproduce_the_scatter():
         idx = torch.as_tensor(s["idx"].T.astype(np.int64).copy())
         order, res, t = PL.build_blocked_pairs(idx, n, P, rs, ts, cap, es)
         assert len(order) + len(res) == m and t is not None
-        f = torch.randn(t["n_tiles"], 2 * P + 4, dtype=torch.float64)
-        f[:, 2 * P:] = 0
+        M = t["n_tiles"] * P
+        f = torch.randn(M, 2, dtype=torch.float64)                     # flows of (pool, slot), blocked order
+        f[len(order):] = 0.0                                            # padding pools produce zero flows
+        pos = t["pos"].to(torch.int64) & 0xffffffff
+        g = torch.zeros(t["n_tiles"], 2 * P, dtype=torch.float64)       # the pool phase scatters into row order
+        tl_all = torch.arange(M) // P
+        g[tl_all, pos & 0xffff] = f[:, 0]
+        g[tl_all, pos >> 16] = f[:, 1]
         rows = t["rows"].to(torch.int64) & 0xffffffff
-        ent = (t["ent"].to(torch.int64) & 0xffff).view(t["n_tiles"], es)
         out = torch.zeros(n, dtype=torch.float64)
         for tile in range(t["n_tiles"]):
-            ntok, nrow, ng, _ = t["desc"][tile].tolist()
-            assert ntok <= ts and nrow <= rs and 4 * ng <= es
+            ntok, nrow, _, _ = t["desc"][tile].tolist()
+            assert ntok <= ts and nrow <= rs
             w = rows[tile, :nrow]
-            st4, g, lt = w & 0xffff, (w >> 16) & 0x3f, w >> 22
-            assert bool((g[:-1] >= g[1:]).all())                     # longest rows first
+            st, ln, lt = w & 0xffff, (w >> 16) & 0x3f, w >> 22
+            assert bool((ln[:-1] >= ln[1:]).all()) and int(ln.max()) <= cap     # longest rows first
             for r in range(nrow):
-                e = ent[tile, 4 * st4[r]:4 * (st4[r] + g[r])]
-                out[t["tok"][tile, lt[r]]] += f[tile][e].sum()
+                out[t["tok"][tile, lt[r]]] += g[tile, st[r]:st[r] + ln[r]].sum()
         a, b = idx[0][order], idx[1][order]
         q = torch.arange(len(order)); tl, l = q // P, q % P
         ref = torch.zeros(n, dtype=torch.float64)
-        ref.index_add_(0, a, f[tl, 2 * l]); ref.index_add_(0, b, f[tl, 2 * l + 1])
+        ref.index_add_(0, a, f[q, 0]); ref.index_add_(0, b, f[q, 1])
         assert float((out - ref).abs().max()) <= 1e-12 * float(ref.abs().max())
         lid = t["lid"].to(torch.int64)[:len(order)]
         assert bool((t["tok"][tl, lid & 0xffff] == a).all() and (t["tok"][tl, lid >> 16] == b).all())
