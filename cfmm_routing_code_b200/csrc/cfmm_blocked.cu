@@ -26,7 +26,8 @@ struct BlockedCfg {
     // the layout builder guarantees <= P distinct tokens per tile (tiles that would exceed it go to the
     // plain bucket), so rows <= P + 2P/32 (every token one row, plus one extra row per 32 entries)
     static constexpr int kTokMax = P;
-    static constexpr int kRowsMax = P + 2 * P / 32 + 8;
+    static constexpr int kRowCapMin = 8;                     // smallest row cap the tables are sized for
+    static constexpr int kRowsMax = P + 2 * P / kRowCapMin + 8;
 
 };
 
@@ -136,10 +137,15 @@ k_blocked(const BlockedArgs A) {
         mbar_fence_init();
     }
     __syncthreads();
+    // Each CTA walks a CONTIGUOUS chunk of tiles.  Tiles are sorted by (token block of slot 0, of slot 1), so at any
+    // moment the resident CTAs work on different token blocks and their red.adds hit different addresses (a
+    // grid-strided walk would have all CTAs hammer the same ~130 tokens at once).
+    const long long t_beg = (A.n_tiles * (long long)blockIdx.x) / gridDim.x;
+    const long long t_end = (A.n_tiles * (long long)(blockIdx.x + 1)) / gridDim.x;
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
-            if (t < A.n_tiles) issue_tile<P, NF>(&stages[s], &full[s], A, t, __ldg(A.desc + t));
+            const long long t = t_beg + s;
+            if (t < t_end) issue_tile<P, NF>(&stages[s], &full[s], A, t, __ldg(A.desc + t));
         }
     }
     // Programmatic dependent launch: everything above touches only this launch's own shared memory and the
@@ -154,7 +160,7 @@ k_blocked(const BlockedArgs A) {
     unsigned parity = 0;
     constexpr int NPRE = (P + THREADS - 1) / THREADS;       // nu_local values each thread prefetches
     // prologue: nu_local of this CTA's first tile
-    if ((long long)blockIdx.x < A.n_tiles) {
+    if (t_beg < t_end) {
         mbar_wait(&full[0], 0);
         if (MODE != 2) {
             const int ntok = stages[0].desc.x;
@@ -162,13 +168,13 @@ k_blocked(const BlockedArgs A) {
         }
     }
     __syncthreads();
-    for (long long tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+    for (long long tile = t_beg; tile < t_end; ++tile) {
         St& S = stages[stage];                          // full (waited for when its nu_local was fetched)
         const int4 d = S.desc;                          // (ntok, nrow, groups, -)
         // the producer thread fetches the descriptor of the tile it will issue at the end of this iteration
-        const long long far = tile + (long long)STAGES * gridDim.x;
+        const long long far = tile + STAGES;
         int4 dfar = make_int4(0, 0, 0, 0);
-        if (tid == 0 && far < A.n_tiles) dfar = __ldg(A.desc + far);
+        if (tid == 0 && far < t_end) dfar = __ldg(A.desc + far);
         // ---- phase 2: per-pool values into f
 #pragma unroll
         for (int l = tid; l < P; l += THREADS) {
@@ -190,13 +196,13 @@ k_blocked(const BlockedArgs A) {
         }
         __syncthreads();                 // g complete; nu_local of this tile is dead from here on
         // ---- prefetch nu_local of the NEXT tile into registers: the L2 latency hides behind the row phase
-        const long long nxt = tile + gridDim.x;
+        const long long nxt = tile + 1;
         int nstage = stage + 1;
         unsigned nparity = parity;
         if (nstage == STAGES) { nstage = 0; nparity ^= 1u; }
         double pre[NPRE];
         int ntok_n = 0;
-        if (nxt < A.n_tiles) {
+        if (nxt < t_end) {
             mbar_wait(&full[nstage], nparity);           // also makes the next iteration's stage reads safe
             if (MODE != 2) {
                 ntok_n = stages[nstage].desc.x;
@@ -220,9 +226,10 @@ k_blocked(const BlockedArgs A) {
             for (; k + 4 <= len; k += 4) { s0 += q[k] + q[k + 2]; s1 += q[k + 1] + q[k + 3]; }
             for (; k < len; ++k) s0 += q[k];
             const double s = s0 + s1;
-            if (s != 0.0) atomicAdd(A.out + S.tok[row_tok(rw)], s);
+            if (A.dbg & 8) acc += s;
+            else if (s != 0.0) atomicAdd(A.out + S.tok[row_tok(rw)], s);
         }
-        if (MODE != 2 && nxt < A.n_tiles) {
+        if (MODE != 2 && nxt < t_end) {
 #pragma unroll
             for (int k = 0; k < NPRE; ++k) {
                 const int t = tid + k * THREADS;
@@ -230,7 +237,7 @@ k_blocked(const BlockedArgs A) {
             }
         }
         __syncthreads();                 // stage and f are free again; nu_local of the next tile is in place
-        if (tid == 0 && far < A.n_tiles) {
+        if (tid == 0 && far < t_end) {
             fence_proxy_async();
             issue_tile<P, NF>(&S, &full[stage], A, far, dfar);
         }
@@ -255,6 +262,7 @@ struct Cfg2 { static constexpr int P = 512, T = 256, S = 2, CTAS = 4; };    // 4
 int g_cfg = 0;
 int g_dbg = 0;
 int g_pdl = 1;
+int g_row_cap = 32;
 
 template <class C, int MODE, bool TRADES, bool HESS>
 int launch_cfg(const BlockedArgs& A, cudaStream_t st) {
@@ -317,16 +325,17 @@ extern "C" {
 int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int32_t* tok_stride, int32_t* row_cap,
                              int32_t* ent_stride) {
     const int P = cfg_P();
-    const int rows = P + 2 * P / 32 + 8;
+    const int rows = P + 2 * P / 8 + 8;
     if (pools_per_tile) *pools_per_tile = P;
     if (rows_stride) *rows_stride = rows;
     if (tok_stride) *tok_stride = P;
-    if (row_cap) *row_cap = 32;
+    if (row_cap) *row_cap = g_row_cap;
     if (ent_stride) *ent_stride = 0;          /* unused since the row-ordered scatter (kept for ABI stability) */
     return CFMM_OK;
 }
 
 int cfmm_set_blocked_config(int32_t cfg) {
+    if (cfg >= 300) { const int c = cfg - 300; if (c < 8 || c > 32) return CFMM_E_KIND; g_row_cap = c; return CFMM_OK; }
     if (cfg >= 200) { g_pdl = cfg - 200; return CFMM_OK; }      // 200 / 201: programmatic dependent launch off / on
     if (cfg >= 100) { g_dbg = cfg - 100; return CFMM_OK; }      // measurement-only phase switches
     if (cfg < 0 || cfg > 2) return CFMM_E_KIND;

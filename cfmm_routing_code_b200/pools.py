@@ -254,7 +254,9 @@ def build_blocked_pairs(idx: torch.Tensor, n_tokens: int, P: int, rows_stride: i
     i64 = dict(dtype=torch.int64, device=dev)
     nb = max(1, int(round((m / P) ** 0.5)))
     a, b = idx[0], idx[1]
-    key = (a * nb // n_tokens) * nb + (b * nb // n_tokens)
+    # primary: (token block of slot 0, token block of slot 1); secondary: slot-0 token, so that the lanes of a warp
+    # read the same nu_local entry (shared-memory broadcast) and scatter slot-0 flows to consecutive positions
+    key = ((a * nb // n_tokens) * nb + (b * nb // n_tokens)) * n_tokens + a
     order = torch.argsort(key, stable=True)
     residual = []
     for _pass in range(4):
