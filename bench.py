@@ -117,22 +117,21 @@ class ClockSampler:
 # CPU legs (the ONLY places this file executes oracle/)
 # --------------------------------------------------------------------------------------------------
 def cpu_eval_throughput(seconds_budget=12.0):
-    """oracle (numpy port) dual evaluations over the full 1M-pool instance on the host: pool-evals/s."""
+    """oracle dual evaluations of the full 1M-pool instance on ALL host cores (oracle/cfmm_oracle_c.c, pthreads):
+    pool-evals/s, number of evaluations, seconds, threads."""
     from cfmm_routing_code_b200 import instances as I
-    from oracle import cfmm_oracle as O
+    from oracle import c_oracle as CO
     s = I.synth_const_product(M_POOLS, N_TOKENS, seed=3)
-    P = O.Pools(N_TOKENS, np.arange(0, 2 * M_POOLS + 1, 2, dtype=np.int64), s["idx"].reshape(-1).astype(np.int32),
-                s["reserves"].reshape(-1), np.full(2 * M_POOLS, 0.5), s["gamma"], np.zeros(M_POOLS, np.uint8))
-    bk = O.Buckets(P)
+    idx = np.ascontiguousarray(s["idx"], np.int32); R = np.ascontiguousarray(s["reserves"]); g = s["gamma"]
     nu = s["prices"] * np.exp(0.01 * np.random.default_rng(0).standard_normal(N_TOKENS))
-    O.evaluate(bk, nu)            # warm
+    CO.eval_pairs(idx, R, g, N_TOKENS, nu)            # warm
     t0 = time.perf_counter(); k = 0
     while True:
-        O.evaluate(bk, nu * (1 + 1e-3 * k)); k += 1
+        CO.eval_pairs(idx, R, g, N_TOKENS, nu * (1 + 1e-3 * k)); k += 1
         dt = time.perf_counter() - t0
-        if dt > seconds_budget or k >= 50:
+        if dt > seconds_budget or k >= 2000:
             break
-    return M_POOLS * k / dt, k, dt
+    return M_POOLS * k / dt, k, dt, CO.num_threads()
 
 
 def run_reference(args):
@@ -147,19 +146,21 @@ def run_reference(args):
     except Exception:
         have_cvxpy = False
     vals = []
-    per_step_budget = max(2.0, min(20.0, 120.0 / max(args.steps + args.warmup, 1)))
+    per_step_budget = max(1.0, min(15.0, 90.0 / max(args.steps + args.warmup, 1)))
+    cores = 1
     for i in range(args.warmup + args.steps):
-        v, k, dt = cpu_eval_throughput(per_step_budget)
+        v, k, dt, cores = cpu_eval_throughput(per_step_budget)
         if i >= args.warmup:
             vals.append((v, k, dt))
     value = float(np.mean([v for v, _, _ in vals]))
-    sample = f"{vals[0][1]} oracle dual evaluations of the full 1M-pool/4096-token instance per step (numpy, fp64)"
+    sample = (f"{vals[0][1]} oracle dual evaluations of the full 1M-pool/4096-token instance per step "
+              f"(C restatement oracle/cfmm_oracle_c.c, {cores} pthreads, fp64)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean([dt / k for _, k, dt in vals])),
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(args.gpus, args.scaling),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "note": "reference solver (cvxpy) " + ("present but not used for this metric" if have_cvxpy
                                                                else "unavailable in image")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -228,7 +229,7 @@ def run_b200(args):
     # N = 1: the K steps are captured once into CUDA graphs of CHUNK steps each and replayed, so the timed
     # region holds kernel work only (no Python / ctypes launch overhead between the ~10 us kernels).
     CHUNK = 64
-    use_graph = (world == 1) and not args.no_graph and args.steps >= CHUNK
+    use_graph = not args.no_graph and args.steps >= CHUNK and (world == 1 or args.graph_nccl)
     steps = (args.steps // CHUNK) * CHUNK if use_graph else args.steps
     graph = None
     if use_graph:
@@ -313,9 +314,10 @@ def run_b200(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, k, dt = cpu_eval_throughput(12.0)
-        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"{k} oracle (numpy, fp64) dual evaluations of the same 1M-pool instance in {dt:.1f}s"}
+        v, k, dt, cores = cpu_eval_throughput(12.0)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{k} oracle dual evaluations (C restatement, {cores} pthreads, fp64) of the same 1M-pool "
+                         f"instance in {dt:.1f}s"}
 
     if rank == 0:
         line = {
@@ -341,10 +343,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer solve leg (profiling runs)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of CUDA-graph replay")
+    ap.add_argument("--graph-nccl", action="store_true", help="N>1: capture the all-reduce into the step graphs too")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 20:
-            args.steps = 5          # each reference step is seconds of CPU work
+            args.steps = 10         # each reference step is seconds of CPU work
             args.warmup = min(args.warmup, 1)
         run_reference(args)
     else:

@@ -135,3 +135,17 @@ def test_gradient_and_hessian_by_finite_differences():
         assert abs((ep["arb"] - em["arb"]) / (2 * h) - ev["psi"][j]) <= 1e-5 * (abs(ev["psi"][j]) + 1)
         np.testing.assert_allclose((ep["psi"] - em["psi"]) / (2 * h), Hs[:, j],
                                    atol=2e-4 * np.abs(Hs[:, j]).max())
+
+
+def test_c_restatement_matches_numpy_oracle():
+    """oracle/cfmm_oracle_c.c (the multi-threaded CPU baseline of bench.py) against the numpy oracle"""
+    from oracle import c_oracle as CO
+    hp, s = H.cp_host_pools(50_000, 300, seed=2)
+    nu = H.random_prices(s["prices"], 5)
+    psi, arb, d, l = CO.eval_pairs(hp.tok_idx.reshape(-1, 2), hp.reserves.reshape(-1, 2), hp.gamma, 300, nu, True)
+    ev = O.evaluate(O.Buckets(H.oracle_pools(hp)), nu, want_trades=True)
+    np.testing.assert_allclose(psi, ev["psi"], atol=1e-12 * np.abs(ev["psi"]).max())
+    assert abs(arb - ev["arb"]) <= 1e-12 * abs(ev["arb"])
+    np.testing.assert_allclose(d.ravel(), ev["delta"], atol=1e-13 * hp.reserves.max())
+    np.testing.assert_allclose(l.ravel(), ev["lam"], atol=1e-13 * hp.reserves.max())
+    assert CO.num_threads() >= 1
