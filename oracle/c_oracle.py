@@ -19,7 +19,9 @@ def load():
         _lib = C.CDLL(so)
         _lib.oracle_eval_pairs.restype = C.c_int
         _lib.oracle_eval_pairs.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
-                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.oracle_hess_pairs.restype = C.c_int
+        _lib.oracle_hess_pairs.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int]
         _lib.oracle_num_threads.restype = C.c_int
     return _lib
 
@@ -28,8 +30,8 @@ def num_threads():
     return int(load().oracle_num_threads())
 
 
-def eval_pairs(idx, R, gamma, n_tokens, nu, want_trades=False):
-    """idx (m,2) int32, R (m,2) f64, gamma (m,) -> psi (n,), arb, [delta (m,2), lam (m,2)]"""
+def eval_pairs(idx, R, gamma, n_tokens, nu, want_trades=False, hcoef=None):
+    """idx (m,2) int32, R (m,2) f64, gamma (m,) -> psi (n,), arb, [delta (m,2), lam (m,2)]; hcoef (m,) filled if given"""
     lib = load()
     idx = np.ascontiguousarray(idx, np.int32); R = np.ascontiguousarray(R, np.float64)
     gamma = np.ascontiguousarray(gamma, np.float64); nu = np.ascontiguousarray(nu, np.float64)
@@ -39,7 +41,51 @@ def eval_pairs(idx, R, gamma, n_tokens, nu, want_trades=False):
     l = np.empty((m, 2)) if want_trades else None
     rc = lib.oracle_eval_pairs(m, idx.ctypes.data, R.ctypes.data, gamma.ctypes.data, n_tokens, nu.ctypes.data,
                                psi.ctypes.data, arb.ctypes.data, d.ctypes.data if want_trades else None,
-                               l.ctypes.data if want_trades else None)
+                               l.ctypes.data if want_trades else None, hcoef.ctypes.data if hcoef is not None else None)
     if rc:
         raise MemoryError("oracle_eval_pairs")
     return (psi, float(arb[0]), d, l) if want_trades else (psi, float(arb[0]))
+
+
+def hess_pairs(idx, hcoef, n_tokens, vt=None):
+    """y = Hs vt (vt given) or diag(Hs) (vt None) for constant-product pools, log-price coordinates"""
+    lib = load()
+    out = np.empty(n_tokens)
+    vtc = np.ascontiguousarray(vt, np.float64) if vt is not None else None
+    rc = lib.oracle_hess_pairs(len(hcoef), idx.ctypes.data, hcoef.ctypes.data, n_tokens,
+                               vtc.ctypes.data if vtc is not None else None, out.ctypes.data, 1 if vt is not None else 2)
+    if rc:
+        raise MemoryError("oracle_hess_pairs")
+    return out
+
+
+class CpuPairsEvaluator:
+    """The solver's evaluator protocol on the host cores (constant-product pools only): what bench.py's
+    `--impl reference` leg solves with.  CPU torch tensors in/out, C + pthreads underneath."""
+
+    def __init__(self, n_tokens, idx, R, gamma):
+        import torch
+        self.torch = torch
+        self.n_tokens = int(n_tokens)
+        self.idx = np.ascontiguousarray(idx, np.int32); self.R = np.ascontiguousarray(R, np.float64)
+        self.gamma = np.ascontiguousarray(gamma, np.float64)
+        self.hcoef = np.zeros(len(self.gamma))
+        self.has_sum = False
+        self.device = torch.device("cpu")
+        self.evals = 0
+        self.hvps = 0
+
+    def evaluate(self, nu, eps=0.0, trades=False, hess=False):
+        psi, arb = eval_pairs(self.idx, self.R, self.gamma, self.n_tokens, nu.numpy(), hcoef=self.hcoef if hess else None)
+        self.evals += 1
+        return self.torch.as_tensor(np.concatenate([psi, [arb]]))
+
+    def hvp(self, vt):
+        self.hvps += 1
+        return self.torch.as_tensor(hess_pairs(self.idx, self.hcoef, self.n_tokens, vt.numpy()))
+
+    def hess_diag(self):
+        return self.torch.as_tensor(hess_pairs(self.idx, self.hcoef, self.n_tokens))
+
+    def reset_multipliers(self):
+        pass
