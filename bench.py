@@ -124,7 +124,7 @@ def cpu_eval_throughput(seconds_budget=12.0):
     s = I.synth_const_product(M_POOLS, N_TOKENS, seed=3)
     idx = np.ascontiguousarray(s["idx"], np.int32); R = np.ascontiguousarray(s["reserves"]); g = s["gamma"]
     nu = s["prices"] * np.exp(0.01 * np.random.default_rng(0).standard_normal(N_TOKENS))
-    CO.eval_pairs(idx, R, g, N_TOKENS, nu)            # warm
+    CO.autotune_threads(idx, R, g, N_TOKENS, nu)      # best thread count for this host (also warms up)
     t0 = time.perf_counter(); k = 0
     while True:
         CO.eval_pairs(idx, R, g, N_TOKENS, nu * (1 + 1e-3 * k)); k += 1
@@ -141,6 +141,9 @@ def cpu_full_solve():
     from cfmm_routing_code_b200.solver import solve_dual
     from oracle import c_oracle as CO
     s = I.synth_const_product(M_POOLS, N_TOKENS, seed=3)
+    nu = s["prices"].copy()
+    CO.autotune_threads(np.ascontiguousarray(s["idx"], np.int32), np.ascontiguousarray(s["reserves"]), s["gamma"],
+                        N_TOKENS, nu)
     t0 = time.perf_counter()
     ev = CO.CpuPairsEvaluator(N_TOKENS, s["idx"], s["reserves"], s["gamma"])
     r = solve_dual(ev, cf.Arbitrage(s["prices"]).spec(N_TOKENS), tol=1e-6, linear_solver="cg")

@@ -30,6 +30,30 @@ def num_threads():
     return int(load().oracle_num_threads())
 
 
+def set_threads(n):
+    load().oracle_set_threads(int(n))
+
+
+def autotune_threads(idx, R, gamma, n_tokens, nu, candidates=(4, 8, 16, 32, 64, 128, 256)):
+    """pick the thread count with the best evaluation throughput on this host (more is not better: every thread
+    owns a private psi array and the scatter is memory bound)"""
+    import os
+    import time
+    ncpu = os.cpu_count() or 1
+    best, best_t = None, float("inf")
+    for c in sorted({min(c, ncpu) for c in candidates}):
+        set_threads(c)
+        eval_pairs(idx, R, gamma, n_tokens, nu)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            eval_pairs(idx, R, gamma, n_tokens, nu)
+        dt = (time.perf_counter() - t0) / 3
+        if dt < best_t:
+            best, best_t = c, dt
+    set_threads(best)
+    return best
+
+
 def eval_pairs(idx, R, gamma, n_tokens, nu, want_trades=False, hcoef=None):
     """idx (m,2) int32, R (m,2) f64, gamma (m,) -> psi (n,), arb, [delta (m,2), lam (m,2)]; hcoef (m,) filled if given"""
     lib = load()

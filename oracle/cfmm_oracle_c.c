@@ -24,6 +24,8 @@ int oracle_num_threads(void) {
     return g_threads;
 }
 
+void oracle_set_threads(int n) { g_threads = (n < 1) ? 1 : (n > 256 ? 256 : n); }
+
 typedef struct {
     int64_t lo, hi;
     const int32_t* idx; const double* R; const double* gamma; const double* nu;
