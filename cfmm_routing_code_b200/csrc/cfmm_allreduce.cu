@@ -1,0 +1,74 @@
+// cfmm_allreduce.cu -- one-shot all-reduce (sum) of the small [psi | arb] vector over NVLink peer memory.
+//
+// pools shard across GPUs and every dual evaluation ends with ONE all-reduce of n_tokens+1 doubles
+// (32 KB at 4096 tokens).  At that size NCCL is pure latency (~13 us inside a CUDA graph, ~18 us eager, measured);
+// here every rank simply reads all peers' partial vectors through NVLink-mapped pointers (torch symmetric memory:
+// cudaMalloc'd buffers exchanged over the process group) and sums them in rank order, so the result is
+// bit-identical on all ranks (the dual iterate nu must not drift between ranks).  Hand-shake: one system-scope
+// release store per peer into its signal pad, one acquire spin per peer on our own pad; per-CTA slots so the CTAs of
+// the grid need no sync among themselves.  Buffers rotate over 3 slots (see pools.py), which makes reuse safe without
+// a second hand-shake: a rank that has seen everybody's "ready k" knows everybody finished reading slot k-1.
+#include "cfmm_dev.cuh"
+
+using namespace cfmm;
+
+namespace {
+
+constexpr int kArThreads = 256;
+constexpr int kArCtas = 4;
+constexpr int kPadBase = 512;      // first signal-pad word we use (torch's own barriers live below)
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(kArThreads)
+k_allreduce_oneshot(const double* const* __restrict__ bufs, uint32_t* const* __restrict__ pads, int rank, int world,
+                    long long offset, int n, double* __restrict__ out, uint32_t seq, int channel) {
+    // the partial vector of this rank was produced by earlier kernels on this stream
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int tid = threadIdx.x;
+    const int slot0 = kPadBase + (channel * kArCtas + blockIdx.x) * world;
+    if (tid < world && tid != rank) st_release_sys(pads[tid] + slot0 + rank, seq);          // "my partial k is ready"
+    if (tid < world && tid != rank) {
+        const uint32_t* mine = pads[rank] + slot0 + tid;
+        while ((int)(ld_acquire_sys(mine) - seq) < 0) { }
+    }
+    __syncthreads();
+    const int per = (n + kArCtas - 1) / kArCtas;
+    const int lo = blockIdx.x * per, hi = min(n, lo + per);
+    for (int j = lo + tid; j < hi; j += kArThreads) {
+        double s = 0.0;
+        for (int r = 0; r < world; ++r) s += __ldcv(bufs[r] + offset + j);               // rank order: same bits everywhere
+        out[j] = s;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int cfmm_allreduce_oneshot(const void* peer_bufs_dev, const void* peer_pads_dev, int32_t rank, int32_t world,
+                           int64_t offset_elems, int32_t n, double* out, uint32_t seq, int32_t channel, void* stream) {
+    if (!peer_bufs_dev || !peer_pads_dev || !out) return CFMM_E_NULL;
+    if (world < 1 || world > 64 || rank < 0 || rank >= world || n <= 0 || channel < 0 || channel > 3) return CFMM_E_SIZE;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kArCtas); cfg.blockDim = dim3(kArThreads); cfg.dynamicSmemBytes = 0;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k_allreduce_oneshot, static_cast<const double* const*>(peer_bufs_dev),
+                       static_cast<uint32_t* const*>(const_cast<void*>(peer_pads_dev)), (int)rank, (int)world,
+                       (long long)offset_elems, (int)n, out, seq, (int)channel);
+    return check_launch();
+}
+
+}  // extern "C"

@@ -457,6 +457,33 @@ class PoolStore:
         self.evals = 0
         self.hvps = 0
 
+    # -- multi-GPU: fused peer-memory all-reduce ---------------------------------------------------
+    def enable_peer_allreduce(self, group=None):
+        """Pool-sharded stores (world > 1): keep the partial [psi | arb] and y vectors in torch symmetric memory and
+        finish every evaluate()/hvp() with cfmm_allreduce_oneshot (NVLink peer reads, PDL-chained behind the pool
+        kernels) instead of returning a partial for NCCL.  Collective: every rank must call it."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        group = group or dist.group.WORLD
+        n = self.n_tokens
+        f64 = dict(dtype=torch.float64, device=self.device)
+        self._sym_acc = symm.empty((3, n + 1), **f64); self._sym_acc.zero_()
+        self._sym_y = symm.empty((3, n), **f64); self._sym_y.zero_()
+        self._hdl_acc = symm.rendezvous(self._sym_acc, group)
+        self._hdl_y = symm.rendezvous(self._sym_y, group)
+        self._red_acc = torch.zeros(n + 1, **f64)
+        self._red_y = torch.zeros(n, **f64)
+        self._peer_rank, self._peer_world = dist.get_rank(group), dist.get_world_size(group)
+        self._seq_acc = self._seq_y = 0
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group)
+        self.reduces_internally = True
+
+    def _peer_reduce(self, hdl, slot, n, out, seq, channel, st):
+        _lib.check(self.lib.cfmm_allreduce_oneshot(int(hdl.buffer_ptrs_dev), int(hdl.signal_pad_ptrs_dev),
+                                                   self._peer_rank, self._peer_world, slot * n, n, out.data_ptr(),
+                                                   seq, channel, st), "cfmm_allreduce_oneshot")
+
     # -- helpers -------------------------------------------------------------------------------
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -475,9 +502,14 @@ class PoolStore:
     def evaluate(self, nu: torch.Tensor, eps: float = 0.0, trades: bool = False, hess: bool = False):
         """psi(nu) (n_tokens) and arb(nu) (1) for this rank's pools, as views into one (n+1) buffer."""
         st = self._stream()
-        acc = self._acc2[self._acc_i]
-        nxt = self._acc2[self._acc_i ^ 1]
-        self._acc_i ^= 1
+        peer = getattr(self, "reduces_internally", False)
+        if peer:                            # 3-slot rotation in symmetric memory (see csrc/cfmm_allreduce.cu)
+            k = self._seq_acc % 3
+            acc, nxt = self._sym_acc[k], self._sym_acc[(k + 1) % 3]
+        else:
+            acc = self._acc2[self._acc_i]
+            nxt = self._acc2[self._acc_i ^ 1]
+            self._acc_i ^= 1
         if not self._blocked_first:       # otherwise the previous blocked launch already cleared `acc`
             _lib.check(self.lib.cfmm_zero(acc.data_ptr(), acc.numel() * 8, st), "cfmm_zero")
         lognu = torch.log(nu) if self.has_geomean else None
@@ -496,13 +528,22 @@ class PoolStore:
                                         C.byref(out) if out is not None else None, st)
             _lib.check(rc, "cfmm_arb_eval")
         self.evals += 1
+        if peer:
+            self._seq_acc += 1
+            self._peer_reduce(self._hdl_acc, k, self.n_tokens + 1, self._red_acc, self._seq_acc, 0, st)
+            return self._red_acc
         return acc
 
     def hvp(self, vt: torch.Tensor) -> torch.Tensor:
         st = self._stream()
-        y = self._y2[self._y_i]
-        ynxt = self._y2[self._y_i ^ 1]
-        self._y_i ^= 1
+        peer = getattr(self, "reduces_internally", False)
+        if peer:
+            k = self._seq_y % 3
+            y, ynxt = self._sym_y[k], self._sym_y[(k + 1) % 3]
+        else:
+            y = self._y2[self._y_i]
+            ynxt = self._y2[self._y_i ^ 1]
+            self._y_i ^= 1
         if not self._blocked_first:
             _lib.check(self.lib.cfmm_zero(y.data_ptr(), y.numel() * 8, st), "cfmm_zero")
         for b in self.buckets:
@@ -515,6 +556,10 @@ class PoolStore:
                                    b.hmask.data_ptr(), vt.data_ptr(), y.data_ptr(), st)
             _lib.check(rc, "cfmm_hvp")
         self.hvps += 1
+        if peer:
+            self._seq_y += 1
+            self._peer_reduce(self._hdl_y, k, self.n_tokens, self._red_y, self._seq_y, 1, st)
+            return self._red_y
         return y
 
     def hess_diag(self) -> torch.Tensor:

@@ -108,9 +108,12 @@ def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 0.1
         linear_solver = "dense" if (n <= 256 or (has_sum and n <= 4096)) else "cg"
     evals0, hvps0 = ev.evals, ev.hvps
     history = []
+    internal = bool(getattr(ev, "reduces_internally", False))     # PoolStore.enable_peer_allreduce(): no NCCL needed
 
     def G(nu_, hess=True, trades=False):
-        acc = comm.allreduce(ev.evaluate(nu_, eps_t, trades=trades, hess=hess))
+        acc = ev.evaluate(nu_, eps_t, trades=trades, hess=hess)
+        if not internal:
+            acc = comm.allreduce(acc)
         psi = acc[:n].clone()
         g = torch.dot(nu_ - c, a) + acc[n]
         return psi, g
@@ -198,7 +201,8 @@ def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 0.1
         # is a true optimality certificate; stop on it rather than on the multiplier step, whose floor is
         # (fp64 resolution of the price ratio) / eps.
         psi_s, _ = G(nu, hess=False, trades=True)
-        acc0 = comm.allreduce(ev.evaluate(nu, 0.0, trades=False, hess=False))
+        acc0 = ev.evaluate(nu, 0.0, trades=False, hess=False)
+        acc0 = acc0 if internal else comm.allreduce(acc0)
         dual_now = float(torch.dot(nu - c, a) + acc0[n])
         gap_now = (dual_now - float(torch.dot(c, psi_s))) / max(abs(dual_now), 1e-300)
         if verbose:
@@ -210,7 +214,8 @@ def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 0.1
     # ---- final read-back + certificate: primal from the (smoothed, pool-feasible) trades, dual exact
     psi_f, _ = G(nu, hess=False, trades=final_trades)
     if has_sum:
-        acc0 = comm.allreduce(ev.evaluate(nu, 0.0, trades=False, hess=False))
+        acc0 = ev.evaluate(nu, 0.0, trades=False, hess=False)
+        acc0 = acc0 if internal else comm.allreduce(acc0)
         arb_exact = float(acc0[n])
     else:
         arb_exact = float(torch.dot(nu, psi_f))     # arb = nu'psi for the exact evaluation
@@ -238,7 +243,8 @@ def _pcg(ev, comm, rhs, fr, diag, eta, max_it):
     if r0 == 0.0:
         return x
     for k in range(max_it):
-        Hp = comm.allreduce(ev.hvp(p)) * fr
+        Hp = ev.hvp(p)
+        Hp = (Hp if getattr(ev, "reduces_internally", False) else comm.allreduce(Hp)) * fr
         pHp = torch.dot(p, Hp)
         vals = torch.stack([pHp, rz, torch.dot(p, p * torch.clamp(diag, min=1e-300))]).tolist()
         if vals[0] <= 1e-14 * vals[2]:          # (near-)zero curvature: homogeneity direction

@@ -154,6 +154,17 @@ int cfmm_blocked_solve(const cfmm_blocked_pairs* b, int32_t n_tokens, const doub
                        const uint8_t* eq, const uint8_t* pinned, double* nu, double* psi_out, void* work,
                        const cfmm_solve_params* prm, cfmm_solve_result* res, void* stream);
 
+/*
+ * One-shot all-reduce (sum) of out[0..n) = sum_r peer_buf[r][offset .. offset+n) over NVLink peer memory: the ONE
+ * collective of a pool-sharded dual evaluation, fused into the launch chain (PDL) right behind the
+ * evaluation kernels.  peer_bufs_dev / peer_pads_dev: DEVICE arrays of `world` pointers to every rank's partial
+ * buffer / signal pad (torch symmetric memory: hdl.buffer_ptrs_dev, hdl.signal_pad_ptrs_dev).  seq: strictly
+ * increasing per call and equal on all ranks; channel 0..3 separates concurrent uses (psi, y).  Callers rotate the
+ * partial buffers over 3 slots.  Same bits on every rank (fixed rank order).
+ */
+int cfmm_allreduce_oneshot(const void* peer_bufs_dev, const void* peer_pads_dev, int32_t rank, int32_t world,
+                           int64_t offset_elems, int32_t n, double* out, uint32_t seq, int32_t channel, void* stream);
+
 /* SUM buckets: theta_bar <- current fills (= lambda), returns max_i |change|/R in move[0] (device). */
 int cfmm_sum_update_multipliers(const cfmm_bucket* bucket, const double* lambda, double* theta_bar_out,
                                 double* move, void* stream);
