@@ -197,7 +197,7 @@ def workload_config(n_gpus, scaling):
     return {"workload": "BASELINE.json configs[4]: 1M constant-product pools, 4096 tokens, Arbitrage(c=p), seed 3",
             "pools_per_gpu": per, "n_tokens": N_TOKENS, "parallelism": f"pool-shard x{n_gpus}",
             "l2": f"rotating {N_INSTANCES} pool instances per GPU ({N_INSTANCES * per * 32 // 2**20} MiB) > 126 MB L2",
-            "collective": "none" if n_gpus == 1 else "one all-reduce of n_tokens+1 f64 per step (NCCL)"}
+            "collective": "none" if n_gpus == 1 else "one all-reduce of n_tokens+1 f64 per step"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -231,13 +231,22 @@ def run_b200(args):
             s = dict(s, idx=s["idx"][sl], reserves=s["reserves"][sl], gamma=s["gamma"][sl])
         hp = cf.HostPools.from_pairs(N_TOKENS, s["idx"], s["reserves"], s["gamma"])
         stores.append(cf.PoolStore(hp, device=dev, validate=False))
+        if world > 1 and args.collective == "peer":
+            try:
+                stores[-1].enable_peer_allreduce()
+            except Exception as e:                       # symmetric memory unavailable: NCCL does the all-reduce
+                if rank == 0:
+                    print(f"peer all-reduce unavailable ({type(e).__name__}: {e}); falling back to NCCL", file=sys.stderr)
+                args.collective = "nccl"
         p = I.synth_const_product(8, N_TOKENS, seed=3)["prices"]        # same token prices on every rank
         nus.append(torch.as_tensor(p * np.exp(0.01 * np.random.default_rng(k).standard_normal(N_TOKENS)), **f64))
     lib = stores[0].lib
 
+    peer = world > 1 and args.collective == "peer"
+
     def step(i):
-        acc = stores[i % N_INSTANCES].evaluate(nus[i % N_INSTANCES])
-        if world > 1:
+        acc = stores[i % N_INSTANCES].evaluate(nus[i % N_INSTANCES])      # peer mode: already all-reduced
+        if world > 1 and not peer:
             dist.all_reduce(acc)
         return acc
 
@@ -252,7 +261,7 @@ def run_b200(args):
     # N = 1: the K steps are captured once into CUDA graphs of CHUNK steps each and replayed, so the timed
     # region holds kernel work only (no Python / ctypes launch overhead between the ~10 us kernels).
     CHUNK = 64
-    use_graph = not args.no_graph and args.steps >= CHUNK and (world == 1 or args.graph_nccl)
+    use_graph = not args.no_graph and args.steps >= CHUNK and (world == 1 or peer or args.graph_nccl)
     steps = (args.steps // CHUNK) * CHUNK if use_graph else args.steps
     graph = None
     if use_graph:
@@ -319,7 +328,13 @@ def run_b200(args):
         for rep in range(3):
             barrier()
             t0 = time.perf_counter()
-            r = cf.solve_pools(hp, cf.Arbitrage(s["prices"]), tol=1e-6, want_trades=False, device=dev)
+            if world > 1:
+                st_e = cf.PoolStore(hp, device=dev, rank=rank, world=world, validate=False)
+                if peer:
+                    st_e.enable_peer_allreduce()
+                r = cf.solve_pools(hp, cf.Arbitrage(s["prices"]), tol=1e-6, want_trades=False, store=st_e)
+            else:
+                r = cf.solve_pools(hp, cf.Arbitrage(s["prices"]), tol=1e-6, want_trades=False, device=dev)
             torch.cuda.synchronize()
             runs.append((time.perf_counter() - t0, r))
         wall, r = min(runs, key=lambda x: x[0])
@@ -349,13 +364,18 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(n_gpus, args.scaling), "roofline": roofline, "cpu_baseline": cpu,
+            "config": dict(workload_config(n_gpus, args.scaling),
+                           **({"collective_impl": ("cfmm_allreduce_oneshot over NVLink peer memory, PDL-chained" if peer
+                                                   else "NCCL all_reduce")} if world > 1 else {})),
+            "roofline": roofline, "cpu_baseline": cpu,
             "e2e": e2e, "time_to_1e-6_gap": time_to_gap, "gpu_launches": launches, "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        sys.stdout.flush()
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        os._exit(0)          # captured graphs + symmetric memory: skip the (hang-prone) communicator teardown
 
 
 def main():
@@ -369,6 +389,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer solve leg (profiling runs)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of CUDA-graph replay")
     ap.add_argument("--graph-nccl", action="store_true", help="N>1: capture the all-reduce into the step graphs too")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="N>1: fused one-shot NVLink all-reduce (cfmm_allreduce_oneshot) or NCCL")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 20:
