@@ -14,38 +14,52 @@ using namespace cfmm;
 
 namespace {
 
-constexpr int kArThreads = 256;
-constexpr int kArCtas = 4;
-constexpr int kPadBase = 512;      // first signal-pad word we use (torch's own barriers live below)
+constexpr int kArThreads = 256;     // one output element per thread
+constexpr int kArMaxCtas = 64;      // signal-pad slots reserved per channel: kArMaxCtas * world words
+constexpr int kPadBase = 512;       // first signal-pad word we use (torch's own barriers live below)
+constexpr int kMaxWorld = 16;
 
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
 
+// Every CTA hand-shakes on its own pad slots (no intra-grid sync), then each thread fetches its element from all
+// peers with independent loads in flight and adds them in rank order.
 __global__ void __launch_bounds__(kArThreads)
 k_allreduce_oneshot(const double* const* __restrict__ bufs, uint32_t* const* __restrict__ pads, int rank, int world,
                     long long offset, int n, double* __restrict__ out, uint32_t seq, int channel) {
-    // the partial vector of this rank was produced by earlier kernels on this stream
+    // the partial vector of this rank was produced by earlier kernels on this stream: wait for them (PDL), after
+    // that every write of theirs (red.add resolved in this GPU's L2) is visible to peers reading over NVLink
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int tid = threadIdx.x;
-    const int slot0 = kPadBase + (channel * kArCtas + blockIdx.x) * world;
-    if (tid < world && tid != rank) st_release_sys(pads[tid] + slot0 + rank, seq);          // "my partial k is ready"
+    const int slot0 = kPadBase + (channel * kArMaxCtas + blockIdx.x) * world;
     if (tid < world && tid != rank) {
+        st_relaxed_sys(pads[tid] + slot0 + rank, seq);                       // "my partial `seq` is ready"
         const uint32_t* mine = pads[rank] + slot0 + tid;
-        while ((int)(ld_acquire_sys(mine) - seq) < 0) { }
+        while ((int)(ld_acquire_sys(mine) - seq) < 0) { }                    // peer `tid` is ready too
     }
     __syncthreads();
-    const int per = (n + kArCtas - 1) / kArCtas;
-    const int lo = blockIdx.x * per, hi = min(n, lo + per);
-    for (int j = lo + tid; j < hi; j += kArThreads) {
+    const int j = blockIdx.x * kArThreads + tid;
+    if (j < n) {
+        double v[kMaxWorld];
+#pragma unroll
+        for (int r = 0; r < kMaxWorld; ++r)
+            if (r < world) v[r] = ld_relaxed_sys_f64(bufs[r] + offset + j);
         double s = 0.0;
-        for (int r = 0; r < world; ++r) s += __ldcv(bufs[r] + offset + j);               // rank order: same bits everywhere
+#pragma unroll
+        for (int r = 0; r < kMaxWorld; ++r)
+            if (r < world) s += v[r];                                        // rank order: same bits on every rank
         out[j] = s;
     }
 }
@@ -57,9 +71,12 @@ extern "C" {
 int cfmm_allreduce_oneshot(const void* peer_bufs_dev, const void* peer_pads_dev, int32_t rank, int32_t world,
                            int64_t offset_elems, int32_t n, double* out, uint32_t seq, int32_t channel, void* stream) {
     if (!peer_bufs_dev || !peer_pads_dev || !out) return CFMM_E_NULL;
-    if (world < 1 || world > 64 || rank < 0 || rank >= world || n <= 0 || channel < 0 || channel > 3) return CFMM_E_SIZE;
+    if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || n <= 0 || channel < 0 || channel > 3)
+        return CFMM_E_SIZE;
+    const int ctas = (n + kArThreads - 1) / kArThreads;
+    if (ctas > kArMaxCtas) return CFMM_E_SIZE;        /* n_tokens <= 16383 for the fused path; larger: use NCCL */
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(kArCtas); cfg.blockDim = dim3(kArThreads); cfg.dynamicSmemBytes = 0;
+    cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(kArThreads); cfg.dynamicSmemBytes = 0;
     cfg.stream = static_cast<cudaStream_t>(stream);
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

@@ -466,6 +466,11 @@ class PoolStore:
         import torch.distributed._symmetric_memory as symm
         group = group or dist.group.WORLD
         n = self.n_tokens
+        if n + 1 > 64 * 256:
+            raise _lib.CfmmError("fused peer all-reduce supports n_tokens < 16384; use NCCL (Comm) beyond that")
+        # our hand-shake slots live above word 512 of the signal pad: 4 channels x 64 CTAs x 16 ranks words
+        if symm.get_signal_pad_size() < 65536:
+            symm.set_signal_pad_size(65536)
         f64 = dict(dtype=torch.float64, device=self.device)
         self._sym_acc = symm.empty((3, n + 1), **f64); self._sym_acc.zero_()
         self._sym_y = symm.empty((3, n), **f64); self._sym_y.zero_()
