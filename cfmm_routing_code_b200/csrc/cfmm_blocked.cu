@@ -59,7 +59,6 @@ struct BlockedArgs {
     double* delta;                // eval, optional: [2][M] blocked order
     double* lambda;
     double* hcoef;                // eval, optional: [M]
-    int dbg;                      // MEASUREMENT ONLY: bit0 skip row phase, bit1 skip pool math, bit2 skip nu gather
 };
 
 __device__ __forceinline__ unsigned round16(unsigned bytes) { return (bytes + 15u) & ~15u; }
@@ -216,7 +215,6 @@ k_blocked(const BlockedArgs A) {
         // ---- phase 3: one thread per row; a row is a CONTIGUOUS run of g (the pool phase scattered the flows
         // into row order), rows are sorted by length so a warp's 32 rows have (nearly) equal trip counts.
         // Fixed summation order; one red.add per row.
-        if (!(A.dbg & 1))
         for (int r = tid; r < d.y; r += THREADS) {
             const uint32_t rw = S.rows[r];
             const double* q = g + row_start(rw);
@@ -226,8 +224,7 @@ k_blocked(const BlockedArgs A) {
             for (; k + 4 <= len; k += 4) { s0 += q[k] + q[k + 2]; s1 += q[k + 1] + q[k + 3]; }
             for (; k < len; ++k) s0 += q[k];
             const double s = s0 + s1;
-            if (A.dbg & 8) acc += s;
-            else if (s != 0.0) atomicAdd(A.out + S.tok[row_tok(rw)], s);
+            if (s != 0.0) atomicAdd(A.out + S.tok[row_tok(rw)], s);
         }
         if (MODE != 2 && nxt < t_end) {
 #pragma unroll
@@ -260,7 +257,6 @@ struct Cfg0 { static constexpr int P = 1024, T = 512, S = 2, CTAS = 2; };   // 2
 struct Cfg1 { static constexpr int P = 512, T = 512, S = 3, CTAS = 2; };    // 2 x (64 + 12) KB, deeper ring
 struct Cfg2 { static constexpr int P = 512, T = 256, S = 2, CTAS = 4; };    // 4 x (43 + 12) KB
 int g_cfg = 0;
-int g_dbg = 0;
 int g_pdl = 1;
 int g_row_cap = 32;
 
@@ -314,7 +310,6 @@ int fill_args(const cfmm_blocked_pairs* b, BlockedArgs& A) {
     A.zero_next = nullptr; A.n_zero = 0;
     A.slab[0] = A.slab[1] = A.slab[2] = nullptr;
     A.vec = nullptr; A.out = nullptr; A.arb = nullptr; A.delta = A.lambda = A.hcoef = nullptr;
-    A.dbg = g_dbg;
     return CFMM_OK;
 }
 
@@ -337,7 +332,6 @@ int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int3
 int cfmm_set_blocked_config(int32_t cfg) {
     if (cfg >= 300) { const int c = cfg - 300; if (c < 8 || c > 32) return CFMM_E_KIND; g_row_cap = c; return CFMM_OK; }
     if (cfg >= 200) { g_pdl = cfg - 200; return CFMM_OK; }      // 200 / 201: programmatic dependent launch off / on
-    if (cfg >= 100) { g_dbg = cfg - 100; return CFMM_OK; }      // measurement-only phase switches
     if (cfg < 0 || cfg > 2) return CFMM_E_KIND;
     g_cfg = cfg;
     return CFMM_OK;

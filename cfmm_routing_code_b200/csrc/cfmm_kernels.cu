@@ -198,14 +198,13 @@ __device__ __forceinline__ void issue_pair_tile(PairStage* st, uint64_t* bar, lo
     bulk_g2s(st->i1, idx + ld + o, kTile * 4, bar);
 }
 
-template <int KIND, bool TRADES, bool HESS, bool SCATTER = true>
+template <int KIND, bool TRADES, bool HESS>
 __global__ void __launch_bounds__(kTmaThreads, 2)
 k_eval_pair_tma(long long m, long long ld, int n_tokens, const double* __restrict__ R, const int* __restrict__ idx,
                 const double* __restrict__ gamma, const double* __restrict__ thbar, double eps,
                 const double* __restrict__ nu, double* psi, double* arb, double* delta, double* lambda,
-                double* hcoef, int n_rep = 1, long long rep_stride = 0) {
+                double* hcoef) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    psi += (long long)(blockIdx.x % n_rep) * rep_stride;
     PairStage* stages = reinterpret_cast<PairStage*>(smem_raw);
     __shared__ uint64_t full[kStages];
     __shared__ double part[kTmaThreads / 32];
@@ -256,10 +255,8 @@ k_eval_pair_tma(long long m, long long ld, int n_tokens, const double* __restric
                     }
                 }
                 if (HESS) hcoef[i] = h;
-                if (SCATTER) {
-                    if (y0 != 0.0) atomicAdd(psi + i0, y0);
-                    if (y1 != 0.0) atomicAdd(psi + i1, y1);
-                }
+                if (y0 != 0.0) atomicAdd(psi + i0, y0);
+                if (y1 != 0.0) atomicAdd(psi + i1, y1);
                 acc += n0 * y0 + n1 * y1;
             }
         }
@@ -520,7 +517,7 @@ inline int grid_for(long long m, int blocks_per_sm) {
 }
 
 inline bool use_shared(int n_tokens, long long m) {
-    if (g_scatter_mode == 1 || g_scatter_mode >= 3) return false;
+    if (g_scatter_mode == 1 || g_scatter_mode == 3) return false;
     const bool fits = (size_t)n_tokens * sizeof(double) <= 96 * 1024;
     if (g_scatter_mode == 2) return fits;
     // auto: privatise only when each CTA makes many more contributions than it has bins to flush
@@ -530,15 +527,6 @@ inline bool use_shared(int n_tokens, long long m) {
 template <typename K>
 inline void allow_smem(K kernel, size_t bytes) {
     if (bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-}
-
-__global__ void k_fold(const double* __restrict__ rep, int n_rep, long long rs, int n, double* out) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n) {
-        double s = 0.0;
-        for (int r = 0; r < n_rep; ++r) s += rep[r * rs + j];
-        out[j] += s;
-    }
 }
 
 inline bool tma_ok(const cfmm_bucket* b) {
@@ -565,41 +553,7 @@ int launch_pair(const cfmm_bucket* b, int n_tokens, const double* nu, double eps
         const long long cap = 2LL * num_sms();
         const int grid = (int)(ntiles < cap ? ntiles : cap);
         kern<<<grid, kTmaThreads, sm, st>>>(m, b->stride, n_tokens, b->reserves, b->tok_idx, b->gamma, b->theta_bar,
-                                            eps, nu, psi, arb, delta, lambda, hcoef, 1, 0);
-        return check_launch();
-    }
-    if (g_scatter_mode >= 5 && tma_ok(b)) {
-        // EXPERIMENT: psi replicated n_rep times (mode value = n_rep) to cut same-address serialisation in L2
-        const int n_rep = g_scatter_mode;
-        const long long rs = ((long long)n_tokens + 15) / 16 * 16;
-        static double* scratch = nullptr; static long long cap_elems = 0;
-        if (cap_elems < rs * n_rep) {
-            if (scratch) cudaFree(scratch);
-            cudaMalloc(&scratch, sizeof(double) * rs * n_rep); cap_elems = rs * n_rep;
-        }
-        cudaMemsetAsync(scratch, 0, sizeof(double) * rs * n_rep, st);
-        auto kern = k_eval_pair_tma<KIND, TRADES, HESS>;
-        const size_t sm = (size_t)kStages * kStageBytes;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        const long long ntiles = (m + kTile - 1) / kTile;
-        const long long cap = 2LL * num_sms();
-        kern<<<(int)(ntiles < cap ? ntiles : cap), kTmaThreads, sm, st>>>(
-            m, b->stride, n_tokens, b->reserves, b->tok_idx, b->gamma, b->theta_bar, eps, nu, scratch, arb, delta, lambda,
-            hcoef, n_rep, rs);
-        k_fold<<<(n_tokens + 255) / 256, 256, 0, st>>>(scratch, n_rep, rs, n_tokens, psi);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        return check_launch();
-    }
-    if (g_scatter_mode == 4 && tma_ok(b) && KIND == CFMM_KIND_PRODUCT && !TRADES && !HESS) {
-        // MEASUREMENT ONLY: the same kernel without the psi scatter (wrong results; bounds the atomics' cost)
-        auto kern = k_eval_pair_tma<CFMM_KIND_PRODUCT, false, false, false>;
-        const size_t sm = (size_t)kStages * kStageBytes;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        const long long ntiles = (m + kTile - 1) / kTile;
-        const long long cap = 2LL * num_sms();
-        kern<<<(int)(ntiles < cap ? ntiles : cap), kTmaThreads, sm, st>>>(
-            m, b->stride, n_tokens, b->reserves, b->tok_idx, b->gamma, b->theta_bar, eps, nu, psi, arb, delta, lambda, hcoef,
-            1, 0);
+                                            eps, nu, psi, arb, delta, lambda, hcoef);
         return check_launch();
     }
     if (use_shared(n_tokens, m)) {
@@ -801,7 +755,7 @@ int cfmm_zero(void* ptr, int64_t bytes, void* stream) {
 }
 
 int cfmm_set_scatter_mode(int32_t mode) {
-    if (mode < 0 || mode > 64) return CFMM_E_KIND;
+    if (mode < 0 || mode > 3) return CFMM_E_KIND;
     g_scatter_mode = mode;
     return CFMM_OK;
 }

@@ -57,16 +57,12 @@ def graph_time(fn, reps=64, replays=5):
     return e0.elapsed_time(e1) / (reps * replays) * 1e-3
 
 
-modes = [int(x) for x in sys.argv[1:]] or [0]
-for mode in modes:
-    lib.cfmm_set_scatter_mode(0)
-    lib.cfmm_set_blocked_config(100 + mode)      # mode = debug phase mask here
+for mode in [0]:
     for label, kw in (("eval", {}), ("eval+hess", dict(hess=True))):
         t_rot = graph_time(lambda i: stores[i % ninst][0].evaluate(nus[i % ninst], **kw))
         t_hot = graph_time(lambda i: stores[0][0].evaluate(nus[0], **kw))
         print(f"mode {mode:2d} {label:12s} rotating {t_rot*1e6:8.1f} us  {m/t_rot/1e9:7.2f} Gpool/s  "
               f"{32*m/t_rot/1e9:7.0f} GB/s | L2-hot {t_hot*1e6:8.1f} us {32*m/t_hot/1e9:7.0f} GB/s", flush=True)
-lib.cfmm_set_blocked_config(100)
 st = stores[0][0]
 st.evaluate(nus[0], hess=True)
 v = torch.randn(n, dtype=torch.float64, device=dev)

@@ -12,8 +12,7 @@ for k in range(6):
 nu = torch.as_tensor(stores[0][1]["prices"] * np.exp(0.01 * np.random.default_rng(0).standard_normal(n)),
                      dtype=torch.float64, device="cuda")
 lib = stores[0][0].lib
-for mode in [int(x) for x in sys.argv[1:]]:
-    lib.cfmm_set_scatter_mode(mode)
+for mode in [0]:
     for k in range(6):
         stores[k][0].evaluate(nu)
     torch.cuda.synchronize()
