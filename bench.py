@@ -323,7 +323,7 @@ def run_b200(args):
     time_to_gap = None
     if (rank == 0 or world > 1) and not args.no_e2e:
         s = I.synth_const_product(M_POOLS, N_TOKENS, seed=3)
-        hp = cf.HostPools.from_pairs(N_TOKENS, s["idx"], s["reserves"], s["gamma"])
+        hp = cf.HostPools.from_pairs(N_TOKENS, s["idx"], s["reserves"], s["gamma"]).pin_memory()
         runs = []
         for rep in range(3):
             barrier()
@@ -343,7 +343,7 @@ def run_b200(args):
         h2d = hp.reserves.nbytes + hp.tok_idx.nbytes + hp.gamma.nbytes + 8 * N_TOKENS
         e2e = {"value": M_POOLS * r.evals / wall, "unit": UNIT, "h2d_bytes_per_step": int(h2d / max(world, 1)),
                "d2h_bytes_per_step": 16 * N_TOKENS + 64,
-               "what": "cf.solve_pools(host numpy pools, Arbitrage(p), tol=1e-6): upload + solve + psi/nu read-back; "
+               "what": "cf.solve_pools(pinned host numpy pools, Arbitrage(p), tol=1e-6): upload + layout build + solve + psi/nu read-back; "
                        "value = pools x dual evaluations / wall",
                "wall_s": wall, "evals": r.evals, "hvps": r.hvps, "iters": r.iters, "status": r.status,
                "gap": r.gap, "primal_infeas": r.primal_infeas}

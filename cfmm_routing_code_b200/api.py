@@ -167,3 +167,21 @@ def solve_pools(hp: HostPools, utility, nu0=None, tol: float = 1e-8, max_iter: i
                   nu=info.nu.cpu().numpy(), dual_value=info.dual_value, gap=info.gap,
                   primal_infeas=info.primal_infeas, iters=info.iters, evals=info.evals, hvps=info.hvps,
                   status=info.status, wall_s=info.wall_s, info=info)
+
+
+def solve_sweep(local_indices, reserves, fees, kinds, weights, utilities, n_tokens: Optional[int] = None,
+                tol: float = 1e-8, device="cuda", **solver_kw) -> List[Result]:
+    """The loop of two-asset.py:40-100 as one call: the same pools under a sequence of utilities (there: Swap(0, 2, t)
+    for t in linspace(0, 50)).  The pool buckets are uploaded once and every solve is warm-started from the
+    previous prices, where the reference rebuilds the whole cvxpy problem per t (two-asset.py:47-91)."""
+    if n_tokens is None:
+        n_tokens = 1 + max(int(t) for l in local_indices for t in l)
+    hp = HostPools.from_lists(n_tokens, local_indices, reserves, fees, kinds, weights)
+    store = PoolStore(hp, device=device)
+    out: List[Result] = []
+    nu = None
+    for u in utilities:
+        r = solve_pools(hp, u, nu0=nu, tol=tol, store=store, **solver_kw)
+        nu = r.nu if r.status == "optimal" else None
+        out.append(r)
+    return out

@@ -76,6 +76,16 @@ class HostPools:
                          np.ascontiguousarray(reserves, np.float64).reshape(-1),
                          np.full(2 * m, 0.5), np.ascontiguousarray(gamma, np.float64), np.zeros(m, np.uint8))
 
+    def pin_memory(self) -> "HostPools":
+        """Move the arrays into page-locked host memory (in place) so PoolStore uploads run at full PCIe speed."""
+        keep = []
+        for name in ("tok_idx", "reserves", "weights", "gamma", "kind", "pool_ptr"):
+            t = torch.from_numpy(np.ascontiguousarray(getattr(self, name))).pin_memory()
+            keep.append(t)
+            setattr(self, name, t.numpy())
+        self._pinned = keep                  # the numpy views borrow these tensors' storage
+        return self
+
     def validate(self):
         if np.any(self.reserves <= 0) or not np.all(np.isfinite(self.reserves)):
             raise ValueError("reserves must be positive and finite")

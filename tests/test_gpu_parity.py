@@ -161,6 +161,40 @@ def test_reference_instances_end_to_end(golden):
         assert abs(r.value - golden["two_asset"][j]["value"]) <= 1e-6 * max(1.0, golden["two_asset"][j]["value"]), j
 
 
+def test_two_asset_sweep_all_50_points_match_golden(golden):
+    """two-asset.py:40-100: u(t) and the per-pool flows (lambdas - deltas, :93-94) for every t in linspace(0, 50)"""
+    d = I.two_asset_instance()
+    rs = cf.solve_sweep(d["local_indices"], d["reserves"], d["fees"], d["kinds"], d["weights"],
+                        [cf.Swap(d["tok_in"], d["tok_out"], t) for t in d["amounts"]], tol=1e-9)
+    assert len(rs) == 50
+    for j, r in enumerate(rs):
+        g = golden["two_asset"][j]
+        assert r.status == "optimal", j
+        assert abs(r.value - g["value"]) <= 1e-6 * max(1.0, g["value"]), j
+        np.testing.assert_allclose(r.psi, g["psi"], atol=2e-5)
+    # u(t) is concave and increasing in the tendered amount
+    u = np.array([r.value for r in rs])
+    assert np.all(np.diff(u) > 0) and np.all(np.diff(u, 2) < 1e-6)
+
+
+def test_back_to_back_evaluations_keep_their_buffers_consistent():
+    """ping-pong psi buffers cleared inside the kernels + programmatic dependent launch: 60 alternating calls"""
+    hp, s = H.cp_host_pools(60_000, 500, seed=23)
+    st = cf.PoolStore(hp)
+    nus = [torch.as_tensor(H.random_prices(s["prices"], k, 0.02), **F64) for k in range(3)]
+    ref = [st.evaluate(nu).clone() for nu in nus]
+    torch.cuda.synchronize()
+    for it in range(60):
+        k = (it * 7) % 3
+        out = st.evaluate(nus[k], hess=(it % 5 == 0)).clone()
+        assert float((out - ref[k]).abs().max()) <= 1e-9 * float(ref[k].abs().max()), it
+    st.evaluate(nus[0], hess=True)
+    v = torch.randn(500, **F64)
+    y0 = st.hvp(v).clone()
+    for _ in range(9):
+        assert float((st.hvp(v) - y0).abs().max()) <= 1e-9 * float(y0.abs().max())
+
+
 @pytest.mark.parametrize("linear_solver", ["cg", "dense"])
 def test_cfg2_solve_matches_oracle(linear_solver):
     """BASELINE.json configs[1]: 10k constant-product pools, 256 tokens."""
