@@ -78,38 +78,44 @@ __device__ __forceinline__ void issue_tile(Stage<P, NF>* st, uint64_t* bar, cons
     bulk_g2s(st->tok, A.tok + tile * BlockedCfg<P>::kTokMax, tok_b, bar);
 }
 
-// ---- per-pool operators: produce the two values (f0, f1) that the rows sum ----------------------
-// constant product with gi = 1/gamma (arbitrage.py:68-70): trade 0->1 iff nu1 R1 > nu0 R0 / gamma.
-//   v = rsqrt(num den gi); t = num v = sqrt(gamma num/den); 1/t = den gi v; h = sqrt(p0 p1 / gamma)/2 = w v / 2
+// ---- per-pool operator: the two net flows (f0, f1) of a constant-product pool (arbitrage.py:68-70) ----------
+// With gi = 1/gamma, p_j = nu_j R_j and v = rsqrt(p0 p1 gi):  a = p0 v, b = p1 v  (a b gi = 1).  The KKT solution
+// x_j = clip(R_j; gamma M/(2 nu_j), M/(2 nu_j)) reads  x0/R0 = clamp(1, b, b gi),  x1/R1 = clamp(1, a, a gi):
+// ratio > 1 => token tendered (Delta = R (ratio-1)/gamma), ratio < 1 => token received (Lambda = R (1-ratio)),
+// ratio = 1 on both => no-trade cone.  Branch-free, so the two pools a thread owns interleave in the pipeline.
+// h = sqrt(p0 p1 / gamma)/2 = w v / 2 on trading pools (Hs_i = h [[1,-1],[-1,1]] in log-price coordinates).
+// 1/sqrt(w) for positive, finite, normal w without the library routine's slow-path branch (which would fence the
+// two pools of a thread into separate reconvergence regions): scale the exponent into [1,4), seed with the fp32
+// MUFU.RSQ, two Newton steps in fp64 (22 -> 44 -> 88 bits), scale back.  ~1 ulp.
+__device__ __forceinline__ double rsqrt_pos(double w) {
+    const int hi = __double2hiint(w);
+    const int k = ((((hi >> 20) & 0x7ff) - 1023) >> 1);
+    const double ws = __hiloint2double(hi - (k << 21), __double2loint(w));
+    double y = (double)rsqrtf((float)ws);
+    const double hws = 0.5 * ws;
+    y = y * (1.5 - hws * y * y);
+    y = y * (1.5 - hws * y * y);
+    return __hiloint2double(__double2hiint(y) - (k << 20), __double2loint(y));
+}
+
 struct EvalOp {
-    static constexpr int NF = 3;
-    static constexpr bool kNeedsVec = true;
     template <bool TRADES, bool HESS>
     __device__ __forceinline__ static void apply(const BlockedArgs& A, long long q, double R0, double R1, double gi,
                                                  double n0, double n1, double& f0, double& f1, double& acc) {
         const double p0 = n0 * R0, p1 = n1 * R1;
-        const bool fwd = p1 > p0 * gi;
-        const bool bwd = p0 > p1 * gi;
-        f0 = 0.0; f1 = 0.0;
-        double h = 0.0;
-        if (fwd || bwd) {
-            const double num = fwd ? p1 : p0, den = fwd ? p0 : p1;
-            const double w = num * den * gi;
-            const double v = rsqrt(w);
-            const double t = num * v;
-            const double u = den * gi * v;
-            const double din = (fwd ? R0 : R1) * (t - 1.0) * gi;
-            const double lout = (fwd ? R1 : R0) * (1.0 - u);
-            f0 = fwd ? -din : lout;
-            f1 = fwd ? lout : -din;
-            h = 0.5 * w * v;
-            acc += n0 * f0 + n1 * f1;
-        }
+        const double w = p0 * p1 * gi;
+        const double v = rsqrt_pos(w);
+        const double a = p0 * v, b = p1 * v;
+        const double d0 = 1.0 - fmin(fmax(1.0, b), b * gi);
+        const double d1 = 1.0 - fmin(fmax(1.0, a), a * gi);
+        f0 = R0 * d0 * (d0 < 0.0 ? gi : 1.0);
+        f1 = R1 * d1 * (d1 < 0.0 ? gi : 1.0);
+        acc += n0 * f0 + n1 * f1;
         if (TRADES) {
             A.delta[q] = fmax(-f0, 0.0); A.delta[A.M + q] = fmax(-f1, 0.0);
             A.lambda[q] = fmax(f0, 0.0); A.lambda[A.M + q] = fmax(f1, 0.0);
         }
-        if (HESS) A.hcoef[q] = h;
+        if (HESS) A.hcoef[q] = (d0 != 0.0 || d1 != 0.0) ? 0.5 * w * v : 0.0;
     }
 };
 
@@ -174,24 +180,33 @@ k_blocked(const BlockedArgs A) {
         const long long far = tile + STAGES;
         int4 dfar = make_int4(0, 0, 0, 0);
         if (tid == 0 && far < t_end) dfar = __ldg(A.desc + far);
-        // ---- phase 2: per-pool values into f
+        // ---- phase 2: per-pool flows, scattered into row order.  All loads and math of the thread's NPOOL pools
+        // first, the shared-memory stores afterwards, so the independent chains overlap in the pipeline.
+        {
+            constexpr int NPOOL = P / THREADS;
+            double f0[NPOOL], f1[NPOOL];
+            uint32_t ps[NPOOL];
 #pragma unroll
-        for (int l = tid; l < P; l += THREADS) {
-            const uint32_t li = S.lid[l];
-            double f0, f1;
-            if (MODE == 0) {
-                EvalOp::apply<TRADES, HESS>(A, tile * P + l, S.a[0][l], S.a[1][l], S.a[2][l], nul[li & 0xffffu],
-                                            nul[li >> 16], f0, f1, acc);
-            } else if (MODE == 1) {
-                f0 = S.a[0][l] * (nul[li & 0xffffu] - nul[li >> 16]);
-                f1 = -f0;
-            } else {
-                f0 = S.a[0][l];
-                f1 = f0;
+            for (int u = 0; u < NPOOL; ++u) {
+                const int l = tid + u * THREADS;
+                const uint32_t li = S.lid[l];
+                ps[u] = S.pos[l];
+                if (MODE == 0) {
+                    EvalOp::apply<TRADES, HESS>(A, tile * P + l, S.a[0][l], S.a[1][l], S.a[2][l], nul[li & 0xffffu],
+                                                nul[li >> 16], f0[u], f1[u], acc);
+                } else if (MODE == 1) {
+                    f0[u] = S.a[0][l] * (nul[li & 0xffffu] - nul[li >> 16]);
+                    f1[u] = -f0[u];
+                } else {
+                    f0[u] = S.a[0][l];
+                    f1[u] = f0[u];
+                }
             }
-            const uint32_t ps = S.pos[l];
-            g[ps & 0xffffu] = f0;
-            g[ps >> 16] = f1;
+#pragma unroll
+            for (int u = 0; u < NPOOL; ++u) {
+                g[ps[u] & 0xffffu] = f0[u];
+                g[ps[u] >> 16] = f1[u];
+            }
         }
         __syncthreads();                 // g complete; nu_local of this tile is dead from here on
         // ---- prefetch nu_local of the NEXT tile into registers: the L2 latency hides behind the row phase
