@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(kVT) k_cg_init(Vecs V) {
 // one PCG iteration after y = Hs p:  stop flags: 1 = converged, 2 = (near-)zero curvature
 __global__ void __launch_bounds__(kVT) k_cg_step(Vecs V, const double* y, double eta, int first) {
     __shared__ double sh[33];
+    if (V.sc[S_STOP] != 0.0) return;                // an earlier iteration of this batch already finished the solve
     double pHp = 0, pdp = 0;
     for (int j = threadIdx.x; j < V.n; j += kVT) {
         const double hp = y[j] * V.fr[j];
@@ -249,11 +250,15 @@ int cfmm_blocked_solve(const cfmm_blocked_pairs* b, int32_t n_tokens, const doub
     if (rc) return rc;
     double err = INFINITY;
     int iters = 0, status = 1;     // 0 optimal, 1 max_iter, 2 stalled
+    bool have_kkt = false;         // V.grad / fr / pg and the host scalars describe (cur_nu, cur_acc)
+    constexpr int kCgBatch = 3;    // PCG iterations launched per host synchronisation
     for (; iters < prm->max_iter;) {
         ++iters;
         const double thr = fmin(1e-2, fmax(isfinite(err) ? err : 1e-2, 1e-14));
-        k_kkt<<<1, kVT, 0, st>>>(V, cur_nu, cur_acc, thr);
-        if (!fetch()) return CFMM_E_CUDA;
+        if (!have_kkt) {
+            k_kkt<<<1, kVT, 0, st>>>(V, cur_nu, cur_acc, thr);
+            if (!fetch()) return CFMM_E_CUDA;
+        }
         err = hsc[S_ERR];
         const double g0 = hsc[S_G];
         if (err <= prm->tol) { status = 0; break; }
@@ -263,48 +268,53 @@ int cfmm_blocked_solve(const cfmm_blocked_pairs* b, int32_t n_tokens, const doub
         if (rc) return rc;
         k_cg_init<<<1, kVT, 0, st>>>(V);
         const double eta = fmin(0.1, sqrt(err));
-        for (int k = 0; k < prm->cg_max; ++k) {
-            double* y = yb[yi];
-            double* ynx = yb[yi ^ 1];
-            yi ^= 1;
-            rc = cfmm_blocked_hvp(b, n, hcoef, V.p, y, ynx, st);
-            if (rc) return rc;
-            ++hvps;
-            k_cg_step<<<1, kVT, 0, st>>>(V, y, eta, k == 0);
+        for (int k = 0; k < prm->cg_max;) {
+            // a batch of iterations per synchronisation; k_cg_step turns into a no-op once the stop flag is set
+            for (int bi = 0; bi < kCgBatch && k < prm->cg_max; ++bi, ++k) {
+                double* y = yb[yi];
+                double* ynx = yb[yi ^ 1];
+                yi ^= 1;
+                rc = cfmm_blocked_hvp(b, n, hcoef, V.p, y, ynx, st);
+                if (rc) return rc;
+                ++hvps;
+                k_cg_step<<<1, kVT, 0, st>>>(V, y, eta, k == 0);
+            }
             if (!fetch()) return CFMM_E_CUDA;
             if (hsc[S_STOP] != 0.0) break;
         }
         k_direction<<<1, kVT, 0, st>>>(V);
-        // ---- projected Armijo backtracking along nu * exp(alpha dt)
+        // ---- projected Armijo backtracking along nu * exp(alpha dt); the KKT data of the trial point is computed
+        // speculatively behind it, so an accepted step (the rule) costs one synchronisation
         double alpha = 1.0;
         bool ok = false;
         for (int ls = 0; ls < 50; ++ls) {
             k_step<<<1, kVT, 0, st>>>(V, cur_nu, alpha, oth_nu);
             double* acct = eval(oth_nu);
             if (rc) return rc;
-            k_trial<<<1, kVT, 0, st>>>(V, cur_nu, oth_nu, acct);
+            k_trial<<<1, kVT, 0, st>>>(V, cur_nu, oth_nu, acct);          // uses the OLD gradient: before k_kkt
+            k_kkt<<<1, kVT, 0, st>>>(V, oth_nu, acct, thr);
             if (!fetch()) return CFMM_E_CUDA;
             const double gt = hsc[S_GT], lin = hsc[S_LIN];
             if (gt <= g0 + 1e-4 * lin) { ok = true; cur_acc = acct; break; }
             if (fabs(gt - g0) <= 1e-13 * fabs(g0)) {
-                // below the resolution of g: accept if the KKT residual improves
-                k_kkt<<<1, kVT, 0, st>>>(V, oth_nu, acct, thr);
-                if (!fetch()) return CFMM_E_CUDA;
-                if (hsc[S_ERR] < err) { ok = true; cur_acc = acct; break; }
-                break;          // V.grad now belongs to the rejected trial: stop here (handled as 'stalled' below)
+                // below the resolution of g: accept if the KKT residual improves, else give up (stalled)
+                if (hsc[S_ERR] < err) { ok = true; cur_acc = acct; }
+                break;
             }
+            // rejected: the gradient buffers now belong to the trial -- restore them at the current point
+            cur_acc = eval(cur_nu);
+            if (rc) return rc;
+            k_kkt<<<1, kVT, 0, st>>>(V, cur_nu, cur_acc, thr);
             alpha *= 0.5;
         }
         if (!ok) { status = 2; break; }
         double* t = cur_nu; cur_nu = oth_nu; oth_nu = t;
+        have_kkt = true;
     }
-    if (status != 0 && iters >= prm->max_iter) {
-        k_kkt<<<1, kVT, 0, st>>>(V, cur_nu, cur_acc, 1e-14);
-        if (!fetch()) return CFMM_E_CUDA;
-        err = hsc[S_ERR];
-    } else if (status == 2) {
-        // hcoef/acc belong to the rejected trial: re-evaluate at the accepted point for a consistent read-back
+    if (status != 0) {
+        // max_iter or stalled: make buffers and host scalars consistent with the accepted point
         cur_acc = eval(cur_nu);
+        if (rc) return rc;
         k_kkt<<<1, kVT, 0, st>>>(V, cur_nu, cur_acc, 1e-14);
         if (!fetch()) return CFMM_E_CUDA;
         err = hsc[S_ERR];

@@ -71,10 +71,12 @@ class HostPools:
     def from_pairs(n_tokens, idx, reserves, gamma) -> "HostPools":
         """m constant-product pools given as (m,2) arrays."""
         m = len(gamma)
-        return HostPools(int(n_tokens), np.arange(0, 2 * m + 1, 2, dtype=np.int64),
-                         np.ascontiguousarray(idx, np.int32).reshape(-1),
-                         np.ascontiguousarray(reserves, np.float64).reshape(-1),
-                         np.full(2 * m, 0.5), np.ascontiguousarray(gamma, np.float64), np.zeros(m, np.uint8))
+        hp = HostPools(int(n_tokens), np.arange(0, 2 * m + 1, 2, dtype=np.int64),
+                       np.ascontiguousarray(idx, np.int32).reshape(-1),
+                       np.ascontiguousarray(reserves, np.float64).reshape(-1),
+                       np.full(2 * m, 0.5), np.ascontiguousarray(gamma, np.float64), np.zeros(m, np.uint8))
+        hp._uniform_product = True          # known structure: split_buckets / validation take the device-side path
+        return hp
 
     def pin_memory(self) -> "HostPools":
         """Move the arrays into page-locked host memory (in place) so PoolStore uploads run at full PCIe speed."""
@@ -134,6 +136,11 @@ def split_buckets(hp: HostPools, rank: int = 0, world: int = 1) -> List["BucketS
     m = hp.m
     if m == 0:
         return []
+    if getattr(hp, "_uniform_product", False):
+        if world == 1:
+            return [BucketSpec(hp, _lib.KIND_PRODUCT, 2, None)]
+        lo, hi = (m * rank) // world, (m * (rank + 1)) // world
+        return [BucketSpec(hp, _lib.KIND_PRODUCT, 2, np.arange(lo, hi, dtype=np.int64))]
     uniform_pairs = int(hp.pool_ptr[-1]) == 2 * m and (hp.pool_ptr[1] - hp.pool_ptr[0]) == 2 and \
         bool(np.all(np.diff(hp.pool_ptr[::max(1, m // 64)]) == 2 * max(1, m // 64))) and \
         bool(np.array_equal(hp.pool_ptr[:3], np.arange(0, 2 * min(m, 2) + 1, 2)[:3]))
@@ -360,6 +367,12 @@ class BlockedBucket:
             R = torch.from_numpy(hp.reserves).to(device, non_blocking=True).view(-1, 2)
             idx = torch.from_numpy(hp.tok_idx).to(device, non_blocking=True).view(-1, 2).to(torch.int64)
             gam = torch.from_numpy(hp.gamma).to(device, non_blocking=True)
+            if getattr(hp, "_validate_on_device", False):          # same checks as HostPools.validate(), on the GPU
+                chk = torch.stack([R.min(), gam.min(), 1.0 - gam.max(), idx.min().double(),
+                                   float(hp.n_tokens - 1) - idx.max().double(),
+                                   torch.isfinite(R).all().double() - 0.5]).cpu()
+                if bool((chk[:2] <= 0).any()) or bool((chk[2:] < 0).any()):
+                    raise ValueError("invalid pool data (reserves > 0, fees in (0, 1], token ids in range, finite)")
         else:
             R = torch.as_tensor(np.ascontiguousarray(hp.reserves[spec.off].T), **f64)
             idx = torch.as_tensor(np.ascontiguousarray(hp.tok_idx[spec.off].T).astype(np.int64), device=device)
@@ -427,7 +440,10 @@ class PoolStore:
         if layout not in ("blocked", "plain"):
             raise ValueError("layout must be 'blocked' or 'plain'")
         if validate:
-            hp.validate()
+            if getattr(hp, "_uniform_product", False) and layout == "blocked" and world == 1:
+                hp._validate_on_device = True           # checked after the upload, by reductions on the GPU
+            else:
+                hp.validate()
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":

@@ -297,3 +297,9 @@ def test_error_codes_and_empty_bucket():
         cf.HostPools.from_lists(3, [[0, 1, 2]], [[1, 1, 1]], [0.99], ["sum"])
     with pytest.raises(ValueError):
         cf.HostPools.from_pairs(2, [[0, 1]], [[1.0, -1.0]], [0.99]).validate()
+    with pytest.raises(ValueError):                  # the device-side validation of the fast path
+        cf.PoolStore(cf.HostPools.from_pairs(2, [[0, 1]] * 4, [[1.0, -1.0]] * 4, [0.99] * 4))
+    with pytest.raises(ValueError):
+        cf.PoolStore(cf.HostPools.from_pairs(2, [[0, 5]] * 4, [[1.0, 1.0]] * 4, [0.99] * 4))
+    with pytest.raises(ValueError):
+        cf.PoolStore(cf.HostPools.from_pairs(2, [[0, 1]] * 4, [[1.0, 1.0]] * 4, [1.5] * 4))
