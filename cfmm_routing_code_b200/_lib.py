@@ -113,6 +113,8 @@ def load(build_if_missing: bool = True):
     lib.cfmm_reset_launch_count.restype = None
     lib.cfmm_last_cuda_error.restype = C.c_char_p
     lib.cfmm_version.restype = C.c_char_p
+    if os.environ.get("CFMM_BLOCKED_CFG"):          # kernel-variant override for experiments / A-B tests
+        lib.cfmm_set_blocked_config(int(os.environ["CFMM_BLOCKED_CFG"]))
     _lib = lib
     return lib
 

@@ -79,23 +79,18 @@ __device__ __forceinline__ void issue_tile(Stage<P, NF>* st, uint64_t* bar, cons
 }
 
 // ---- per-pool operator: the two net flows (f0, f1) of a constant-product pool (arbitrage.py:68-70) ----------
-// With gi = 1/gamma, p_j = nu_j R_j and v = rsqrt(p0 p1 gi):  a = p0 v, b = p1 v  (a b gi = 1).  The KKT solution
-// x_j = clip(R_j; gamma M/(2 nu_j), M/(2 nu_j)) reads  x0/R0 = clamp(1, b, b gi),  x1/R1 = clamp(1, a, a gi):
-// ratio > 1 => token tendered (Delta = R (ratio-1)/gamma), ratio < 1 => token received (Lambda = R (1-ratio)),
-// ratio = 1 on both => no-trade cone.  Branch-free, so the two pools a thread owns interleave in the pipeline.
+// With gi = 1/gamma, p_j = nu_j R_j and v = rsqrt(p0 p1 gi):  a = p0 v, b = p1 v  (a b gi = 1).  The KKT solution is
+//   b > 1 : tender token 0:  x0 = R0 b,       x1 = R1 a gi   =>  f0 = -R0 (b-1) gi,  f1 = R1 (1 - a gi)
+//   a > 1 : tender token 1:  x1 = R1 a,       x0 = R0 b gi   =>  f1 = -R1 (a-1) gi,  f0 = R0 (1 - b gi)
+//   else  : no-trade cone (then b gi >= 1 and a gi >= 1, so the "receive" expressions clamp to 0 by themselves).
+// Written with selects only (no divergent branch on the direction).
 // h = sqrt(p0 p1 / gamma)/2 = w v / 2 on trading pools (Hs_i = h [[1,-1],[-1,1]] in log-price coordinates).
-// 1/sqrt(w) for positive, finite, normal w without the library routine's slow-path branch (which would fence the
-// two pools of a thread into separate reconvergence regions): scale the exponent into [1,4), seed with the fp32
-// MUFU.RSQ, two Newton steps in fp64 (22 -> 44 -> 88 bits), scale back.  ~1 ulp.
-__device__ __forceinline__ double rsqrt_pos(double w) {
-    const int hi = __double2hiint(w);
-    const int k = ((((hi >> 20) & 0x7ff) - 1023) >> 1);
-    const double ws = __hiloint2double(hi - (k << 21), __double2loint(w));
-    double y = (double)rsqrtf((float)ws);
-    const double hws = 0.5 * ws;
-    y = y * (1.5 - hws * y * y);
-    y = y * (1.5 - hws * y * y);
-    return __hiloint2double(__double2hiint(y) - (k << 20), __double2loint(y));
+// max(x, 0) on the bit pattern: a negative double has its sign bit set, so masking with ~(hi >> 31) zeroes it (3 integer
+// instructions instead of the NaN-propagating fp64 max sequence)
+__device__ __forceinline__ double clamp0(double x) {
+    const int hi = __double2hiint(x);
+    const int m = ~(hi >> 31);
+    return __hiloint2double(hi & m, __double2loint(x) & m);
 }
 
 struct EvalOp {
@@ -104,18 +99,20 @@ struct EvalOp {
                                                  double n0, double n1, double& f0, double& f1, double& acc) {
         const double p0 = n0 * R0, p1 = n1 * R1;
         const double w = p0 * p1 * gi;
-        const double v = rsqrt_pos(w);
+        const double v = rsqrt(w);
         const double a = p0 * v, b = p1 * v;
-        const double d0 = 1.0 - fmin(fmax(1.0, b), b * gi);
-        const double d1 = 1.0 - fmin(fmax(1.0, a), a * gi);
-        f0 = R0 * d0 * (d0 < 0.0 ? gi : 1.0);
-        f1 = R1 * d1 * (d1 < 0.0 ? gi : 1.0);
-        acc += n0 * f0 + n1 * f1;
+        const double ob = 1.0 - b, oa = 1.0 - a;
+        const double r0 = fma(-b, gi, 1.0), r1 = fma(-a, gi, 1.0);          // 1 - b gi, 1 - a gi  (received share)
+        const double x0 = (ob < 0.0) ? ob * gi : clamp0(r0);
+        const double x1 = (oa < 0.0) ? oa * gi : clamp0(r1);
+        f0 = R0 * x0;
+        f1 = R1 * x1;
+        acc = fma(n0, f0, fma(n1, f1, acc));
         if (TRADES) {
-            A.delta[q] = fmax(-f0, 0.0); A.delta[A.M + q] = fmax(-f1, 0.0);
-            A.lambda[q] = fmax(f0, 0.0); A.lambda[A.M + q] = fmax(f1, 0.0);
+            A.delta[q] = f0 < 0.0 ? -f0 : 0.0; A.delta[A.M + q] = f1 < 0.0 ? -f1 : 0.0;
+            A.lambda[q] = f0 > 0.0 ? f0 : 0.0; A.lambda[A.M + q] = f1 > 0.0 ? f1 : 0.0;
         }
-        if (HESS) A.hcoef[q] = (d0 != 0.0 || d1 != 0.0) ? 0.5 * w * v : 0.0;
+        if (HESS) A.hcoef[q] = (x0 != 0.0 || x1 != 0.0) ? 0.5 * w * v : 0.0;
     }
 };
 
@@ -236,8 +233,10 @@ k_blocked(const BlockedArgs A) {
             const int len = row_len(rw);
             double s0 = 0.0, s1 = 0.0;
             int k = 0;
+#pragma unroll 1
             for (; k + 4 <= len; k += 4) { s0 += q[k] + q[k + 2]; s1 += q[k + 1] + q[k + 3]; }
-            for (; k < len; ++k) s0 += q[k];
+            if (k + 2 <= len) { s0 += q[k]; s1 += q[k + 1]; k += 2; }
+            if (k < len) s0 += q[k];
             const double s = s0 + s1;
             if (s != 0.0) atomicAdd(A.out + S.tok[row_tok(rw)], s);
         }
@@ -267,11 +266,205 @@ k_blocked(const BlockedArgs A) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Variant "regs" (configuration 3): the per-pool slabs (R0, R1, 1/gamma, ids, positions) are read exactly once, so they
+// go global -> registers directly (coalesced LDG, prefetched one tile ahead) instead of through shared memory.  Only
+// the small per-tile tables (row table, token list, descriptor) ride a 4-deep TMA ring.  That frees ~80 KB of shared
+// memory per CTA, which pays for double-buffered nu_local and flows, and those allow ONE barrier per tile: the row
+// phase of tile k overlaps the pool phase of tile k+1 in other warps, and nu_local of tile k+1 is fetched from L2
+// while tile k's pool phase computes.
+// ---------------------------------------------------------------------------------------------------------------
+template <int P>
+struct __align__(128) TabStage {
+    uint32_t rows[BlockedCfg<P>::kRowsMax];
+    int32_t tok[BlockedCfg<P>::kTokMax];
+    int4 desc;
+};
+
+template <int P>
+__device__ __forceinline__ void issue_tables(TabStage<P>* st, uint64_t* bar, const BlockedArgs& A, long long tile,
+                                             const int4 d) {
+    const unsigned rows_b = round16(4u * (unsigned)d.y);
+    const unsigned tok_b = round16(4u * (unsigned)d.x);
+    mbar_expect_tx(bar, 16u + rows_b + tok_b);
+    bulk_g2s(&st->desc, A.desc + tile, 16, bar);
+    bulk_g2s(st->rows, A.rows + tile * BlockedCfg<P>::kRowsMax, rows_b, bar);
+    bulk_g2s(st->tok, A.tok + tile * BlockedCfg<P>::kTokMax, tok_b, bar);
+}
+
+template <int NF>
+struct PoolRegs {
+    double a[NF];
+    uint32_t lid, pos;
+};
+
+template <int P, int THREADS, int NF, int NPOOL>
+__device__ __forceinline__ void load_pools(PoolRegs<NF> (&r)[NPOOL], const BlockedArgs& A, long long tile, int tid) {
+#pragma unroll
+    for (int u = 0; u < NPOOL; ++u) {
+        const long long q = tile * P + tid + u * THREADS;
+#pragma unroll
+        for (int k = 0; k < NF; ++k) r[u].a[k] = __ldg(A.slab[k] + q);
+        r[u].lid = __ldg(A.lid + q);
+        r[u].pos = __ldg(A.pos + q);
+    }
+}
+
+// pull the slabs of `tile` from HBM into L2 ahead of the register loads (one thread, 5 bulk prefetches)
+template <int P, int NF>
+__device__ __forceinline__ void prefetch_pools_l2(const BlockedArgs& A, long long tile) {
+#pragma unroll
+    for (int k = 0; k < NF; ++k) bulk_prefetch_l2(A.slab[k] + tile * P, P * 8);
+    bulk_prefetch_l2(A.lid + tile * P, P * 4);
+    bulk_prefetch_l2(A.pos + tile * P, P * 4);
+}
+
+template <int P, int THREADS, int STAGES, int MODE, bool TRADES, bool HESS>
+__global__ void __launch_bounds__(THREADS, 2)
+k_blocked_regs(const BlockedArgs A) {
+    constexpr int NF = (MODE == 0) ? 3 : 1;
+    constexpr int NPOOL = P / THREADS;
+    constexpr int NPRE = (P + THREADS - 1) / THREADS;
+    using St = TabStage<P>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    St* stages = reinterpret_cast<St*>(smem_raw);
+    double* nul0 = reinterpret_cast<double*>(smem_raw + (size_t)STAGES * sizeof(St));      // [2][P]  nu_local
+    double* g0 = nul0 + 2 * P;                                                              // [2][2P] flows, row order
+    __shared__ uint64_t full[STAGES];
+    __shared__ double part[THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long t_beg = (A.n_tiles * (long long)blockIdx.x) / gridDim.x;
+    const long long t_end = (A.n_tiles * (long long)(blockIdx.x + 1)) / gridDim.x;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            const long long t = t_beg + s;
+            if (t < t_end) issue_tables<P>(&stages[s], &full[s], A, t, __ldg(A.desc + t));
+        }
+        if (t_beg + 1 < t_end) prefetch_pools_l2<P, NF>(A, t_beg + 1);
+        if (t_beg + 2 < t_end) prefetch_pools_l2<P, NF>(A, t_beg + 2);
+    }
+    PoolRegs<NF> cur[NPOOL], nxt[NPOOL];
+    if (t_beg < t_end) load_pools<P, THREADS, NF, NPOOL>(cur, A, t_beg, tid);      // constant tables: before the PDL wait
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    for (int j = blockIdx.x * THREADS + tid; j < A.n_zero; j += gridDim.x * THREADS) A.zero_next[j] = 0.0;
+    double acc = 0.0;
+    if (t_beg < t_end) {
+        mbar_wait(&full[0], 0);
+        if (MODE != 2) {
+            const int ntok = stages[0].desc.x;
+            for (int t = tid; t < ntok; t += THREADS) nul0[t] = __ldg(A.vec + stages[0].tok[t]);
+        }
+    }
+    __syncthreads();
+    int stage = 0, pstage = 0, buf = 0;
+    unsigned parity = 0;
+    for (long long tile = t_beg; tile < t_end; ++tile) {
+        St& S = stages[stage];
+        const double* nul = nul0 + buf * P;
+        double* g = g0 + buf * 2 * P;
+        const long long nx = tile + 1;
+        int nstage = stage + 1;
+        unsigned nparity = parity;
+        if (nstage == STAGES) { nstage = 0; nparity ^= 1u; }
+        // 1. pool slabs of the next tile -> registers; nu_local of the next tile -> registers (both land while we compute)
+        double pre[NPRE];
+        int ntok_n = 0;
+        if (tid == 0 && tile + 3 < t_end) prefetch_pools_l2<P, NF>(A, tile + 3);      // HBM -> L2, 3 tiles ahead
+        if (nx < t_end) {
+            load_pools<P, THREADS, NF, NPOOL>(nxt, A, nx, tid);
+            mbar_wait(&full[nstage], nparity);
+            if (MODE != 2) {
+                ntok_n = stages[nstage].desc.x;
+#pragma unroll
+                for (int k = 0; k < NPRE; ++k) {
+                    const int t = tid + k * THREADS;
+                    pre[k] = (t < ntok_n) ? __ldg(A.vec + stages[nstage].tok[t]) : 0.0;
+                }
+            }
+        }
+        // 2. pool phase of this tile (registers + nu_local) -> flows in row order
+        {
+            double f0[NPOOL], f1[NPOOL];
+#pragma unroll
+            for (int u = 0; u < NPOOL; ++u) {
+                const uint32_t li = cur[u].lid;
+                if (MODE == 0) {
+                    EvalOp::apply<TRADES, HESS>(A, tile * P + tid + u * THREADS, cur[u].a[0], cur[u].a[NF > 1 ? 1 : 0],
+                                                cur[u].a[NF > 2 ? 2 : 0], nul[li & 0xffffu], nul[li >> 16], f0[u], f1[u],
+                                                acc);
+                } else if (MODE == 1) {
+                    f0[u] = cur[u].a[0] * (nul[li & 0xffffu] - nul[li >> 16]);
+                    f1[u] = -f0[u];
+                } else {
+                    f0[u] = cur[u].a[0];
+                    f1[u] = f0[u];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < NPOOL; ++u) {
+                g[cur[u].pos & 0xffffu] = f0[u];
+                g[cur[u].pos >> 16] = f1[u];
+            }
+        }
+        // 3. nu_local of the next tile into the other buffer (read last in the pool phase of tile-1: before barrier-1)
+        if (MODE != 2 && nx < t_end) {
+            double* nn = nul0 + (buf ^ 1) * P;
+#pragma unroll
+            for (int k = 0; k < NPRE; ++k) {
+                const int t = tid + k * THREADS;
+                if (t < ntok_n) nn[t] = pre[k];
+            }
+        }
+        __syncthreads();      // flows of this tile and nu_local of the next are complete; everybody left tile-1's rows
+        if (tid == 0 && tile > t_beg) {
+            const long long far = tile - 1 + STAGES;
+            if (far < t_end) {
+                fence_proxy_async();
+                issue_tables<P>(&stages[pstage], &full[pstage], A, far, __ldg(A.desc + far));
+            }
+        }
+        // 4. row phase: overlaps the next tile's steps 1-3 in the warps that get there first
+        const int nrow = S.desc.y;
+        for (int r = tid; r < nrow; r += THREADS) {
+            const uint32_t rw = S.rows[r];
+            const double* q = g + row_start(rw);
+            const int len = row_len(rw);
+            double s0 = 0.0, s1 = 0.0;
+            int k = 0;
+#pragma unroll 1
+            for (; k + 4 <= len; k += 4) { s0 += q[k] + q[k + 2]; s1 += q[k + 1] + q[k + 3]; }
+            if (k + 2 <= len) { s0 += q[k]; s1 += q[k + 1]; k += 2; }
+            if (k < len) s0 += q[k];
+            const double s = s0 + s1;
+            if (s != 0.0) atomicAdd(A.out + S.tok[row_tok(rw)], s);
+        }
+#pragma unroll
+        for (int u = 0; u < NPOOL; ++u) cur[u] = nxt[u];
+        pstage = stage; stage = nstage; parity = nparity; buf ^= 1;
+    }
+    if (MODE == 0) {
+        acc = warp_sum(acc);
+        if (lane == 0) part[warp] = acc;
+        __syncthreads();
+        if (tid < 32) {
+            double s = (tid < THREADS / 32) ? part[tid] : 0.0;
+            s = warp_sum(s);
+            if (tid == 0 && s != 0.0) atomicAdd(A.arb, s);
+        }
+    }
+}
+
 // ---- shipped configurations (selectable at run time for tuning; the layout must be built for the same P)
 struct Cfg0 { static constexpr int P = 1024, T = 512, S = 2, CTAS = 2; };   // 2 x (85 + 24) KB smem per SM
 struct Cfg1 { static constexpr int P = 512, T = 512, S = 3, CTAS = 2; };    // 2 x (64 + 12) KB, deeper ring
 struct Cfg2 { static constexpr int P = 512, T = 256, S = 2, CTAS = 4; };    // 4 x (43 + 12) KB
-int g_cfg = 0;
+int g_cfg = -1;
 int g_pdl = 1;
 int g_row_cap = 32;
 
@@ -302,15 +495,40 @@ int launch_cfg(const BlockedArgs& A, cudaStream_t st) {
 }
 
 template <int MODE, bool TRADES, bool HESS>
+int launch_regs(const BlockedArgs& A, cudaStream_t st) {
+    constexpr int P = 1024, T = 512, S = 4;
+    auto kern = k_blocked_regs<P, T, S, MODE, TRADES, HESS>;
+    const size_t sm = (size_t)S * sizeof(TabStage<P>) + (size_t)(2 * P + 4 * P) * sizeof(double);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        attr = true;
+    }
+    const long long cap = 2LL * num_sms();
+    const int grid = (int)(A.n_tiles < cap ? A.n_tiles : cap);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T); cfg.dynamicSmemBytes = sm; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = g_pdl;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, A);
+    return check_launch();
+}
+
+template <int MODE, bool TRADES, bool HESS>
 int launch_blocked(const BlockedArgs& A, cudaStream_t st) {
+    // default (-1): evaluation through the TMA-staged slabs, Hessian products / diagonal (1 slab, less data per tile)
+    // through the register-fed single-barrier variant -- each is the faster one for its mode (profiles/r1f_*)
+    if (g_cfg == 3 || (g_cfg < 0 && MODE != 0)) return launch_regs<MODE, TRADES, HESS>(A, st);
     switch (g_cfg) {
-        case 0: return launch_cfg<Cfg0, MODE, TRADES, HESS>(A, st);
         case 2: return launch_cfg<Cfg2, MODE, TRADES, HESS>(A, st);
-        default: return launch_cfg<Cfg1, MODE, TRADES, HESS>(A, st);
+        case 1: return launch_cfg<Cfg1, MODE, TRADES, HESS>(A, st);
+        default: return launch_cfg<Cfg0, MODE, TRADES, HESS>(A, st);
     }
 }
 
-int cfg_P() { return g_cfg == 0 ? Cfg0::P : Cfg1::P; }
+int cfg_P() { return (g_cfg <= 0 || g_cfg == 3) ? Cfg0::P : Cfg1::P; }
 
 int fill_args(const cfmm_blocked_pairs* b, BlockedArgs& A) {
     if (!b) return CFMM_E_NULL;
@@ -347,7 +565,7 @@ int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int3
 int cfmm_set_blocked_config(int32_t cfg) {
     if (cfg >= 300) { const int c = cfg - 300; if (c < 8 || c > 32) return CFMM_E_KIND; g_row_cap = c; return CFMM_OK; }
     if (cfg >= 200) { g_pdl = cfg - 200; return CFMM_OK; }      // 200 / 201: programmatic dependent launch off / on
-    if (cfg < 0 || cfg > 2) return CFMM_E_KIND;
+    if (cfg < -1 || cfg > 3) return CFMM_E_KIND;
     g_cfg = cfg;
     return CFMM_OK;
 }

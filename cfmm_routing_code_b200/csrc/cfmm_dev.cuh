@@ -62,4 +62,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// bulk prefetch of a contiguous global range into L2 (no registers, no shared memory): cp.async.bulk.prefetch.L2
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 }  // namespace cfmm

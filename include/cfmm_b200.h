@@ -114,8 +114,9 @@ typedef struct cfmm_blocked_pairs {
 
 int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int32_t* tok_stride, int32_t* row_cap,
                              int32_t* ent_stride);
-/* tuning: 0 = 1024-pool tiles / 2-stage ring, 1 = 512-pool tiles / 4-stage ring (default), 2 = 512 / 2-stage / 4 CTAs per SM.
- * Layouts must be (re)built after changing it. */
+/* tuning: -1 = default (evaluation: TMA-staged slabs, 1024-pool tiles; Hessian products: register-fed variant),
+ * 0 = TMA-staged for everything, 3 = register-fed for everything, 1 / 2 = 512-pool-tile experiments (layouts must be
+ * rebuilt after switching to or from those).  200/201 = PDL off/on, 300+c = row cap c for newly built layouts. */
 int cfmm_set_blocked_config(int32_t cfg);
 
 /* Same contract as cfmm_arb_eval for a blocked constant-product bucket: psi/arb ACCUMULATE (one red.add per row

@@ -16,7 +16,7 @@ ninst = 8
 stores = []
 LAYOUT = os.environ.get("LAYOUT", "blocked")
 from cfmm_routing_code_b200 import _lib as _L
-_L.load().cfmm_set_blocked_config(int(os.environ.get("BLOCKED_CFG", "0")))
+_L.load().cfmm_set_blocked_config(int(os.environ.get("BLOCKED_CFG", "-1")))
 _L.load().cfmm_set_blocked_config(200 + int(os.environ.get("PDL", "1")))
 _L.load().cfmm_set_blocked_config(300 + int(os.environ.get("ROWCAP", "32")))
 for k in range(ninst):
