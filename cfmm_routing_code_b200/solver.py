@@ -84,7 +84,7 @@ def default_nu0(spec: DualSpec) -> np.ndarray:
 
 def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 0.1, eps_min: float = 1e-4,
                eps_shrink: float = 0.25, max_outer: int = 60, max_inner: int = 100, linear_solver: str = "auto", cg_max: int = 200, comm: Optional[Comm] = None,
-               verbose: bool = False, final_trades: bool = True) -> SolveInfo:
+               verbose: bool = False, final_trades: bool = True, lookahead: int = 3) -> SolveInfo:
     t_start = time.perf_counter()
     comm = comm or Comm()
     n = ev.n_tokens
@@ -150,21 +150,45 @@ def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 0.1
                 break
             rhs = -pg
             # ---- Newton direction in log-price coordinates: Hs dt = -(nu*grad) on the free set
-            if linear_solver == "dense":
-                Hs = comm.allreduce(ev.hess_dense())
-                Hm = Hs * fr[:, None] * fr[None, :]
-                dg = torch.diagonal(Hm)
-                reg = 1e-14 * float(dg.sum()) / max(int(fr.sum()), 1)
-                Hm = Hm + torch.diag((1.0 - fr) + reg * fr)
-                L, info = torch.linalg.cholesky_ex(Hm)
-                if int(info) == 0:
-                    dt = torch.cholesky_solve(rhs[:, None], L)[:, 0]
-                else:
-                    dt = torch.linalg.lstsq(Hm, rhs[:, None]).solution[:, 0]
-                dt = dt * fr
-            else:
-                diag = comm.allreduce(ev.hess_diag())
-                dt = _pcg(ev, comm, rhs, fr, diag, eta=min(0.1, err ** 0.5), max_it=cg_max)
+            pgfull = nu * grad
+            Hs = comm.allreduce(ev.hess_dense()) if linear_solver == "dense" else None
+            diag = None if linear_solver == "dense" else comm.allreduce(ev.hess_diag())
+
+            def newton_dir(fr_, x0=None):
+                if linear_solver == "dense":
+                    Hm = Hs * fr_[:, None] * fr_[None, :]
+                    reg = 1e-14 * float(torch.diagonal(Hm).sum()) / max(int(fr_.sum()), 1)
+                    Hm = Hm + torch.diag((1.0 - fr_) + reg * fr_)
+                    L, info = torch.linalg.cholesky_ex(Hm)
+                    if int(info) == 0:
+                        d_ = torch.cholesky_solve((-pgfull * fr_)[:, None], L)[:, 0]
+                    else:
+                        d_ = torch.linalg.lstsq(Hm, (-pgfull * fr_)[:, None]).solution[:, 0]
+                    return d_ * fr_
+                return _pcg(ev, comm, -pgfull * fr_, fr_, diag, eta=min(0.1, err ** 0.5), max_it=cg_max, x0=x0)
+
+            dt = newton_dir(fr)
+            # ---- look-ahead on the active set: a token held at its bound (grad > 0) whose PREDICTED gradient after
+            # this step, nu*grad + Hs dt, is negative would be released at the next iteration anyway; release it now
+            # and re-solve (warm started).  Costs Hessian-vector products only, saves whole Newton iterations
+            # (the all-at-bound start of the arbitrage utility otherwise frees tokens layer by layer).
+            bound_act = (fr == 0) & ~fixed
+            for _la in range(lookahead if linear_solver == "dense" else 0):   # with CG the extra HVPs eat the gain
+                if not bool(bound_act.any()):
+                    break
+                Hd = (Hs @ dt) if linear_solver == "dense" else _reduce_hvp(ev, comm, dt)
+                newly = bound_act & ((pgfull + Hd) < 0)
+                if not bool(newly.any()):
+                    break
+                fr2 = fr + newly.to(fr.dtype)
+                dt2 = newton_dir(fr2, x0=dt)
+                bad = newly & (dt2 <= 0)                 # would be pushed below its bound after all: keep it active
+                if bool(bad.any()):
+                    fr2 = fr2 - bad.to(fr.dtype)
+                    dt2 = dt2 * fr2
+                fr, dt = fr2, dt2
+                bound_act = (fr == 0) & ~fixed
+            pg = pgfull * fr
             slope = torch.dot(pg, dt)     # = grad . (nu*dt)
             if not bool(torch.isfinite(slope)) or float(slope) >= 0.0:
                 dt = -pg / pg.abs().max().clamp(min=1e-300)
@@ -231,11 +255,20 @@ def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 0.1
                      status=status, wall_s=time.perf_counter() - t_start, history=history)
 
 
-def _pcg(ev, comm, rhs, fr, diag, eta, max_it):
+def _reduce_hvp(ev, comm, vt):
+    y = ev.hvp(vt)
+    return (y if getattr(ev, "reduces_internally", False) else comm.allreduce(y)).clone()
+
+
+def _pcg(ev, comm, rhs, fr, diag, eta, max_it, x0=None):
     """Truncated Jacobi-PCG for Hs x = rhs restricted to the free coordinates (fr = 0/1 mask)."""
     minv = fr / torch.clamp(diag, min=1e-300)
-    x = torch.zeros_like(rhs)
-    r = rhs * fr
+    if x0 is None:
+        x = torch.zeros_like(rhs)
+        r = rhs * fr
+    else:
+        x = x0 * fr
+        r = (rhs - _reduce_hvp(ev, comm, x)) * fr
     z = minv * r
     p = z.clone()
     rz = torch.dot(r, z)

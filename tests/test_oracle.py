@@ -149,3 +149,46 @@ def test_c_restatement_matches_numpy_oracle():
     np.testing.assert_allclose(d.ravel(), ev["delta"], atol=1e-13 * hp.reserves.max())
     np.testing.assert_allclose(l.ravel(), ev["lam"], atol=1e-13 * hp.reserves.max())
     assert CO.num_threads() >= 1
+
+
+# ---- property tests: random pools / prices, invariants of the per-pool solutions -------
+from hypothesis import given, settings, strategies as st
+
+
+@settings(max_examples=60, deadline=None)
+@given(k=st.integers(2, 6), seed=st.integers(0, 10_000), gam=st.sampled_from([0.9, 0.99, 0.997, 0.9995]),
+       spread=st.floats(0.0, 1.5))
+def test_property_geomean_solution_satisfies_kkt(k, seed, gam, spread):
+    """feasible on the trading-function boundary, never tenders and receives the same token, complementary
+    slackness of the price bounds gamma*M*w/nu <= x <= M*w/nu, degree-0 in nu, and no better than no trade <=> zero"""
+    rng = np.random.default_rng(seed)
+    R = np.exp(rng.normal(3, 1, k)); w = rng.dirichlet(np.ones(k)); nu = np.exp(spread * rng.standard_normal(k))
+    D, L, s = O.arb_geomean_scalar(R, w, gam, nu)
+    assert np.all(D >= 0) and np.all(L >= 0) and np.all(D * L == 0)
+    x = R + gam * D - L
+    assert np.all(x > 0)
+    assert abs(np.dot(w, np.log(x)) - np.dot(w, np.log(R))) <= 1e-11          # phi(x) == phi(R)  (arbitrage.py:65)
+    val = float(np.dot(nu, L - D))
+    assert val >= -1e-12 * np.dot(nu, R)                                         # at least as good as not trading
+    if D.any() or L.any():
+        M = np.exp(s)
+        lo, hi = gam * M * w / nu, M * w / nu
+        assert np.all(x >= lo * (1 - 1e-9)) and np.all(x <= hi * (1 + 1e-9))
+        np.testing.assert_allclose(x[D > 0], lo[D > 0], rtol=1e-9)
+        np.testing.assert_allclose(x[L > 0], hi[L > 0], rtol=1e-9)
+    D2, L2, _ = O.arb_geomean_scalar(R, w, gam, 3.7 * nu)
+    np.testing.assert_allclose(D2, D, rtol=1e-9, atol=1e-12 * R.max())
+    np.testing.assert_allclose(L2, L, rtol=1e-9, atol=1e-12 * R.max())
+
+
+@settings(max_examples=60, deadline=None)
+@given(seed=st.integers(0, 10_000), gam=st.sampled_from([0.99, 0.997, 0.999]), eps=st.sampled_from([0.0, 1e-3, 1e-1]),
+       frac=st.floats(0.0, 1.0))
+def test_property_const_sum_trades_respect_the_pool(seed, gam, eps, frac):
+    """any (smoothed or exact) constant-sum trade keeps sum(x) >= sum(R), x >= 0 (arbitrage.py:73-74) and D, L >= 0"""
+    rng = np.random.default_rng(seed)
+    R = np.exp(rng.normal(2, 1, 2)); nu = np.array([1.0, np.exp(0.01 * rng.standard_normal())])
+    D, L = O.arb_sum_scalar(R, gam, nu, eps=eps, theta_bar=frac * R)
+    x = R + gam * D - L
+    assert np.all(D >= -1e-15) and np.all(L >= -1e-15)
+    assert x.sum() >= R.sum() * (1 - 1e-13) and np.all(x >= -1e-12 * R.max())
