@@ -84,7 +84,7 @@ def default_nu0(spec: DualSpec) -> np.ndarray:
 
 def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 0.1, eps_min: float = 1e-4,
                eps_shrink: float = 0.25, max_outer: int = 60, max_inner: int = 100, linear_solver: str = "auto", cg_max: int = 200, comm: Optional[Comm] = None,
-               verbose: bool = False, final_trades: bool = True, lookahead: int = 3) -> SolveInfo:
+               verbose: bool = False, final_trades: bool = True, lookahead: Optional[int] = None) -> SolveInfo:
     t_start = time.perf_counter()
     comm = comm or Comm()
     n = ev.n_tokens
@@ -106,6 +106,10 @@ def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 0.1
         ev.reset_multipliers()
     if linear_solver == "auto":
         linear_solver = "dense" if (n <= 256 or (has_sum and n <= 4096)) else "cg"
+    if lookahead is None:
+        # every look-ahead round is one more factorisation: worth it where evaluations dominate (tiny n, or a CPU
+        # evaluator in the tests), not where a 1000 x 1000 Cholesky costs more than a pool pass (measured on cfg3)
+        lookahead = 3 if (n <= 64 or dev.type == "cpu") else 0
     evals0, hvps0 = ev.evals, ev.hvps
     history = []
     internal = bool(getattr(ev, "reduces_internally", False))     # PoolStore.enable_peer_allreduce(): no NCCL needed
