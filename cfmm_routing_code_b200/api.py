@@ -78,7 +78,7 @@ class Result:
     iters: int
     evals: int
     hvps: int
-    status: str                   # 'optimal' | 'max_iter' | 'line_search_failed'   (cf. prob.status)
+    status: str                   # 'optimal' | 'max_iter' | 'stalled'   (cf. prob.status)
     wall_s: float
     info: Optional[SolveInfo] = None
 

@@ -460,10 +460,8 @@ k_blocked_regs(const BlockedArgs A) {
     }
 }
 
-// ---- shipped configurations (selectable at run time for tuning; the layout must be built for the same P)
+// ---- configuration of the TMA-staged variant (the register-fed variant uses the same tile size)
 struct Cfg0 { static constexpr int P = 1024, T = 512, S = 2, CTAS = 2; };   // 2 x (85 + 24) KB smem per SM
-struct Cfg1 { static constexpr int P = 512, T = 512, S = 3, CTAS = 2; };    // 2 x (64 + 12) KB, deeper ring
-struct Cfg2 { static constexpr int P = 512, T = 256, S = 2, CTAS = 4; };    // 4 x (43 + 12) KB
 int g_cfg = -1;
 int g_pdl = 1;
 int g_row_cap = 32;
@@ -521,14 +519,10 @@ int launch_blocked(const BlockedArgs& A, cudaStream_t st) {
     // default (-1): evaluation through the TMA-staged slabs, Hessian products / diagonal (1 slab, less data per tile)
     // through the register-fed single-barrier variant -- each is the faster one for its mode (profiles/r1f_*)
     if (g_cfg == 3 || (g_cfg < 0 && MODE != 0)) return launch_regs<MODE, TRADES, HESS>(A, st);
-    switch (g_cfg) {
-        case 2: return launch_cfg<Cfg2, MODE, TRADES, HESS>(A, st);
-        case 1: return launch_cfg<Cfg1, MODE, TRADES, HESS>(A, st);
-        default: return launch_cfg<Cfg0, MODE, TRADES, HESS>(A, st);
-    }
+    return launch_cfg<Cfg0, MODE, TRADES, HESS>(A, st);
 }
 
-int cfg_P() { return (g_cfg <= 0 || g_cfg == 3) ? Cfg0::P : Cfg1::P; }
+int cfg_P() { return Cfg0::P; }
 
 int fill_args(const cfmm_blocked_pairs* b, BlockedArgs& A) {
     if (!b) return CFMM_E_NULL;
@@ -565,7 +559,7 @@ int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int3
 int cfmm_set_blocked_config(int32_t cfg) {
     if (cfg >= 300) { const int c = cfg - 300; if (c < 8 || c > 32) return CFMM_E_KIND; g_row_cap = c; return CFMM_OK; }
     if (cfg >= 200) { g_pdl = cfg - 200; return CFMM_OK; }      // 200 / 201: programmatic dependent launch off / on
-    if (cfg < -1 || cfg > 3) return CFMM_E_KIND;
+    if (cfg != -1 && cfg != 0 && cfg != 3) return CFMM_E_KIND;
     g_cfg = cfg;
     return CFMM_OK;
 }

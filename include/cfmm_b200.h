@@ -114,9 +114,9 @@ typedef struct cfmm_blocked_pairs {
 
 int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int32_t* tok_stride, int32_t* row_cap,
                              int32_t* ent_stride);
-/* tuning: -1 = default (evaluation: TMA-staged slabs, 1024-pool tiles; Hessian products: register-fed variant),
- * 0 = TMA-staged for everything, 3 = register-fed for everything, 1 / 2 = 512-pool-tile experiments (layouts must be
- * rebuilt after switching to or from those).  200/201 = PDL off/on, 300+c = row cap c for newly built layouts. */
+/* tuning: -1 = default (evaluation: TMA-staged slabs; Hessian products / diagonal: register-fed variant),
+ * 0 = TMA-staged for everything, 3 = register-fed for everything; 200/201 = programmatic dependent launch off/on;
+ * 300+c = row cap c (8..32) for layouts built afterwards. */
 int cfmm_set_blocked_config(int32_t cfg);
 
 /* Same contract as cfmm_arb_eval for a blocked constant-product bucket: psi/arb ACCUMULATE (one red.add per row
