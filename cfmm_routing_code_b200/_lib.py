@@ -103,6 +103,8 @@ def load(build_if_missing: bool = True):
     lib.cfmm_blocked_solve.restype = C.c_int
     lib.cfmm_allreduce_oneshot.argtypes = [vp, vp, i32, i32, i64, i32, vp, C.c_uint32, i32, vp]
     lib.cfmm_allreduce_oneshot.restype = C.c_int
+    lib.cfmm_allreduce_ll.argtypes = [vp, vp, i32, i32, i32, i64, i64, vp, C.c_uint64, vp]
+    lib.cfmm_allreduce_ll.restype = C.c_int
     lib.cfmm_sum_update_multipliers.argtypes = [C.POINTER(Bucket), vp, vp, vp, vp]
     lib.cfmm_sum_update_multipliers.restype = C.c_int
     lib.cfmm_zero.argtypes = [vp, i64, vp]

@@ -64,6 +64,53 @@ k_allreduce_oneshot(const double* const* __restrict__ bufs, uint32_t* const* __r
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Low-latency variant ("LL", the protocol NCCL uses for small messages): PUSH instead of pull.  Every rank writes its
+// element j straight into a receive area of every peer as ONE 16-byte store {value, seq}; 16-byte aligned vector
+// stores arrive atomically, so the flag travels with the data and no separate hand-shake or fence is needed.  The
+// receiver polls its own (local) memory until the flag equals seq, then adds the values in rank order.  One NVLink
+// one-way trip instead of the three of signal + remote load.  Receive areas rotate over 3 slots: a rank that has
+// received everybody's step-k data knows everybody finished reading step k-1.
+// ---------------------------------------------------------------------------------------------------------------
+struct __align__(16) LLCell { double val; unsigned long long flag; };
+
+__device__ __forceinline__ void st_ll(LLCell* p, double v, unsigned long long f) {
+    asm volatile("st.relaxed.sys.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(f) : "memory");
+}
+__device__ __forceinline__ void ld_ll(const LLCell* p, double& v, unsigned long long& f) {
+    long long bits;
+    asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(bits), "=l"(f) : "l"(p) : "memory");
+    v = __longlong_as_double(bits);
+}
+
+__global__ void __launch_bounds__(kArThreads)
+k_allreduce_ll(const double* __restrict__ local, LLCell* const* __restrict__ recv, int rank, int world, int n,
+               long long slot_off, long long src_stride, double* __restrict__ out, unsigned long long seq) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");            // `local` was produced by earlier kernels on this stream
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int j = blockIdx.x * kArThreads + threadIdx.x;
+    if (j >= n) return;
+    const double mine = local[j];
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; ++r)
+        if (r < world && r != rank) st_ll(recv[r] + slot_off + (long long)rank * src_stride + j, mine, seq);
+    double v[kMaxWorld];
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; ++r) {
+        if (r < world) {
+            if (r == rank) { v[r] = mine; continue; }
+            const LLCell* c = recv[rank] + slot_off + (long long)r * src_stride + j;
+            unsigned long long f;
+            do { ld_ll(c, v[r], f); } while (f != seq);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; ++r)
+        if (r < world) s += v[r];                                  // rank order: same bits on every rank
+    out[j] = s;
+}
+
 }  // namespace
 
 extern "C" {
@@ -85,6 +132,23 @@ int cfmm_allreduce_oneshot(const void* peer_bufs_dev, const void* peer_pads_dev,
     cudaLaunchKernelEx(&cfg, k_allreduce_oneshot, static_cast<const double* const*>(peer_bufs_dev),
                        static_cast<uint32_t* const*>(const_cast<void*>(peer_pads_dev)), (int)rank, (int)world,
                        (long long)offset_elems, (int)n, out, seq, (int)channel);
+    return check_launch();
+}
+
+int cfmm_allreduce_ll(const double* local, const void* peer_recv_dev, int32_t rank, int32_t world, int32_t n,
+                      int64_t slot_off_cells, int64_t src_stride_cells, double* out, uint64_t seq, void* stream) {
+    if (!local || !peer_recv_dev || !out) return CFMM_E_NULL;
+    if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || n <= 0 || seq == 0) return CFMM_E_SIZE;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((n + kArThreads - 1) / kArThreads); cfg.blockDim = dim3(kArThreads); cfg.dynamicSmemBytes = 0;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k_allreduce_ll, local, static_cast<LLCell* const*>(const_cast<void*>(peer_recv_dev)), (int)rank,
+                       (int)world, (int)n, (long long)slot_off_cells, (long long)src_stride_cells, out,
+                       (unsigned long long)seq);
     return check_launch();
 }
 

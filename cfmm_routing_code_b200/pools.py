@@ -484,12 +484,16 @@ class PoolStore:
         self.hvps = 0
 
     # -- multi-GPU: fused peer-memory all-reduce ---------------------------------------------------
-    def enable_peer_allreduce(self, group=None):
-        """Pool-sharded stores (world > 1): keep the partial [psi | arb] and y vectors in torch symmetric memory and
-        finish every evaluate()/hvp() with cfmm_allreduce_oneshot (NVLink peer reads, PDL-chained behind the pool
-        kernels) instead of returning a partial for NCCL.  Collective: every rank must call it."""
+    def enable_peer_allreduce(self, group=None, protocol: str = "ll"):
+        """Pool-sharded stores (world > 1): finish every evaluate()/hvp() with a fused NVLink all-reduce kernel
+        (PDL-chained behind the pool kernels) instead of returning a partial for NCCL.  protocol 'll': every rank
+        pushes {value, seq} cells into the peers' receive areas (cfmm_allreduce_ll, one NVLink one-way trip);
+        'pull': hand-shake + remote loads of the peers' partial vectors (cfmm_allreduce_oneshot).  The buffers live
+        in torch symmetric memory.  Collective: every rank must call it."""
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
+        if protocol not in ("ll", "pull"):
+            raise ValueError("protocol must be 'll' or 'pull'")
         group = group or dist.group.WORLD
         n = self.n_tokens
         if n + 1 > 64 * 256:
@@ -498,22 +502,33 @@ class PoolStore:
         if symm.get_signal_pad_size() < 65536:
             symm.set_signal_pad_size(65536)
         f64 = dict(dtype=torch.float64, device=self.device)
-        self._sym_acc = symm.empty((3, n + 1), **f64); self._sym_acc.zero_()
-        self._sym_y = symm.empty((3, n), **f64); self._sym_y.zero_()
+        self._peer_rank, self._peer_world = dist.get_rank(group), dist.get_world_size(group)
+        w = self._peer_world
+        self._peer_protocol = protocol
+        if protocol == "pull":
+            self._sym_acc = symm.empty((3, n + 1), **f64); self._sym_acc.zero_()
+            self._sym_y = symm.empty((3, n), **f64); self._sym_y.zero_()
+        else:                               # receive areas: [3 slots][world sources][n cells of {value, flag}]
+            self._sym_acc = symm.empty((3 * w * (n + 1) * 2,), **f64); self._sym_acc.zero_()
+            self._sym_y = symm.empty((3 * w * n * 2,), **f64); self._sym_y.zero_()
         self._hdl_acc = symm.rendezvous(self._sym_acc, group)
         self._hdl_y = symm.rendezvous(self._sym_y, group)
         self._red_acc = torch.zeros(n + 1, **f64)
         self._red_y = torch.zeros(n, **f64)
-        self._peer_rank, self._peer_world = dist.get_rank(group), dist.get_world_size(group)
         self._seq_acc = self._seq_y = 0
         torch.cuda.synchronize(self.device)
         dist.barrier(group)
         self.reduces_internally = True
 
-    def _peer_reduce(self, hdl, slot, n, out, seq, channel, st):
-        _lib.check(self.lib.cfmm_allreduce_oneshot(int(hdl.buffer_ptrs_dev), int(hdl.signal_pad_ptrs_dev),
-                                                   self._peer_rank, self._peer_world, slot * n, n, out.data_ptr(),
-                                                   seq, channel, st), "cfmm_allreduce_oneshot")
+    def _peer_reduce(self, hdl, local, slot, n, out, seq, channel, st):
+        if self._peer_protocol == "pull":
+            _lib.check(self.lib.cfmm_allreduce_oneshot(int(hdl.buffer_ptrs_dev), int(hdl.signal_pad_ptrs_dev),
+                                                       self._peer_rank, self._peer_world, slot * n, n, out.data_ptr(),
+                                                       seq, channel, st), "cfmm_allreduce_oneshot")
+        else:
+            w = self._peer_world
+            _lib.check(self.lib.cfmm_allreduce_ll(local.data_ptr(), int(hdl.buffer_ptrs_dev), self._peer_rank, w, n,
+                                                  slot * w * n, n, out.data_ptr(), seq, st), "cfmm_allreduce_ll")
 
     # -- helpers -------------------------------------------------------------------------------
     def _stream(self):
@@ -534,7 +549,8 @@ class PoolStore:
         """psi(nu) (n_tokens) and arb(nu) (1) for this rank's pools, as views into one (n+1) buffer."""
         st = self._stream()
         peer = getattr(self, "reduces_internally", False)
-        if peer:                            # 3-slot rotation in symmetric memory (see csrc/cfmm_allreduce.cu)
+        pull = peer and self._peer_protocol == "pull"
+        if pull:                            # 3-slot rotation in symmetric memory (see csrc/cfmm_allreduce.cu)
             k = self._seq_acc % 3
             acc, nxt = self._sym_acc[k], self._sym_acc[(k + 1) % 3]
         else:
@@ -561,14 +577,16 @@ class PoolStore:
         self.evals += 1
         if peer:
             self._seq_acc += 1
-            self._peer_reduce(self._hdl_acc, k, self.n_tokens + 1, self._red_acc, self._seq_acc, 0, st)
+            k = (self._seq_acc - 1) % 3 if pull else self._seq_acc % 3
+            self._peer_reduce(self._hdl_acc, acc, k, self.n_tokens + 1, self._red_acc, self._seq_acc, 0, st)
             return self._red_acc
         return acc
 
     def hvp(self, vt: torch.Tensor) -> torch.Tensor:
         st = self._stream()
         peer = getattr(self, "reduces_internally", False)
-        if peer:
+        pull = peer and self._peer_protocol == "pull"
+        if pull:
             k = self._seq_y % 3
             y, ynxt = self._sym_y[k], self._sym_y[(k + 1) % 3]
         else:
@@ -589,7 +607,8 @@ class PoolStore:
         self.hvps += 1
         if peer:
             self._seq_y += 1
-            self._peer_reduce(self._hdl_y, k, self.n_tokens, self._red_y, self._seq_y, 1, st)
+            k = (self._seq_y - 1) % 3 if pull else self._seq_y % 3
+            self._peer_reduce(self._hdl_y, y, k, self.n_tokens, self._red_y, self._seq_y, 1, st)
             return self._red_y
         return y
 

@@ -166,6 +166,16 @@ int cfmm_blocked_solve(const cfmm_blocked_pairs* b, int32_t n_tokens, const doub
 int cfmm_allreduce_oneshot(const void* peer_bufs_dev, const void* peer_pads_dev, int32_t rank, int32_t world,
                            int64_t offset_elems, int32_t n, double* out, uint32_t seq, int32_t channel, void* stream);
 
+/*
+ * Low-latency ("LL") variant of the same all-reduce: every rank PUSHES its n doubles into a receive area of every
+ * peer as 16-byte {value, seq} cells (flag travels with the data: one NVLink one-way trip, no hand-shake) and sums what
+ * it received, in rank order.  peer_recv_dev: device array of `world` pointers to every rank's receive area
+ * [3 slots][world sources][src_stride cells of 16 B]; slot_off_cells = (seq % 3) * world * src_stride.  seq >= 1,
+ * strictly increasing, equal on all ranks.  The receive areas must start zeroed.
+ */
+int cfmm_allreduce_ll(const double* local, const void* peer_recv_dev, int32_t rank, int32_t world, int32_t n,
+                      int64_t slot_off_cells, int64_t src_stride_cells, double* out, uint64_t seq, void* stream);
+
 /* SUM buckets: theta_bar <- current fills (= lambda), returns max_i |change|/R in move[0] (device). */
 int cfmm_sum_update_multipliers(const cfmm_bucket* bucket, const double* lambda, double* theta_bar_out,
                                 double* move, void* stream);

@@ -14,7 +14,7 @@ hp = cf.HostPools.from_pairs(n, s["idx"], s["reserves"], s["gamma"])
 nu = torch.as_tensor(s["prices"] * np.exp(0.01 * np.random.default_rng(0).standard_normal(n)), dtype=torch.float64, device=dev)
 st_nccl = cf.PoolStore(hp, device=dev, rank=rank, world=world, validate=False)
 st_peer = cf.PoolStore(hp, device=dev, rank=rank, world=world, validate=False)
-st_peer.enable_peer_allreduce()
+st_peer.enable_peer_allreduce(protocol=os.environ.get("PEER_PROTOCOL", "ll"))
 ok = True
 for it in range(7):                      # > 3 rounds: exercises the slot rotation
     nui = nu * (1 + 0.001 * it)
@@ -48,6 +48,6 @@ def timeit(fn, reps=200):
     return e0.elapsed_time(e1) / reps * 1e3
 t_n = timeit(lambda: dist.all_reduce(st_nccl.evaluate(nu)))
 t_p = timeit(lambda: st_peer.evaluate(nu))
-if rank == 0: print(f"eager step: nccl {t_n:.1f} us   peer one-shot {t_p:.1f} us   ALL OK={ok}", flush=True)
+if rank == 0: print(os.environ.get("PEER_PROTOCOL", "ll"), f"eager step: nccl {t_n:.1f} us   peer one-shot {t_p:.1f} us   ALL OK={ok}", flush=True)
 dist.barrier()
 os._exit(0 if ok else 1)
