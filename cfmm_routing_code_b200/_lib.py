@@ -51,6 +51,12 @@ class SolveResult(C.Structure):
                 ("hvps", C.c_int32), ("status", C.c_int32)]
 
 
+class PeerLL(C.Structure):
+    _fields_ = [("peer_recv_dev", C.c_void_p), ("done_counter", C.c_void_p), ("reduced", C.c_void_p),
+                ("slot_off_cells", C.c_int64), ("src_stride_cells", C.c_int64), ("seq", C.c_uint64),
+                ("rank", C.c_int32), ("world", C.c_int32)]
+
+
 class EvalOut(C.Structure):
     _fields_ = [("delta", C.c_void_p), ("lambda_", C.c_void_p), ("hcoef", C.c_void_p), ("hmask", C.c_void_p)]
 
@@ -94,6 +100,11 @@ def load(build_if_missing: bool = True):
     lib.cfmm_blocked_eval.restype = C.c_int
     lib.cfmm_blocked_hvp.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp, vp, vp]
     lib.cfmm_blocked_hvp.restype = C.c_int
+    lib.cfmm_blocked_eval_fused.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp, C.POINTER(EvalOut), vp, i64,
+                                            C.POINTER(PeerLL), vp]
+    lib.cfmm_blocked_eval_fused.restype = C.c_int
+    lib.cfmm_blocked_hvp_fused.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp, vp, C.POINTER(PeerLL), vp]
+    lib.cfmm_blocked_hvp_fused.restype = C.c_int
     lib.cfmm_blocked_diag.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp]
     lib.cfmm_blocked_diag.restype = C.c_int
     lib.cfmm_blocked_solve_work_bytes.argtypes = [C.POINTER(BlockedPairs), i32]

@@ -72,17 +72,6 @@ k_allreduce_oneshot(const double* const* __restrict__ bufs, uint32_t* const* __r
 // one-way trip instead of the three of signal + remote load.  Receive areas rotate over 3 slots: a rank that has
 // received everybody's step-k data knows everybody finished reading step k-1.
 // ---------------------------------------------------------------------------------------------------------------
-struct __align__(16) LLCell { double val; unsigned long long flag; };
-
-__device__ __forceinline__ void st_ll(LLCell* p, double v, unsigned long long f) {
-    asm volatile("st.relaxed.sys.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(f) : "memory");
-}
-__device__ __forceinline__ void ld_ll(const LLCell* p, double& v, unsigned long long& f) {
-    long long bits;
-    asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(bits), "=l"(f) : "l"(p) : "memory");
-    v = __longlong_as_double(bits);
-}
-
 __global__ void __launch_bounds__(kArThreads)
 k_allreduce_ll(const double* __restrict__ local, LLCell* const* __restrict__ recv, int rank, int world, int n,
                long long slot_off, long long src_stride, double* __restrict__ out, unsigned long long seq) {

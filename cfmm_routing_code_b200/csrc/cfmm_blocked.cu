@@ -42,6 +42,17 @@ struct __align__(128) Stage {
     int4 desc;                                    // (ntok, nrow, groups, 0) of the tile in this stage
 };
 
+// fused LL all-reduce (see csrc/cfmm_allreduce.cu for the protocol): the CTA that finishes last pushes the finished
+// vector to the peers' receive areas and sums what the peers pushed
+struct PeerLL {
+    LLCell* const* recv;          // device array [world] of receive areas, [3 slots][world sources][stride] cells
+    unsigned int* done_ctr;       // zero-initialised; counts finished CTAs of one launch
+    double* red;                  // [n] all-reduced result
+    long long slot_off, stride;   // in cells
+    unsigned long long seq;
+    int rank, world, n;
+};
+
 struct BlockedArgs {
     long long n_tiles;
     long long M;                  // n_tiles * P (padded pool count = slab stride)
@@ -59,6 +70,7 @@ struct BlockedArgs {
     double* delta;                // eval, optional: [2][M] blocked order
     double* lambda;
     double* hcoef;                // eval, optional: [M]
+    PeerLL peer;                  // optional fused all-reduce of `out` (world > 1): done by the last CTA to finish
 };
 
 __device__ __forceinline__ unsigned round16(unsigned bytes) { return (bytes + 15u) & ~15u; }
@@ -115,6 +127,46 @@ struct EvalOp {
         if (HESS) A.hcoef[q] = (x0 != 0.0 || x1 != 0.0) ? 0.5 * w * v : 0.0;
     }
 };
+
+// Called by every thread at the end of a blocked kernel.  The last CTA to arrive owns the finished `out` vector of this
+// rank (all red.adds of the launch are ordered before the counter bump by the fences) and runs the LL all-reduce.
+template <int THREADS>
+__device__ __forceinline__ void fused_allreduce_tail(const BlockedArgs& A) {
+    if (A.peer.world <= 1) return;
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned t = atomicAdd(A.peer.done_ctr, 1u);
+        s_last = (t == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    if (tid == 0) *A.peer.done_ctr = 0u;                  // next launch starts from zero (it cannot get here before we exit)
+    __threadfence();
+    const int rank = A.peer.rank, world = A.peer.world, n = A.peer.n;
+    for (int j = tid; j < n; j += THREADS) {
+        const double mine = __ldcg(A.out + j);
+        for (int r = 0; r < world; ++r)
+            if (r != rank) st_ll(A.peer.recv[r] + A.peer.slot_off + (long long)rank * A.peer.stride + j, mine, A.peer.seq);
+    }
+    for (int j = tid; j < n; j += THREADS) {
+        double s = 0.0;
+        for (int r = 0; r < world; ++r) {               // rank order: same bits on every rank
+            double v;
+            if (r == rank) {
+                v = __ldcg(A.out + j);
+            } else {
+                const LLCell* c = A.peer.recv[rank] + A.peer.slot_off + (long long)r * A.peer.stride + j;
+                unsigned long long f;
+                do { ld_ll(c, v, f); } while (f != A.peer.seq);
+            }
+            s += v;
+        }
+        A.peer.red[j] = s;
+    }
+}
 
 // row word: start (16 bits) | length (6 bits, 1..32) | local token (10 bits).  Rows of a tile are sorted by
 // decreasing length by the builder, so the 32 rows of a warp have (nearly) equal trip counts.
@@ -264,6 +316,7 @@ k_blocked(const BlockedArgs A) {
             if (tid == 0 && s != 0.0) atomicAdd(A.arb, s);
         }
     }
+    fused_allreduce_tail<THREADS>(A);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -458,6 +511,7 @@ k_blocked_regs(const BlockedArgs A) {
             if (tid == 0 && s != 0.0) atomicAdd(A.arb, s);
         }
     }
+    fused_allreduce_tail<THREADS>(A);
 }
 
 // ---- configuration of the TMA-staged variant (the register-fed variant uses the same tile size)
@@ -537,6 +591,7 @@ int fill_args(const cfmm_blocked_pairs* b, BlockedArgs& A) {
     A.zero_next = nullptr; A.n_zero = 0;
     A.slab[0] = A.slab[1] = A.slab[2] = nullptr;
     A.vec = nullptr; A.out = nullptr; A.arb = nullptr; A.delta = A.lambda = A.hcoef = nullptr;
+    A.peer = PeerLL{};
     return CFMM_OK;
 }
 
@@ -564,8 +619,25 @@ int cfmm_set_blocked_config(int32_t cfg) {
     return CFMM_OK;
 }
 
+static int fill_peer(const cfmm_peer_ll* p, int n, PeerLL& P) {
+    if (!p) return CFMM_OK;
+    if (!p->peer_recv_dev || !p->done_counter || !p->reduced) return CFMM_E_NULL;
+    if (p->world < 2 || p->world > 16 || p->rank < 0 || p->rank >= p->world || p->seq == 0) return CFMM_E_SIZE;
+    P.recv = static_cast<LLCell* const*>(const_cast<void*>(p->peer_recv_dev));
+    P.done_ctr = p->done_counter; P.red = p->reduced;
+    P.slot_off = p->slot_off_cells; P.stride = p->src_stride_cells; P.seq = p->seq;
+    P.rank = p->rank; P.world = p->world; P.n = n;
+    return CFMM_OK;
+}
+
 int cfmm_blocked_eval(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* nu, double* psi, double* arb,
                       const cfmm_eval_out* out, double* zero_next, int64_t n_zero, void* stream) {
+    return cfmm_blocked_eval_fused(b, n_tokens, nu, psi, arb, out, zero_next, n_zero, nullptr, stream);
+}
+
+int cfmm_blocked_eval_fused(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* nu, double* psi, double* arb,
+                            const cfmm_eval_out* out, double* zero_next, int64_t n_zero, const cfmm_peer_ll* peer,
+                            void* stream) {
     BlockedArgs A;
     int rc = fill_args(b, A);
     if (rc) return rc;
@@ -576,6 +648,9 @@ int cfmm_blocked_eval(const cfmm_blocked_pairs* b, int32_t n_tokens, const doubl
     A.slab[0] = b->r0; A.slab[1] = b->r1; A.slab[2] = b->gamma_inv;
     A.vec = nu; A.out = psi; A.arb = arb;
     A.zero_next = zero_next; A.n_zero = zero_next ? (int)n_zero : 0;
+    if (peer && arb != psi + n_tokens) return CFMM_E_STATE;      // the fused reduce covers [psi | arb] as one vector
+    rc = fill_peer(peer, n_tokens + 1, A.peer);
+    if (rc) return rc;
     const bool trades = out && out->delta && out->lambda;
     const bool hess = out && out->hcoef;
     if (trades) { A.delta = out->delta; A.lambda = out->lambda; }
@@ -589,6 +664,11 @@ int cfmm_blocked_eval(const cfmm_blocked_pairs* b, int32_t n_tokens, const doubl
 
 int cfmm_blocked_hvp(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* hcoef, const double* vt, double* y,
                      double* zero_next, void* stream) {
+    return cfmm_blocked_hvp_fused(b, n_tokens, hcoef, vt, y, zero_next, nullptr, stream);
+}
+
+int cfmm_blocked_hvp_fused(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* hcoef, const double* vt, double* y,
+                           double* zero_next, const cfmm_peer_ll* peer, void* stream) {
     BlockedArgs A;
     int rc = fill_args(b, A);
     if (rc) return rc;
@@ -597,6 +677,8 @@ int cfmm_blocked_hvp(const cfmm_blocked_pairs* b, int32_t n_tokens, const double
     if (b->n_tiles == 0) return CFMM_OK;
     A.slab[0] = hcoef; A.vec = vt; A.out = y;
     A.zero_next = zero_next; A.n_zero = zero_next ? n_tokens : 0;
+    rc = fill_peer(peer, n_tokens, A.peer);
+    if (rc) return rc;
     return launch_blocked<1, false, false>(A, static_cast<cudaStream_t>(stream));
 }
 

@@ -62,6 +62,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// LL protocol cell: 8 bytes of payload + 8 bytes of sequence flag, moved by ONE 16-byte store / load
+struct __align__(16) LLCell { double val; unsigned long long flag; };
+__device__ __forceinline__ void st_ll(LLCell* p, double v, unsigned long long f) {
+    asm volatile("st.relaxed.sys.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(f) : "memory");
+}
+__device__ __forceinline__ void ld_ll(const LLCell* p, double& v, unsigned long long& f) {
+    long long bits;
+    asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(bits), "=l"(f) : "l"(p) : "memory");
+    v = __longlong_as_double(bits);
+}
+
 // bulk prefetch of a contiguous global range into L2 (no registers, no shared memory): cp.async.bulk.prefetch.L2
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");

@@ -516,6 +516,9 @@ class PoolStore:
         self._red_acc = torch.zeros(n + 1, **f64)
         self._red_y = torch.zeros(n, **f64)
         self._seq_acc = self._seq_y = 0
+        # one blocked bucket and the LL protocol: the all-reduce runs INSIDE the pool kernel (last CTA), no extra launch
+        self._peer_fused = protocol == "ll" and len(self.buckets) == 1 and getattr(self.buckets[0], "blocked", False)
+        self._done_ctr = torch.zeros(2, dtype=torch.int32, device=self.device)
         torch.cuda.synchronize(self.device)
         dist.barrier(group)
         self.reduces_internally = True
@@ -562,6 +565,18 @@ class PoolStore:
         lognu = torch.log(nu) if self.has_geomean else None
         for b in self.buckets:
             out = b.out_struct(trades, hess) if (trades or hess) else None
+            if peer and self._peer_fused:
+                self._seq_acc += 1
+                w, n1 = self._peer_world, self.n_tokens + 1
+                pl = _lib.PeerLL(int(self._hdl_acc.buffer_ptrs_dev), self._done_ctr.data_ptr(), self._red_acc.data_ptr(),
+                                 (self._seq_acc % 3) * w * n1, n1, self._seq_acc, self._peer_rank, w)
+                rc = self.lib.cfmm_blocked_eval_fused(C.byref(b.c_blocked), self.n_tokens, nu.data_ptr(), acc.data_ptr(),
+                                                      acc.data_ptr() + 8 * self.n_tokens,
+                                                      C.byref(out) if out is not None else None,
+                                                      nxt.data_ptr(), nxt.numel(), C.byref(pl), st)
+                _lib.check(rc, "cfmm_blocked_eval_fused")
+                self.evals += 1
+                return self._red_acc
             if getattr(b, "blocked", False):
                 rc = self.lib.cfmm_blocked_eval(C.byref(b.c_blocked), self.n_tokens, nu.data_ptr(), acc.data_ptr(),
                                                 acc.data_ptr() + 8 * self.n_tokens,
@@ -596,6 +611,16 @@ class PoolStore:
         if not self._blocked_first:
             _lib.check(self.lib.cfmm_zero(y.data_ptr(), y.numel() * 8, st), "cfmm_zero")
         for b in self.buckets:
+            if peer and self._peer_fused:
+                self._seq_y += 1
+                w, n = self._peer_world, self.n_tokens
+                pl = _lib.PeerLL(int(self._hdl_y.buffer_ptrs_dev), self._done_ctr.data_ptr() + 4, self._red_y.data_ptr(),
+                                 (self._seq_y % 3) * w * n, n, self._seq_y, self._peer_rank, w)
+                _lib.check(self.lib.cfmm_blocked_hvp_fused(C.byref(b.c_blocked), n, b.hcoef.data_ptr(), vt.data_ptr(),
+                                                           y.data_ptr(), ynxt.data_ptr(), C.byref(pl), st),
+                           "cfmm_blocked_hvp_fused")
+                self.hvps += 1
+                return self._red_y
             if getattr(b, "blocked", False):
                 _lib.check(self.lib.cfmm_blocked_hvp(C.byref(b.c_blocked), self.n_tokens, b.hcoef.data_ptr(),
                                                      vt.data_ptr(), y.data_ptr(), ynxt.data_ptr(), st),

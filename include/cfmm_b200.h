@@ -131,6 +131,29 @@ int cfmm_blocked_hvp(const cfmm_blocked_pairs* b, int32_t n_tokens, const double
 int cfmm_blocked_diag(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* hcoef, double* diag, void* stream);
 
 /*
+ * Pool-sharded (multi-GPU) forms: ONE kernel evaluates this rank's pools AND all-reduces the result over NVLink peer
+ * memory (LL protocol, see cfmm_allreduce_ll): the CTA that finishes last pushes the finished vector into the peers'
+ * receive areas as 16-byte {value, seq} cells and sums what the peers pushed, in rank order, into peer->reduced
+ * ([psi | arb], n_tokens + 1 doubles, for eval -- arb must be psi + n_tokens; n_tokens doubles for hvp).  Because the
+ * collective is inside the launch, consecutive launches stay chained by programmatic dependent launch.
+ */
+typedef struct cfmm_peer_ll {
+    const void* peer_recv_dev;   /* device array of `world` pointers: every rank's receive area [3][world][stride] cells */
+    uint32_t* done_counter;      /* device, zero-initialised, private to this rank                                      */
+    double* reduced;             /* device, all-reduced output                                                          */
+    int64_t slot_off_cells;      /* (seq % 3) * world * src_stride_cells                                                */
+    int64_t src_stride_cells;
+    uint64_t seq;                /* >= 1, strictly increasing per call, equal on all ranks                              */
+    int32_t rank, world;
+} cfmm_peer_ll;
+
+int cfmm_blocked_eval_fused(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* nu, double* psi, double* arb,
+                            const cfmm_eval_out* out, double* zero_next, int64_t n_zero, const cfmm_peer_ll* peer,
+                            void* stream);
+int cfmm_blocked_hvp_fused(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* hcoef, const double* vt, double* y,
+                           double* zero_next, const cfmm_peer_ll* peer, void* stream);
+
+/*
  * Native outer loop (csrc/cfmm_solver.cu) for problems whose pools are ONE blocked constant-product bucket: the
  * whole of `prob.solve()` (arbitrage.py:81-82) in one call -- projected Newton-CG on the dual, all vectors on the
  * device, host loop in C++.  Utility in "linear + box" form: maximise c'psi s.t. psi_j + a_j >= 0 (eq[j]=0),

@@ -15,6 +15,7 @@ nu = torch.as_tensor(s["prices"] * np.exp(0.01 * np.random.default_rng(0).standa
 st_nccl = cf.PoolStore(hp, device=dev, rank=rank, world=world, validate=False)
 st_peer = cf.PoolStore(hp, device=dev, rank=rank, world=world, validate=False)
 st_peer.enable_peer_allreduce(protocol=os.environ.get("PEER_PROTOCOL", "ll"))
+print(rank, "fused:", getattr(st_peer, "_peer_fused", None), flush=True) if rank == 0 else None
 ok = True
 for it in range(7):                      # > 3 rounds: exercises the slot rotation
     nui = nu * (1 + 0.001 * it)
