@@ -365,7 +365,7 @@ def run_b200(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(workload_config(n_gpus, args.scaling),
-                           **({"collective_impl": ("LL all-reduce (16-byte {value, seq} pushes over NVLink peer memory) fused into the evaluation kernel" if peer
+                           **({"collective_impl": ("cfmm_allreduce_ll: 16-byte {value, seq} pushes over NVLink peer memory, PDL-chained between the evaluation kernels" if peer
                                                    else "NCCL all_reduce")} if world > 1 else {})),
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": e2e, "time_to_1e-6_gap": time_to_gap, "gpu_launches": launches, "clocks": clocks.summary(),

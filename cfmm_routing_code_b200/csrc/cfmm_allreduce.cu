@@ -40,8 +40,8 @@ k_allreduce_oneshot(const double* const* __restrict__ bufs, uint32_t* const* __r
                     long long offset, int n, double* __restrict__ out, uint32_t seq, int channel) {
     // the partial vector of this rank was produced by earlier kernels on this stream: wait for them (PDL), after
     // that every write of theirs (red.add resolved in this GPU's L2) is visible to peers reading over NVLink
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // the next kernel may start its ramp now
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int tid = threadIdx.x;
     const int slot0 = kPadBase + (channel * kArMaxCtas + blockIdx.x) * world;
     if (tid < world && tid != rank) {
@@ -75,8 +75,10 @@ k_allreduce_oneshot(const double* const* __restrict__ bufs, uint32_t* const* __r
 __global__ void __launch_bounds__(kArThreads)
 k_allreduce_ll(const double* __restrict__ local, LLCell* const* __restrict__ recv, int rank, int world, int n,
                long long slot_off, long long src_stride, double* __restrict__ out, unsigned long long seq) {
-    asm volatile("griddepcontrol.wait;" ::: "memory");            // `local` was produced by earlier kernels on this stream
+    // Let the NEXT kernel on the stream start its ramp right away (it only touches constant tables before its own
+    // griddepcontrol.wait), then wait for the kernels that produced `local`.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int j = blockIdx.x * kArThreads + threadIdx.x;
     if (j >= n) return;
     const double mine = local[j];

@@ -484,7 +484,7 @@ class PoolStore:
         self.hvps = 0
 
     # -- multi-GPU: fused peer-memory all-reduce ---------------------------------------------------
-    def enable_peer_allreduce(self, group=None, protocol: str = "ll"):
+    def enable_peer_allreduce(self, group=None, protocol: str = "ll", fused: bool = False):
         """Pool-sharded stores (world > 1): finish every evaluate()/hvp() with a fused NVLink all-reduce kernel
         (PDL-chained behind the pool kernels) instead of returning a partial for NCCL.  protocol 'll': every rank
         pushes {value, seq} cells into the peers' receive areas (cfmm_allreduce_ll, one NVLink one-way trip);
@@ -517,7 +517,8 @@ class PoolStore:
         self._red_y = torch.zeros(n, **f64)
         self._seq_acc = self._seq_y = 0
         # one blocked bucket and the LL protocol: the all-reduce runs INSIDE the pool kernel (last CTA), no extra launch
-        self._peer_fused = protocol == "ll" and len(self.buckets) == 1 and getattr(self.buckets[0], "blocked", False)
+        # (measured slower than the separate LL kernel: one CTA polls 9 cells per thread; kept selectable)
+        self._peer_fused = fused and protocol == "ll" and len(self.buckets) == 1 and getattr(self.buckets[0], "blocked", False)
         self._done_ctr = torch.zeros(2, dtype=torch.int32, device=self.device)
         torch.cuda.synchronize(self.device)
         dist.barrier(group)
