@@ -174,7 +174,7 @@ __device__ __forceinline__ int row_start(uint32_t r) { return (int)(r & 0xffffu)
 __device__ __forceinline__ int row_len(uint32_t r) { return (int)((r >> 16) & 0x3fu); }
 __device__ __forceinline__ int row_tok(uint32_t r) { return (int)(r >> 22); }
 
-template <int P, int THREADS, int STAGES, int MODE /*0 eval, 1 hvp, 2 diag*/, bool TRADES, bool HESS>
+template <int P, int THREADS, int STAGES, int MODE /*0 eval, 1 hvp, 2 diag*/, bool TRADES, bool HESS, bool AR = false>
 __global__ void __launch_bounds__(THREADS)
 k_blocked(const BlockedArgs A) {
     constexpr int NF = (MODE == 0) ? 3 : 1;
@@ -316,7 +316,7 @@ k_blocked(const BlockedArgs A) {
             if (tid == 0 && s != 0.0) atomicAdd(A.arb, s);
         }
     }
-    fused_allreduce_tail<THREADS>(A);
+    if (AR) fused_allreduce_tail<THREADS>(A);      // compiled only into the pool-sharded instantiations
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -372,7 +372,7 @@ __device__ __forceinline__ void prefetch_pools_l2(const BlockedArgs& A, long lon
     bulk_prefetch_l2(A.pos + tile * P, P * 4);
 }
 
-template <int P, int THREADS, int STAGES, int MODE, bool TRADES, bool HESS>
+template <int P, int THREADS, int STAGES, int MODE, bool TRADES, bool HESS, bool AR = false>
 __global__ void __launch_bounds__(THREADS, 2)
 k_blocked_regs(const BlockedArgs A) {
     constexpr int NF = (MODE == 0) ? 3 : 1;
@@ -511,7 +511,7 @@ k_blocked_regs(const BlockedArgs A) {
             if (tid == 0 && s != 0.0) atomicAdd(A.arb, s);
         }
     }
-    fused_allreduce_tail<THREADS>(A);
+    if (AR) fused_allreduce_tail<THREADS>(A);      // compiled only into the pool-sharded instantiations
 }
 
 // ---- configuration of the TMA-staged variant (the register-fed variant uses the same tile size)
@@ -523,12 +523,13 @@ int g_row_cap = 32;
 template <class C, int MODE, bool TRADES, bool HESS>
 int launch_cfg(const BlockedArgs& A, cudaStream_t st) {
     constexpr int NF = (MODE == 0) ? 3 : 1;
-    auto kern = k_blocked<C::P, C::T, C::S, MODE, TRADES, HESS>;
+    const bool ar = A.peer.world > 1;
+    auto kern = ar ? k_blocked<C::P, C::T, C::S, MODE, TRADES, HESS, true> : k_blocked<C::P, C::T, C::S, MODE, TRADES, HESS, false>;
     const size_t sm = (size_t)C::S * sizeof(Stage<C::P, NF>) + (size_t)(3 * C::P) * sizeof(double);
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[2] = {false, false};
+    if (!attr[ar]) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        attr = true;
+        attr[ar] = true;
     }
     const long long cap = (long long)C::CTAS * num_sms();
     const int grid = (int)(A.n_tiles < cap ? A.n_tiles : cap);
@@ -549,12 +550,13 @@ int launch_cfg(const BlockedArgs& A, cudaStream_t st) {
 template <int MODE, bool TRADES, bool HESS>
 int launch_regs(const BlockedArgs& A, cudaStream_t st) {
     constexpr int P = 1024, T = 512, S = 4;
-    auto kern = k_blocked_regs<P, T, S, MODE, TRADES, HESS>;
+    const bool ar = A.peer.world > 1;
+    auto kern = ar ? k_blocked_regs<P, T, S, MODE, TRADES, HESS, true> : k_blocked_regs<P, T, S, MODE, TRADES, HESS, false>;
     const size_t sm = (size_t)S * sizeof(TabStage<P>) + (size_t)(2 * P + 4 * P) * sizeof(double);
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[2] = {false, false};
+    if (!attr[ar]) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        attr = true;
+        attr[ar] = true;
     }
     const long long cap = 2LL * num_sms();
     const int grid = (int)(A.n_tiles < cap ? A.n_tiles : cap);
