@@ -57,6 +57,23 @@ class PeerLL(C.Structure):
                 ("rank", C.c_int32), ("world", C.c_int32)]
 
 
+class CsrPools(C.Structure):
+    _fields_ = [("n_tokens", C.c_int32), ("n_pools", C.c_int64), ("nnz", C.c_int64), ("pool_ptr", C.c_void_p),
+                ("tok_idx", C.c_void_p), ("reserves", C.c_void_p), ("weights", C.c_void_p), ("logrw", C.c_void_p),
+                ("gamma", C.c_void_p), ("kind", C.c_void_p)]
+
+
+class Batch(C.Structure):
+    _fields_ = [("n_problems", C.c_int32), ("pool_range", C.c_void_p), ("c", C.c_void_p), ("a", C.c_void_p),
+                ("flags", C.c_void_p), ("nu", C.c_void_p), ("psi", C.c_void_p), ("stats", C.c_void_p),
+                ("delta", C.c_void_p), ("lambda_", C.c_void_p), ("trade_stride", C.c_int64)]
+
+
+class BatchParams(C.Structure):
+    _fields_ = [("tol", C.c_double), ("eps0", C.c_double), ("eps_min", C.c_double), ("eps_shrink", C.c_double),
+                ("floor_rel", C.c_double), ("max_outer", C.c_int32), ("max_inner", C.c_int32)]
+
+
 class EvalOut(C.Structure):
     _fields_ = [("delta", C.c_void_p), ("lambda_", C.c_void_p), ("hcoef", C.c_void_p), ("hmask", C.c_void_p)]
 
@@ -112,6 +129,10 @@ def load(build_if_missing: bool = True):
     lib.cfmm_blocked_solve.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp, vp, vp, vp, vp,
                                        C.POINTER(SolveParams), C.POINTER(SolveResult), vp]
     lib.cfmm_blocked_solve.restype = C.c_int
+    lib.cfmm_batch_solve_work_bytes.argtypes = [C.POINTER(CsrPools), i32]
+    lib.cfmm_batch_solve_work_bytes.restype = i64
+    lib.cfmm_batch_solve.argtypes = [C.POINTER(CsrPools), C.POINTER(Batch), C.POINTER(BatchParams), vp, vp]
+    lib.cfmm_batch_solve.restype = C.c_int
     lib.cfmm_allreduce_oneshot.argtypes = [vp, vp, i32, i32, i64, i32, vp, C.c_uint32, i32, vp]
     lib.cfmm_allreduce_oneshot.restype = C.c_int
     lib.cfmm_allreduce_ll.argtypes = [vp, vp, i32, i32, i32, i64, i64, vp, C.c_uint64, vp]

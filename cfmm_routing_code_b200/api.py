@@ -170,13 +170,20 @@ def solve_pools(hp: HostPools, utility, nu0=None, tol: float = 1e-8, max_iter: i
 
 
 def solve_sweep(local_indices, reserves, fees, kinds, weights, utilities, n_tokens: Optional[int] = None,
-                tol: float = 1e-8, device="cuda", **solver_kw) -> List[Result]:
+                tol: float = 1e-8, device="cuda", batched: Optional[bool] = None, **solver_kw) -> List[Result]:
     """The loop of two-asset.py:40-100 as one call: the same pools under a sequence of utilities (there: Swap(0, 2, t)
-    for t in linspace(0, 50)).  The pool buckets are uploaded once and every solve is warm-started from the
-    previous prices, where the reference rebuilds the whole cvxpy problem per t (two-asset.py:47-91)."""
+    for t in linspace(0, 50)), where the reference rebuilds the whole cvxpy problem per t (two-asset.py:47-91).
+    batched (default whenever the pools fit: <= 64 tokens, arity <= 8): ALL utilities are solved by one kernel launch,
+    one problem per thread (`batch.solve_batch`).  Otherwise the pool buckets are uploaded once and the solves run in
+    turn, each warm-started from the previous prices."""
+    from . import batch as _batch
     if n_tokens is None:
         n_tokens = 1 + max(int(t) for l in local_indices for t in l)
     hp = HostPools.from_lists(n_tokens, local_indices, reserves, fees, kinds, weights)
+    if batched is None:
+        batched = _batch.batch_applicable(hp) and not solver_kw
+    if batched:
+        return _batch.solve_batch(hp, list(utilities), tol=tol, device=device)
     store = PoolStore(hp, device=device)
     out: List[Result] = []
     nu = None

@@ -179,6 +179,51 @@ int cfmm_blocked_solve(const cfmm_blocked_pairs* b, int32_t n_tokens, const doub
                        const cfmm_solve_params* prm, cfmm_solve_result* res, void* stream);
 
 /*
+ * Batches of SMALL problems (the reference's own sizes: 5 pools, 3-5 tokens), one problem per thread, the whole
+ * prob.solve() (arbitrage.py:81-82, liquidation.py:84-85, two-asset.py:90-91) of every problem in ONE launch.  Replaces
+ * the python loop of two-asset.py:40-100 that builds and solves 50 cvxpy problems in turn.  All problems index the same
+ * CSR pool arrays (the literals of arbitrage.py:5-28 flattened); problem p uses the pools [pool_range[2p],
+ * pool_range[2p+1]) or, with pool_range == NULL, all of them (a sweep over utilities).  Limits: n_tokens <= 64, weighted
+ * arity <= 8, constant-sum arity 2; a problem outside them gets status 3 and NaN results.
+ */
+typedef struct cfmm_csr_pools {
+    int32_t n_tokens;
+    int64_t n_pools, nnz;
+    const int64_t* pool_ptr;   /* [n_pools+1]                                                        */
+    const int32_t* tok_idx;    /* [nnz]  local_indices, arbitrage.py:6-12                             */
+    const double* reserves;    /* [nnz]  arbitrage.py:14-20                                          */
+    const double* weights;     /* [nnz]  normalised like cp.geo_mean(p=...), arbitrage.py:65; 0 on constant-sum pools */
+    const double* logrw;       /* [nnz]  log(reserves / weights) (unused on constant-sum pools)      */
+    const double* gamma;       /* [n_pools] fees, arbitrage.py:22-28                                 */
+    const uint8_t* kind;       /* [n_pools] CFMM_KIND_SUM, else (PRODUCT | GEOMEAN) weighted geometric mean */
+} cfmm_csr_pools;
+
+typedef struct cfmm_batch {
+    int32_t n_problems;
+    const int64_t* pool_range; /* nullable [n_problems][2]                                           */
+    const double* c;           /* [n_problems][n_tokens] objective on psi (arbitrage.py:31-36,57)    */
+    const double* a;           /* [n_problems][n_tokens] endowment (liquidation.py:30-36, two-asset.py:45) */
+    const uint8_t* flags;      /* [n_problems][n_tokens] bit0: psi_j + a_j == 0; bit1: psi_j free    */
+    double* nu;                /* [n_problems][n_tokens] in: start prices, out: optimal prices       */
+    double* psi;               /* [n_problems][n_tokens] out: psi.value (liquidation.py:87)          */
+    double* stats;             /* [n_problems][8] out: value (prob.value), dual, gap, infeasibility, kkt err, iters, evals, status */
+    double* delta;             /* nullable; out: problem p's Delta at delta[p * trade_stride + csr offset] */
+    double* lambda;            /* nullable together with delta                                       */
+    int64_t trade_stride;      /* nnz for a shared-pool sweep, 0 for disjoint pool ranges            */
+} cfmm_batch;
+
+typedef struct cfmm_batch_params {
+    double tol;                /* KKT residual and relative duality gap                              */
+    double eps0, eps_min, eps_shrink; /* constant-sum ramp continuation (0.1, 1e-4, 0.25)              */
+    double floor_rel;          /* lower bound of free prices relative to max |c| (1e-12)             */
+    int32_t max_outer, max_inner;
+} cfmm_batch_params;
+
+int64_t cfmm_batch_solve_work_bytes(const cfmm_csr_pools* pools, int32_t n_problems);
+int cfmm_batch_solve(const cfmm_csr_pools* pools, const cfmm_batch* batch, const cfmm_batch_params* prm, void* work,
+                     void* stream);
+
+/*
  * One-shot all-reduce (sum) of out[0..n) = sum_r peer_buf[r][offset .. offset+n) over NVLink peer memory: the ONE
  * collective of a pool-sharded dual evaluation, fused into the launch chain (PDL) right behind the
  * evaluation kernels.  peer_bufs_dev / peer_pads_dev: DEVICE arrays of `world` pointers to every rank's partial

@@ -394,6 +394,7 @@ def solve(pools: Pools, util: Utility, nu0=None, tol=1e-9, eps=0.1, eps_min=1e-4
 
     err = np.inf
     move = 1.0
+    failed_before = False
     for outer in range(max_outer):
         ev = G(nu, want_hess=True)
         inner_status = "max_iter"
@@ -427,8 +428,8 @@ def solve(pools: Pools, util: Utility, nu0=None, tol=1e-9, eps=0.1, eps_min=1e-4
                 if ev_t["g"] <= g0 + 1e-4 * lin:
                     ok = True
                     break
-                if abs(ev_t["g"] - g0) <= 1e-13 * abs(g0):       # below fp64 resolution of g
-                    if kkt(nu_t, ev_t, err)[0] < err:
+                if abs(ev_t["g"] - g0) <= 1e-13 * abs(g0) or abs(lin) <= 1e-9 * abs(g0):   # g cannot resolve this step
+                    if kkt(nu_t, ev_t, err)[0] < 0.99 * err:
                         ok = True
                         break
                     if alpha < 1e-3:
@@ -449,6 +450,9 @@ def solve(pools: Pools, util: Utility, nu0=None, tol=1e-9, eps=0.1, eps_min=1e-4
             print(f"outer={outer} eps={eps_t:.1e} last move={move:.3e} gap={gap_now:.3e}")
         if inner_status == "optimal" and err <= tol and abs(gap_now) <= tol:
             break
+        if inner_status != "optimal" and failed_before and eps_t <= eps_min:
+            break       # ramp at its narrowest and two failed passes: the residual sits at the fp64 floor (ratio / eps)
+        failed_before = inner_status != "optimal"
         move = 0.0
         for g in sum_groups:
             th = fin["lam"][g["off"]]                     # Lambda_b IS the fill of the order paying b

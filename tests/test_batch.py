@@ -1,0 +1,170 @@
+"""Batched small-problem solver (csrc/cfmm_small.cuh / cfmm_small.cu): one whole prob.solve() per GPU thread.
+
+CPU part: the per-thread solver, compiled for the host by tests/small_host.py, against oracle/cfmm_oracle.py::solve --
+same algorithm, so iterates agree to rounding and the evaluation counts are equal.  GPU part: the kernel through the
+C ABI against the oracle and the golden vectors."""
+import numpy as np
+import pytest
+
+import cfmm_routing_code_b200 as cf
+from cfmm_routing_code_b200 import instances as I
+from oracle import cfmm_oracle as O
+import helpers as H
+import small_host
+
+
+def _reference_cases():
+    d = I.arbitrage_instance(); hp = H.host_pools(d)
+    yield "arbitrage", hp, [O.Utility.arbitrage(d["market_value"])]
+    d = I.liquidation_instance(); hp = H.host_pools(d)
+    yield "liquidation", hp, [O.Utility.liquidate(hp.n_tokens, d["target"], d["current_assets"])]
+    d = I.two_asset_instance(); hp = H.host_pools(d)
+    yield "two_asset", hp, [O.Utility.swap(hp.n_tokens, d["tok_in"], d["tok_out"], t) for t in d["amounts"]]
+
+
+def _small_mixed(seed, m=24, n=9):
+    s = I.synth_mixed(m, n, seed)
+    hp = cf.HostPools(n, s["pool_ptr"], s["tok_idx"], s["reserves"], s["weights"], s["gamma"], s["kind"])
+    return hp, s
+
+
+def _check_against_oracle(hp, specs, out, tol=1e-9, rtol=1e-9):
+    op = H.oracle_pools(hp)
+    for p, u in enumerate(specs):
+        r = O.solve(op, u, tol=tol)
+        st = out["stats"][p]
+        assert int(st[7]) == {"optimal": 0, "max_iter": 1, "stalled": 2}[r.status], p
+        scale = max(abs(r.dual_value), 1e-300)
+        assert abs(st[0] - r.value) <= rtol * scale, (p, st[0], r.value)
+        assert abs(st[1] - r.dual_value) <= rtol * scale
+        np.testing.assert_allclose(out["nu"][p], r.nu, rtol=1e-7)
+        gross = np.abs(np.concatenate(r.deltas)).sum() + np.abs(np.concatenate(r.lambdas)).sum()
+        np.testing.assert_allclose(out["psi"][p], r.psi, atol=1e-7 * max(gross, 1e-300))
+        if out.get("delta") is not None and out["delta"].shape[0] == len(specs):
+            np.testing.assert_allclose(out["delta"][p], np.concatenate(r.deltas), atol=1e-6 * max(gross, 1e-300))
+            np.testing.assert_allclose(out["lam"][p], np.concatenate(r.lambdas), atol=1e-6 * max(gross, 1e-300))
+
+
+# ------------------------------------------------------------------------------------------------- CPU (host build)
+@pytest.mark.parametrize("interleave", [0, 1])
+def test_host_build_reference_instances_match_oracle_step_for_step(interleave, golden):
+    for name, hp, specs in _reference_cases():
+        out = small_host.solve(hp, specs, tol=1e-9, interleave=interleave)
+        _check_against_oracle(hp, specs, out)
+        op = H.oracle_pools(hp)
+        for p in (0, len(specs) - 1):           # same control flow => same number of evaluations and iterations
+            r = O.solve(op, specs[p], tol=1e-9)
+            assert (int(out["stats"][p][5]), int(out["stats"][p][6])) == (r.iters, r.evals), name
+    assert abs(out["stats"][0][0] - golden["survey_8c"]["two_asset_t0"]) <= 1e-8 * 6.3
+    assert abs(out["stats"][49][0] - golden["survey_8c"]["two_asset_t50"]) <= 1e-8 * 44.2
+
+
+def test_host_build_two_asset_sweep_matches_golden(golden):
+    _, hp, specs = list(_reference_cases())[2]
+    out = small_host.solve(hp, specs, tol=1e-9)
+    for j in range(50):
+        g = golden["two_asset"][j]
+        assert abs(out["stats"][j][0] - g["value"]) <= 1e-6 * max(1.0, g["value"]), j
+        np.testing.assert_allclose(out["psi"][j], g["psi"], atol=2e-5)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_host_build_mixed_problems_match_oracle(seed):
+    hp, s = _small_mixed(seed)
+    rng = np.random.default_rng(seed)
+    specs = [O.Utility.arbitrage(s["prices"] * np.exp(0.05 * rng.standard_normal(hp.n_tokens))) for _ in range(3)]
+    basket = np.zeros(hp.n_tokens); basket[1:4] = rng.uniform(0.1, 1.0, 3) * 1e-2 / s["prices"][1:4] * 3000.0
+    specs.append(O.Utility.liquidate(hp.n_tokens, 0, basket))
+    specs.append(O.Utility.swap(hp.n_tokens, 2, 5, 10.0 / s["prices"][2]))
+    out = small_host.solve(hp, specs, tol=1e-9)
+    _check_against_oracle(hp, specs, out, rtol=1e-8)
+
+
+def test_host_build_disjoint_pool_ranges_and_rejected_input():
+    """problems over different pool subsets of one CSR array; a pool the closed forms do not cover is refused"""
+    hp, s = _small_mixed(5, m=30, n=8)
+    ranges = np.array([[0, 10], [10, 30], [0, 30]], np.int64)
+    u = O.Utility.arbitrage(s["prices"])
+    out = small_host.solve(hp, [u, u, u], tol=1e-9, pool_range=ranges)
+    for p, (lo, hi) in enumerate(ranges):
+        sub = cf.HostPools(hp.n_tokens, hp.pool_ptr[lo:hi + 1] - hp.pool_ptr[lo],
+                           hp.tok_idx[hp.pool_ptr[lo]:hp.pool_ptr[hi]], hp.reserves[hp.pool_ptr[lo]:hp.pool_ptr[hi]],
+                           hp.weights[hp.pool_ptr[lo]:hp.pool_ptr[hi]], hp.gamma[lo:hi], hp.kind[lo:hi])
+        r = O.solve(H.oracle_pools(sub), u, tol=1e-9)
+        assert abs(out["stats"][p][0] - r.value) <= 1e-8 * max(abs(r.dual_value), 1e-300)
+    d = I.arbitrage_instance(); bad = H.host_pools(d)
+    bad.tok_idx = bad.tok_idx.copy(); bad.tok_idx[1] = 7          # token index outside n_tokens
+    out = small_host.solve(bad, [O.Utility.arbitrage(d["market_value"])])
+    assert int(out["stats"][0][7]) == 3 and np.isnan(out["stats"][0][0])
+
+
+# ------------------------------------------------------------------------------------------------- GPU (the product)
+def _to_api(u):
+    class _U:
+        def spec(self, n):
+            return cf.DualSpec(u.c, u.a, u.eq, u.pinned)
+    return _U()
+
+
+@pytest.mark.gpu
+def test_batch_kernel_reference_instances_match_oracle_and_golden(golden):
+    for name, hp, specs in _reference_cases():
+        rs = cf.solve_batch(hp, [_to_api(u) for u in specs], tol=1e-9)
+        out = dict(stats=np.array([[r.value, r.dual_value, r.gap, r.primal_infeas, 0, r.iters, r.evals,
+                                    {"optimal": 0, "max_iter": 1, "stalled": 2}[r.status]] for r in rs]),
+                   nu=np.stack([r.nu for r in rs]), psi=np.stack([r.psi for r in rs]),
+                   delta=np.stack([np.concatenate(r.deltas) for r in rs]),
+                   lam=np.stack([np.concatenate(r.lambdas) for r in rs]))
+        _check_against_oracle(hp, specs, out)
+        if name == "two_asset":
+            for j, r in enumerate(rs):
+                g = golden["two_asset"][j]
+                assert r.status == "optimal" and abs(r.value - g["value"]) <= 1e-6 * max(1.0, g["value"]), j
+        else:
+            assert abs(rs[0].value - golden["survey_8c"][name]) <= 1e-8 * abs(rs[0].value)
+
+
+@pytest.mark.gpu
+def test_batch_kernel_agrees_with_its_host_build_bit_for_bit_in_control_flow():
+    """4096 random swap quotes over one mixed pool set: same iteration / evaluation counts as the host build of the same
+    source, values to rounding (fp contraction differs)."""
+    hp, s = _small_mixed(7, m=40, n=12)
+    rng = np.random.default_rng(7)
+    B = 4096
+    specs = []
+    for _ in range(B):
+        i, o = rng.choice(hp.n_tokens, 2, replace=False)
+        specs.append(O.Utility.swap(hp.n_tokens, int(i), int(o), float(rng.uniform(0.0, 50.0) / s["prices"][i])))
+    rs = cf.solve_batch(hp, [_to_api(u) for u in specs], tol=1e-9, want_trades=False)
+    ref = small_host.solve(hp, specs, tol=1e-9)
+    val = np.array([r.value for r in rs]); dual = np.array([r.dual_value for r in rs])
+    np.testing.assert_allclose(val, ref["stats"][:, 0], rtol=1e-8, atol=1e-9 * np.abs(dual).max())
+    status = np.array([{"optimal": 0, "max_iter": 1, "stalled": 2}[r.status] for r in rs])
+    assert np.array_equal(status, ref["stats"][:, 7].astype(int))
+    same_flow = np.mean(np.array([r.evals for r in rs]) == ref["stats"][:, 6])
+    assert same_flow >= 0.98, same_flow          # rounding can flip a line-search branch on a few problems
+    assert np.all(np.array([r.gap for r in rs])[status == 0] <= 1e-8)
+
+
+@pytest.mark.gpu
+def test_batched_and_sequential_sweeps_agree():
+    d = I.two_asset_instance()
+    us = [cf.Swap(d["tok_in"], d["tok_out"], t) for t in d["amounts"][::7]]
+    args = (d["local_indices"], d["reserves"], d["fees"], d["kinds"], d["weights"], us)
+    a = cf.solve_sweep(*args, tol=1e-9, batched=True)
+    b = cf.solve_sweep(*args, tol=1e-9, batched=False)
+    for x, y in zip(a, b):
+        assert abs(x.value - y.value) <= 1e-7 * max(1.0, abs(y.value))
+        np.testing.assert_allclose(x.psi, y.psi, atol=2e-5)
+
+
+@pytest.mark.gpu
+def test_batch_kernel_rejects_what_it_does_not_cover():
+    d = I.arbitrage_instance(); hp = H.host_pools(d)
+    store = cf.CsrStore(hp)
+    store.tok[1] = 7                                            # corrupt a token index on the device
+    rs = cf.solve_batch(hp, [cf.Arbitrage(d["market_value"])], store=store)
+    assert rs[0].status == "rejected" and np.isnan(rs[0].value)
+    big = cf.HostPools.from_pairs(100, np.array([[0, 99]]), np.array([[1.0, 2.0]]), np.array([0.997]))
+    with pytest.raises(ValueError):
+        cf.CsrStore(big)

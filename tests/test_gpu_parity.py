@@ -161,11 +161,13 @@ def test_reference_instances_end_to_end(golden):
         assert abs(r.value - golden["two_asset"][j]["value"]) <= 1e-6 * max(1.0, golden["two_asset"][j]["value"]), j
 
 
-def test_two_asset_sweep_all_50_points_match_golden(golden):
-    """two-asset.py:40-100: u(t) and the per-pool flows (lambdas - deltas, :93-94) for every t in linspace(0, 50)"""
+@pytest.mark.parametrize("batched", [True, False])
+def test_two_asset_sweep_all_50_points_match_golden(golden, batched):
+    """two-asset.py:40-100: u(t) and the per-pool flows (lambdas - deltas, :93-94) for every t in linspace(0, 50);
+    batched = all 50 solves in one kernel launch, else one warm-started solve after the other"""
     d = I.two_asset_instance()
     rs = cf.solve_sweep(d["local_indices"], d["reserves"], d["fees"], d["kinds"], d["weights"],
-                        [cf.Swap(d["tok_in"], d["tok_out"], t) for t in d["amounts"]], tol=1e-9)
+                        [cf.Swap(d["tok_in"], d["tok_out"], t) for t in d["amounts"]], tol=1e-9, batched=batched)
     assert len(rs) == 50
     for j, r in enumerate(rs):
         g = golden["two_asset"][j]
