@@ -107,7 +107,7 @@ def pack_utilities(utilities: Sequence, n: int, nu0=None):
 
 
 def solve_batch(hp: HostPools, utilities: Sequence, nu0=None, tol: float = 1e-8, device="cuda",
-                want_trades: bool = True, store: Optional[CsrStore] = None):
+                want_trades: bool = True, store: Optional[CsrStore] = None, max_inner: int = 100):
     """All problems (same pools, one utility each) in one launch.  Returns a list of api.Result."""
     from .api import Result
     t0 = time.perf_counter()
@@ -116,7 +116,8 @@ def solve_batch(hp: HostPools, utilities: Sequence, nu0=None, tol: float = 1e-8,
     c, a, fl, nu = pack_utilities(utilities, n, nu0)
     up = lambda x: torch.as_tensor(x, device=dev)
     nu_d = up(nu)
-    psi, stats, delta, lam = solve_batch_device(store, up(c), up(a), up(fl), nu_d, tol=tol, want_trades=want_trades)
+    psi, stats, delta, lam = solve_batch_device(store, up(c), up(a), up(fl), nu_d, tol=tol, want_trades=want_trades,
+                                                max_inner=max_inner)
     stats_h = stats.cpu().numpy()              # the one synchronisation of the call
     psi_h, nu_h = psi.cpu().numpy(), nu_d.cpu().numpy()
     if want_trades:

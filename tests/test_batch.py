@@ -59,6 +59,24 @@ def test_host_build_reference_instances_match_oracle_step_for_step(interleave, g
     assert abs(out["stats"][49][0] - golden["survey_8c"]["two_asset_t50"]) <= 1e-8 * 44.2
 
 
+def test_host_build_matches_golden_with_the_end_to_end_tolerances(golden):
+    """the assertions of test_gpu_parity.py::test_reference_instances_end_to_end, on the host build"""
+    cases = {name: (hp, specs) for name, hp, specs in _reference_cases()}
+    for name in ("arbitrage", "liquidation"):
+        hp, specs = cases[name]
+        out = small_host.solve(hp, specs, tol=1e-9)
+        g = golden[name]
+        assert int(out["stats"][0][7]) == 0
+        val = out["stats"][0][0]
+        assert abs(val - g["value"]) <= 1e-6 * abs(g["value"])
+        assert abs(val - golden["survey_8c"][name]) <= 1e-8 * abs(val)
+        np.testing.assert_allclose(out["psi"][0], g["psi"], atol=1e-6 * abs(val))
+        ptr = hp.pool_ptr
+        for i in range(hp.m):
+            np.testing.assert_allclose(out["delta"][0][ptr[i]:ptr[i + 1]], g["deltas"][i], atol=5e-5)
+            np.testing.assert_allclose(out["lam"][0][ptr[i]:ptr[i + 1]], g["lambdas"][i], atol=5e-5)
+
+
 def test_host_build_two_asset_sweep_matches_golden(golden):
     _, hp, specs = list(_reference_cases())[2]
     out = small_host.solve(hp, specs, tol=1e-9)

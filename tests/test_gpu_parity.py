@@ -135,10 +135,13 @@ def test_hessian_products_match_oracle():
     np.testing.assert_allclose(st.hvp(torch.as_tensor(v, **F64)).cpu().numpy(), Hs @ v, atol=1e-10 * scale)
 
 
-def test_reference_instances_end_to_end(golden):
+@pytest.mark.parametrize("method", ["pools", "thread", "auto"])
+def test_reference_instances_end_to_end(golden, method):
+    """the three scripts' instances through the pool-parallel kernels under the outer loop ('pools') and through the
+    one-thread-per-problem solver ('thread', what 'auto' picks at this size)"""
     d = I.arbitrage_instance()
     r = cf.solve(d["local_indices"], d["reserves"], d["fees"], d["kinds"], d["weights"],
-                 utility=cf.Arbitrage(d["market_value"]), tol=1e-9)
+                 utility=cf.Arbitrage(d["market_value"]), tol=1e-9, method=method)
     g = golden["arbitrage"]
     assert r.status == "optimal"
     assert abs(r.value - g["value"]) <= 1e-6 * abs(g["value"])          # BASELINE.md pass criterion
@@ -149,7 +152,7 @@ def test_reference_instances_end_to_end(golden):
         np.testing.assert_allclose(r.lambdas[i], g["lambdas"][i], atol=5e-5)
     d = I.liquidation_instance()
     r = cf.solve(d["local_indices"], d["reserves"], d["fees"], d["kinds"], d["weights"],
-                 utility=cf.Liquidate(d["target"], d["current_assets"]), tol=1e-9)
+                 utility=cf.Liquidate(d["target"], d["current_assets"]), tol=1e-9, method=method)
     g = golden["liquidation"]
     assert r.status == "optimal"
     assert abs(r.psi[4] - g["value"]) <= 1e-6 * g["value"]
@@ -157,7 +160,7 @@ def test_reference_instances_end_to_end(golden):
     d = I.two_asset_instance()
     for j in (0, 7, 15, 23, 31, 49):
         r = cf.solve(d["local_indices"], d["reserves"], d["fees"], d["kinds"], d["weights"],
-                     utility=cf.Swap(0, 2, d["amounts"][j]), tol=1e-9)
+                     utility=cf.Swap(0, 2, d["amounts"][j]), tol=1e-9, method=method)
         assert abs(r.value - golden["two_asset"][j]["value"]) <= 1e-6 * max(1.0, golden["two_asset"][j]["value"]), j
 
 
