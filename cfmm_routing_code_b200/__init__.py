@@ -7,7 +7,7 @@ include/cfmm_b200.h).  There is no CPU path.
 """
 from .api import Arbitrage, Liquidate, Swap, Result, solve, solve_pools, solve_sweep   # noqa: F401
 from .pools import HostPools, PoolStore                                    # noqa: F401
-from .batch import CsrStore, solve_batch, solve_batch_device               # noqa: F401
+from .batch import CsrStore, solve_batch, solve_batch_device, solve_many               # noqa: F401
 from .solver import DualSpec, solve_dual                                   # noqa: F401
 from ._lib import CfmmError                                                # noqa: F401
 

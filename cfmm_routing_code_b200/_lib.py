@@ -129,7 +129,7 @@ def load(build_if_missing: bool = True):
     lib.cfmm_blocked_solve.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp, vp, vp, vp, vp,
                                        C.POINTER(SolveParams), C.POINTER(SolveResult), vp]
     lib.cfmm_blocked_solve.restype = C.c_int
-    lib.cfmm_batch_solve_work_bytes.argtypes = [C.POINTER(CsrPools), i32]
+    lib.cfmm_batch_solve_work_bytes.argtypes = [C.POINTER(CsrPools), i32, i64]
     lib.cfmm_batch_solve_work_bytes.restype = i64
     lib.cfmm_batch_solve.argtypes = [C.POINTER(CsrPools), C.POINTER(Batch), C.POINTER(BatchParams), vp, vp]
     lib.cfmm_batch_solve.restype = C.c_int

@@ -55,8 +55,8 @@ class CsrStore:
                                      self.gamma.data_ptr(), self.kind.data_ptr())
         self._work = None
 
-    def work(self, n_problems: int) -> torch.Tensor:
-        nbytes = self.lib.cfmm_batch_solve_work_bytes(C.byref(self.c_pools), n_problems)
+    def work(self, n_problems: int, nnz_max: int = 0) -> torch.Tensor:
+        nbytes = self.lib.cfmm_batch_solve_work_bytes(C.byref(self.c_pools), n_problems, nnz_max)
         if nbytes < 0:
             _lib.check(int(nbytes), "cfmm_batch_solve_work_bytes")
         if self._work is None or self._work.numel() < nbytes:
@@ -67,9 +67,11 @@ class CsrStore:
 @torch.no_grad()
 def solve_batch_device(store: CsrStore, c: torch.Tensor, a: torch.Tensor, flags: torch.Tensor, nu: torch.Tensor,
                        tol: float = 1e-8, want_trades: bool = True, pool_range: Optional[torch.Tensor] = None,
-                       max_outer: int = 60, max_inner: int = 100):
+                       max_outer: int = 60, max_inner: int = 100, nnz_max: int = 0):
     """Device-resident form: c, a [B, n] f64, flags [B, n] u8, nu [B, n] f64 (start prices, overwritten with the
-    solution).  Returns (psi [B, n], stats [B, 8], delta, lambda [B, nnz] or None).  Asynchronous on the current stream."""
+    solution).  Returns (psi [B, n], stats [B, 8], delta, lambda [B, nnz] or None).  Asynchronous on the current stream.
+    pool_range [B, 2] int64 (device): problem p uses pools [lo, hi) -- disjoint problems packed into one CSR array; then
+    delta / lambda are [1, nnz] and nnz_max (slots of the largest problem) sizes the workspace."""
     B, n = c.shape
     if n != store.n_tokens:
         raise ValueError("utilities must have one entry per token")
@@ -82,7 +84,7 @@ def solve_batch_device(store: CsrStore, c: torch.Tensor, a: torch.Tensor, flags:
     if want_trades:
         delta = torch.zeros(B if shared else 1, store.nnz, **f64)
         lam = torch.zeros(B if shared else 1, store.nnz, **f64)
-    work = store.work(B)
+    work = store.work(B, nnz_max)
     batch = _lib.Batch(B, None if shared else pool_range.data_ptr(), c.data_ptr(), a.data_ptr(), flags.data_ptr(),
                        nu.data_ptr(), psi.data_ptr(), stats.data_ptr(),
                        delta.data_ptr() if want_trades else None, lam.data_ptr() if want_trades else None,
@@ -131,6 +133,67 @@ def solve_batch(hp: HostPools, utilities: Sequence, nu0=None, tol: float = 1e-8,
         deltas = [d_h[p, ptr[i]:ptr[i + 1]] for i in range(hp.m)] if want_trades else []
         lambdas = [l_h[p, ptr[i]:ptr[i + 1]] for i in range(hp.m)] if want_trades else []
         out.append(Result(value=float(s[0]), psi=psi_h[p], deltas=deltas, lambdas=lambdas, nu=nu_h[p],
+                          dual_value=float(s[1]), gap=float(s[2]), primal_infeas=float(s[3]), iters=int(s[5]),
+                          evals=int(s[6]), hvps=0, status=names[int(s[7])], wall_s=wall, info=None))
+    return out
+
+
+def pack_problems(problems: Sequence):
+    """Concatenate independent small problems [(HostPools, utility), ...] into one CSR array + per-problem pool ranges.
+    Token indices stay local to each problem; problems with fewer tokens than the widest are padded with tokens no pool
+    touches, pinned at price 1 (objective-only, zero coefficient)."""
+    n = max(hp.n_tokens for hp, _ in problems)
+    B = len(problems)
+    ptr = [np.zeros(1, np.int64)]
+    ranges = np.empty((B, 2), np.int64)
+    c = np.zeros((B, n)); a = np.zeros((B, n)); fl = np.full((B, n), 2, np.uint8); nu = np.ones((B, n))
+    m0, off0, nnz_max = 0, 0, 0
+    for p, (hp, u) in enumerate(problems):
+        hp.validate()
+        ptr.append(np.asarray(hp.pool_ptr[1:], np.int64) + off0)
+        ranges[p] = (m0, m0 + hp.m)
+        m0 += hp.m
+        off0 += int(hp.pool_ptr[-1])
+        nnz_max = max(nnz_max, int(hp.pool_ptr[-1]))
+        sp = u.spec(hp.n_tokens)
+        k = hp.n_tokens
+        c[p, :k] = sp.c; a[p, :k] = sp.a
+        fl[p, :k] = np.asarray(sp.eq, np.uint8) | (np.asarray(sp.pinned, np.uint8) << 1)
+        nu[p, :k] = default_nu0(sp)
+        c[p, k:] = 1.0
+    cat = lambda name, dt: np.concatenate([np.asarray(getattr(hp, name), dt) for hp, _ in problems])
+    merged = HostPools(n, np.concatenate(ptr), cat("tok_idx", np.int32), cat("reserves", np.float64),
+                       cat("weights", np.float64), cat("gamma", np.float64), cat("kind", np.uint8))
+    return merged, ranges, c, a, fl, nu, nnz_max
+
+
+def solve_many(problems: Sequence, tol: float = 1e-8, device="cuda", want_trades: bool = True):
+    """Independent small problems -- each its own pools and utility, e.g. one per market or per block -- in ONE launch.
+    problems: [(HostPools, utility), ...].  Returns a list of api.Result, in order."""
+    from .api import Result
+    t0 = time.perf_counter()
+    if len(problems) == 0:
+        return []
+    merged, ranges, c, a, fl, nu, nnz_max = pack_problems(problems)
+    store = CsrStore(merged, device=device)
+    dev = store.device
+    up = lambda x: torch.as_tensor(x, device=dev)
+    nu_d = up(nu)
+    psi, stats, delta, lam = solve_batch_device(store, up(c), up(a), up(fl), nu_d, tol=tol, want_trades=want_trades,
+                                                pool_range=up(ranges), nnz_max=nnz_max)
+    stats_h, psi_h, nu_h = stats.cpu().numpy(), psi.cpu().numpy(), nu_d.cpu().numpy()
+    if want_trades:
+        d_h, l_h = delta.cpu().numpy()[0], lam.cpu().numpy()[0]
+    wall = time.perf_counter() - t0
+    names = {0: "optimal", 1: "max_iter", 2: "stalled", 3: "rejected"}
+    out: List = []
+    ptr = merged.pool_ptr
+    for p, (hp, _) in enumerate(problems):
+        s, k = stats_h[p], hp.n_tokens
+        lo, hi = ranges[p]
+        deltas = [d_h[ptr[i]:ptr[i + 1]] for i in range(lo, hi)] if want_trades else []
+        lambdas = [l_h[ptr[i]:ptr[i + 1]] for i in range(lo, hi)] if want_trades else []
+        out.append(Result(value=float(s[0]), psi=psi_h[p, :k], deltas=deltas, lambdas=lambdas, nu=nu_h[p, :k],
                           dual_value=float(s[1]), gap=float(s[2]), primal_infeas=float(s[3]), iters=int(s[5]),
                           evals=int(s[6]), hvps=0, status=names[int(s[7])], wall_s=wall, info=None))
     return out

@@ -44,10 +44,11 @@ inline long long padded(long long b) { return (b + kSmallThreads - 1) / kSmallTh
 
 }  // namespace
 
-extern "C" int64_t cfmm_batch_solve_work_bytes(const cfmm_csr_pools* pools, int32_t n_problems) {
+extern "C" int64_t cfmm_batch_solve_work_bytes(const cfmm_csr_pools* pools, int32_t n_problems, int64_t nnz_max) {
     if (!pools) return CFMM_E_NULL;
     if (n_problems < 0 || pools->n_tokens < 1 || pools->n_tokens > cfmm_small::NTOK_MAX || pools->nnz < 0) return CFMM_E_SIZE;
-    return (int64_t)sizeof(double) * cfmm_small::work_doubles(pools->n_tokens, pools->nnz) * padded(n_problems);
+    const int64_t cap = (nnz_max > 0 && nnz_max < pools->nnz) ? nnz_max : pools->nnz;    // slots of the largest problem
+    return (int64_t)sizeof(double) * cfmm_small::work_doubles(pools->n_tokens, cap) * padded(n_problems);
 }
 
 extern "C" int cfmm_batch_solve(const cfmm_csr_pools* pools, const cfmm_batch* batch, const cfmm_batch_params* prm,

@@ -219,7 +219,8 @@ typedef struct cfmm_batch_params {
     int32_t max_outer, max_inner;
 } cfmm_batch_params;
 
-int64_t cfmm_batch_solve_work_bytes(const cfmm_csr_pools* pools, int32_t n_problems);
+/* nnz_max: CSR slots of the largest single problem (<= 0: every problem may use all pools->nnz slots) */
+int64_t cfmm_batch_solve_work_bytes(const cfmm_csr_pools* pools, int32_t n_problems, int64_t nnz_max);
 int cfmm_batch_solve(const cfmm_csr_pools* pools, const cfmm_batch* batch, const cfmm_batch_params* prm, void* work,
                      void* stream);
 

@@ -30,16 +30,23 @@ def load():
 
 def solve(hp, specs, tol=1e-9, interleave=1, nu0=None, pool_range=None):
     """hp: HostPools; specs: objects with c, a, eq, pinned.  Returns dict(nu, psi, stats, delta, lam)."""
-    lib = load()
-    n, B, nnz = hp.n_tokens, len(specs), len(hp.tok_idx)
-    c = np.ascontiguousarray(np.stack([np.asarray(u.c, float) for u in specs]))
-    a = np.ascontiguousarray(np.stack([np.asarray(u.a, float) for u in specs]))
-    fl = np.ascontiguousarray(np.stack([np.asarray(u.eq, np.uint8) | (np.asarray(u.pinned, np.uint8) << 1)
-                                        for u in specs]).astype(np.uint8))
+    n, B = hp.n_tokens, len(specs)
+    c = np.stack([np.asarray(u.c, float) for u in specs])
+    a = np.stack([np.asarray(u.a, float) for u in specs])
+    fl = np.stack([np.asarray(u.eq, np.uint8) | (np.asarray(u.pinned, np.uint8) << 1) for u in specs])
     nu = np.empty((B, n))
     for p, u in enumerate(specs):
         pos = u.c[u.c > 0]
         nu[p] = np.where(u.c > 0, u.c, np.median(pos) if len(pos) else 1.0) if nu0 is None else nu0[p]
+    return solve_raw(hp, c, a, fl, nu, pool_range, tol, interleave)
+
+
+def solve_raw(hp, c, a, fl, nu, pool_range=None, tol=1e-9, interleave=1):
+    """the arrays cfmm_batch_solve takes (see include/cfmm_b200.h: cfmm_csr_pools, cfmm_batch), on the host"""
+    lib = load()
+    n, B, nnz = hp.n_tokens, len(c), len(hp.tok_idx)
+    c = np.ascontiguousarray(c, np.float64); a = np.ascontiguousarray(a, np.float64)
+    fl = np.ascontiguousarray(fl, np.uint8); nu = np.ascontiguousarray(nu, np.float64).copy()
     psi = np.zeros((B, n)); st = np.zeros((B, 8))
     shared = pool_range is None
     d = np.zeros((B if shared else 1, nnz)); l = np.zeros_like(d)

@@ -116,6 +116,40 @@ def test_host_build_disjoint_pool_ranges_and_rejected_input():
     assert int(out["stats"][0][7]) == 3 and np.isnan(out["stats"][0][0])
 
 
+def _many_problems():
+    probs = []
+    d = I.arbitrage_instance(); probs.append((H.host_pools(d), cf.Arbitrage(d["market_value"])))
+    d = I.liquidation_instance(); probs.append((H.host_pools(d), cf.Liquidate(d["target"], d["current_assets"])))
+    d = I.two_asset_instance(); probs.append((H.host_pools(d), cf.Swap(d["tok_in"], d["tok_out"], 12.5)))
+    hp, s = _small_mixed(11, m=20, n=9); probs.append((hp, cf.Arbitrage(s["prices"])))
+    return probs
+
+
+def _oracle_for(hp, util):
+    sp = util.spec(hp.n_tokens)
+    return O.solve(H.oracle_pools(hp), O.Utility(sp.c, sp.a, sp.eq, sp.pinned), tol=1e-9)
+
+
+def test_packing_of_independent_problems_on_the_host_build():
+    """batch.pack_problems (what solve_many launches): problems with different pools AND different token counts"""
+    from cfmm_routing_code_b200 import batch as B
+    probs = _many_problems()
+    merged, ranges, c, a, fl, nu, nnz_max = B.pack_problems(probs)
+    assert merged.n_tokens == 9 and len(merged.gamma) == 5 + 5 + 5 + 20
+    assert nnz_max == max(int(hp.pool_ptr[-1]) for hp, _ in probs) and ranges[-1, 1] == 35
+    out = small_host.solve_raw(merged, c, a, fl, nu, pool_range=ranges, tol=1e-9)
+    off = 0
+    for p, (hp, u) in enumerate(probs):
+        r = _oracle_for(hp, u)
+        assert int(out["stats"][p][7]) == 0
+        assert abs(out["stats"][p][0] - r.value) <= 1e-8 * max(abs(r.dual_value), 1e-300)
+        np.testing.assert_allclose(out["psi"][p, :hp.n_tokens], r.psi, atol=1e-6 * max(1.0, np.abs(r.psi).max()))
+        assert np.all(out["psi"][p, hp.n_tokens:] == 0.0) and np.all(out["nu"][p, hp.n_tokens:] == 1.0)
+        nnz = int(hp.pool_ptr[-1])
+        np.testing.assert_allclose(out["lam"][0, off:off + nnz], np.concatenate(r.lambdas), atol=1e-5 * max(1.0, np.abs(r.psi).max()))
+        off += nnz
+
+
 # ------------------------------------------------------------------------------------------------- GPU (the product)
 def _to_api(u):
     class _U:
@@ -188,3 +222,19 @@ def test_batch_kernel_rejects_what_it_does_not_cover():
     big = cf.HostPools.from_pairs(100, np.array([[0, 99]]), np.array([[1.0, 2.0]]), np.array([0.997]))
     with pytest.raises(ValueError):
         cf.CsrStore(big)
+
+
+@pytest.mark.gpu
+def test_solve_many_independent_problems_in_one_launch():
+    probs = _many_problems() * 40            # 160 problems, four shapes
+    rs = cf.solve_many(probs, tol=1e-9)
+    assert len(rs) == 160
+    refs = [_oracle_for(hp, u) for hp, u in probs[:4]]
+    for p, r in enumerate(rs):
+        ro, hp = refs[p % 4], probs[p][0]
+        assert r.status == "optimal", p
+        assert abs(r.value - ro.value) <= 1e-8 * max(abs(ro.dual_value), 1e-300)
+        assert r.psi.shape == (hp.n_tokens,) and len(r.deltas) == hp.m
+        np.testing.assert_allclose(r.psi, ro.psi, atol=1e-6 * max(1.0, np.abs(ro.psi).max()))
+        for i in range(hp.m):
+            np.testing.assert_allclose(r.lambdas[i], ro.lambdas[i], atol=1e-5 * max(1.0, np.abs(ro.psi).max()))
