@@ -24,12 +24,11 @@ def main():
                  utility=cf.Liquidate(d["target"], d["current_assets"]))
     print(f"Total liquidated value: {r.psi[d['target']]}")
     d = I.two_asset_instance()
+    # the loop of two-asset.py:40-100 as ONE kernel launch: all 50 trade sizes solved at once, one per GPU thread
+    rs = cf.solve_sweep(d["local_indices"], d["reserves"], d["fees"], d["kinds"], d["weights"],
+                        [cf.Swap(d["tok_in"], d["tok_out"], t) for t in d["amounts"]])
     rows = []
-    nu = None
-    for t in d["amounts"]:
-        r = cf.solve(d["local_indices"], d["reserves"], d["fees"], d["kinds"], d["weights"],
-                     utility=cf.Swap(d["tok_in"], d["tok_out"], t), nu0=nu)
-        nu = r.nu                                              # warm start the next t
+    for t, r in zip(d["amounts"], rs):
         print(f"Total liquidated value: {r.psi[d['tok_out']]}")
         for i in range(5):
             print(f"Market {i}, delta: {r.deltas[i]}, lambda: {r.lambdas[i]}")
