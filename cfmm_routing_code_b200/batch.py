@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .pools import HostPools, KIND_SUM_HOST
+from .pools import HostPools, KIND_GEOMEAN_HOST
 from .solver import default_nu0
 
 NTOK_MAX = 64      # cfmm_small::NTOK_MAX
@@ -42,12 +42,12 @@ class CsrStore:
         self.n_tokens, self.m, self.nnz = hp.n_tokens, hp.m, int(len(hp.tok_idx))
         dev = self.device
         per_slot_kind = np.repeat(np.asarray(hp.kind), np.diff(hp.pool_ptr))
-        w = np.where(per_slot_kind == KIND_SUM_HOST, 1.0, hp.weights)
+        w = np.where(per_slot_kind == KIND_GEOMEAN_HOST, hp.weights, 1.0)      # log(R/w) is a weighted-pool quantity
         self.pool_ptr = torch.as_tensor(np.ascontiguousarray(hp.pool_ptr, np.int64), device=dev)
         self.tok = torch.as_tensor(np.ascontiguousarray(hp.tok_idx, np.int32), device=dev)
         self.R = torch.as_tensor(np.ascontiguousarray(hp.reserves, np.float64), device=dev)
         self.w = torch.as_tensor(np.ascontiguousarray(hp.weights, np.float64), device=dev)
-        self.logrw = torch.log(self.R / torch.as_tensor(w, device=dev))
+        self.logrw = torch.log(torch.clamp(self.R, min=1e-300) / torch.as_tensor(w, device=dev))
         self.gamma = torch.as_tensor(np.ascontiguousarray(hp.gamma, np.float64), device=dev)
         self.kind = torch.as_tensor(np.ascontiguousarray(hp.kind, np.uint8), device=dev)
         self.c_pools = _lib.CsrPools(self.n_tokens, self.m, self.nnz, self.pool_ptr.data_ptr(), self.tok.data_ptr(),

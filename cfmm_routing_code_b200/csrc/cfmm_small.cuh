@@ -32,10 +32,11 @@ struct Pools {                       // CSR problem data (device pointers in the
     const int64_t* pool_ptr;         // [m+1]
     const int32_t* tok;              // [nnz]   token of every slot            arbitrage.py:6-12
     const double* R;                 // [nnz]   reserves                       arbitrage.py:14-20
-    const double* w;                 // [nnz]   normalised weights (0 on constant-sum pools)
+    const double* w;                 // [nnz]   normalised weights | 0 on constant-sum pools | virtual offsets (kind 3)
     const double* logrw;             // [nnz]   log(R/w)
     const double* gamma;             // [m]     fees                           arbitrage.py:22-28
-    const uint8_t* kind;             // [m]     1 = constant sum; 0 or 2 = weighted geometric mean (constant product = equal weights)
+    const uint8_t* kind;             // [m]     1 = constant sum; 3 = bounded-liquidity product; 0 or 2 = weighted geometric mean
+                                     //         (constant product = equal weights)
 };
 
 struct Params {
@@ -79,7 +80,32 @@ CFMM_HD inline double evaluate(const Pools& P, const Problem& Q, const Vec& nu, 
         const int k = (int)(P.pool_ptr[i + 1] - off);
         const double gam = P.gamma[i];
         double D[KMAX], L[KMAX];
-        if (P.kind[i] != 1) {
+        if (P.kind[i] == 3) {                                              // constant product on virtual reserves R + o,
+            double hc = 0.0;                                               // real reserves >= 0 (one Uniswap-v3 tick range)
+            D[0] = D[1] = L[0] = L[1] = 0.0;
+            const double V[2] = {P.R[off] + P.w[off], P.R[off + 1] + P.w[off + 1]};
+            const double pv[2] = {nu[P.tok[off]] * V[0], nu[P.tok[off + 1]] * V[1]};
+            for (int dir = 0; dir < 2; ++dir) {
+                const int ta = dir, tb = 1 - dir;
+                if (gam * pv[tb] > pv[ta]) {
+                    const double t = sqrt(gam * pv[tb] / pv[ta]);
+                    const double lb_ = V[tb] * (1.0 - 1.0 / t);
+                    if (lb_ > P.R[off + tb]) {                             // payout capped by the real reserve
+                        L[tb] = P.R[off + tb];
+                        D[ta] = V[ta] * P.R[off + tb] / (P.w[off + tb] * gam);
+                    } else {
+                        L[tb] = lb_;
+                        D[ta] = V[ta] * (t - 1.0) / gam;
+                        hc += 0.5 * sqrt(pv[0] * pv[1] / gam);
+                    }
+                }
+            }
+            if (Hs && hc != 0.0) {
+                const int t0 = P.tok[off], t1 = P.tok[off + 1];
+                (*Hs)[t0 * n + t0] += hc; (*Hs)[t1 * n + t1] += hc;
+                (*Hs)[t0 * n + t1] -= hc; (*Hs)[t1 * n + t0] -= hc;
+            }
+        } else if (P.kind[i] != 1) {
             double wa[KMAX];
             double M = 0.0;
             if (k == 2 && P.w[off] == P.w[off + 1]) {                      // sqrt(x0 x1) >= sqrt(R0 R1), arbitrage.py:68-70
@@ -265,7 +291,7 @@ CFMM_HD inline Stats solve_one(const Pools& P, Problem Q, const Params& prm, dou
         const int64_t o = P.pool_ptr[i];
         const int k = (int)(P.pool_ptr[i + 1] - o);
         has_sum = has_sum || P.kind[i] == 1;
-        bad = P.kind[i] > 2 || k < 2 || k > KMAX || (P.kind[i] == 1 && k != 2);
+        bad = P.kind[i] > 3 || k < 2 || k > KMAX || ((P.kind[i] == 1 || P.kind[i] == 3) && k != 2);
         for (int j = 0; j < k && !bad; ++j) bad = P.tok[o + j] < 0 || P.tok[o + j] >= n;
     }
     if (bad) {

@@ -140,3 +140,33 @@ def synth_basket(n_tokens, prices, seed, n_assets=16, scale=1e-3, liq_mean=np.ex
     a = np.zeros(n_tokens)
     a[toks] = np.exp(rng.standard_normal(n_assets)) * liq_mean / prices[toks] * scale
     return a
+
+
+# ------------------------------------------------------------------------------------------
+# bounded-liquidity constant product (a Uniswap-v3 tick range) -- not in the reference: the first
+# "more trading functions" extension behind the per-pool interface
+# ------------------------------------------------------------------------------------------
+def v3_position(liquidity, p_lo, p_hi, p):
+    """Real reserves and virtual-reserve offsets of a concentrated-liquidity position: liquidity L on the price range
+    [p_lo, p_hi] (token-1 per token-0) at current price p.  Returns (reserves [x, y], offsets [o_x, o_y]) such that
+    (x + o_x)(y + o_y) = L^2 is the position's curve and x, y >= 0 what it can actually pay out."""
+    p = float(np.clip(p, p_lo, p_hi))
+    sp, sa, sb = np.sqrt(p), np.sqrt(p_lo), np.sqrt(p_hi)
+    return [liquidity * (1 / sp - 1 / sb), liquidity * (sp - sa)], [liquidity / sb, liquidity * sa]
+
+
+def v3_instance():
+    """3 tokens; two tick ranges of a v3 pool on (0, 1) (adjacent ranges: the upper one holds token 0 only), one
+    in-range position on (0, 2), a constant-product pair (1, 2) and a weighted 3-token pool."""
+    r_a, o_a = v3_position(100.0, 0.8, 1.25, 1.0)
+    r_b, o_b = v3_position(80.0, 1.25, 1.6, 1.0)        # out of range: all in token 0
+    r_c, o_c = v3_position(50.0, 1.9, 2.2, 2.0)
+    return dict(
+        n_tokens=3,
+        local_indices=[[0, 1], [0, 1], [0, 2], [1, 2], [0, 1, 2]],
+        reserves=[r_a, r_b, r_c, [30.0, 20.0], [10.0, 12.0, 8.0]],
+        fees=[0.997, 0.997, 0.9995, 0.997, 0.99],
+        kinds=["bounded_product", "bounded_product", "bounded_product", "product", "geomean"],
+        weights=[o_a, o_b, o_c, None, [2, 1, 1]],
+        market_value=[1.3, 1.0, 0.45],
+    )

@@ -17,6 +17,7 @@ from . import _lib
 
 KIND_GEOMEAN_HOST = 0   # host CSR convention: 0 = (weighted) geometric mean, 1 = constant sum
 KIND_SUM_HOST = 1
+KIND_BOUNDED_HOST = 3   # constant product on virtual reserves (reserves + offsets), real reserves >= 0; offsets ride in `weights`
 
 
 @dataclasses.dataclass
@@ -56,6 +57,12 @@ class HostPools:
                 if k != 2:
                     raise ValueError("constant-sum pools must have 2 tokens (as arbitrage.py:11)")
                 kd.append(KIND_SUM_HOST); wts += [0.0] * k
+            elif kinds[i] == "bounded_product":
+                # not a reference atom: one Uniswap-v3 tick range; weights[i] = the two virtual-reserve offsets
+                o = None if (weights is None or weights[i] is None) else np.asarray(weights[i], float)
+                if k != 2 or o is None or len(o) != 2 or np.any(o < 0) or not np.all(np.isfinite(o)):
+                    raise ValueError(f"pool {i}: bounded_product needs 2 tokens and 2 non-negative offsets in weights[i]")
+                kd.append(KIND_BOUNDED_HOST); wts += list(o)
             elif kinds[i] in ("geomean", "product"):
                 w = np.ones(k) if (weights is None or weights[i] is None) else np.asarray(weights[i], float)
                 if len(w) != k or np.any(w <= 0):
@@ -89,8 +96,11 @@ class HostPools:
         return self
 
     def validate(self):
-        if np.any(self.reserves <= 0) or not np.all(np.isfinite(self.reserves)):
-            raise ValueError("reserves must be positive and finite")
+        slot_kind = np.repeat(np.asarray(self.kind), np.diff(self.pool_ptr)) if np.any(self.kind == KIND_BOUNDED_HOST) else None
+        virt = self.reserves if slot_kind is None else self.reserves + np.where(slot_kind == KIND_BOUNDED_HOST, self.weights, 0.0)
+        lo_ok = np.all(self.reserves > 0) if slot_kind is None else np.all(self.reserves >= 0) and np.all(virt > 0)
+        if not lo_ok or not np.all(np.isfinite(self.reserves)):
+            raise ValueError("reserves must be positive and finite (bounded_product: >= 0 with positive virtual reserves)")
         if np.any(self.gamma <= 0) or np.any(self.gamma > 1):
             raise ValueError("fees (gamma) must lie in (0, 1]")
         if self.tok_idx.min(initial=0) < 0 or self.tok_idx.max(initial=0) >= self.n_tokens:
@@ -151,6 +161,9 @@ def split_buckets(hp: HostPools, rank: int = 0, world: int = 1) -> List["BucketS
             return [BucketSpec(hp, _lib.KIND_PRODUCT, 2, None)]
         lo, hi = (m * rank) // world, (m * (rank + 1)) // world
         return [BucketSpec(hp, _lib.KIND_PRODUCT, 2, np.arange(lo, hi, dtype=np.int64))]
+    if np.any(hp.kind == KIND_BOUNDED_HOST):
+        raise ValueError("bounded_product pools are only built into the per-thread solver (solve(..., method='thread'), "
+                         "solve_batch, solve_many: <= 64 tokens); the pool-parallel buckets do not take them yet")
     ar = np.diff(hp.pool_ptr)
     first = hp.pool_ptr[:-1]
     is_cp = (hp.kind == KIND_GEOMEAN_HOST) & (ar == 2)

@@ -28,7 +28,10 @@ extern "C" {
 enum {
     CFMM_KIND_PRODUCT = 0, /* sqrt(x1 x2) >= sqrt(R1 R2)                 arbitrage.py:68-70 */
     CFMM_KIND_SUM = 1,     /* sum(x) >= sum(R), x >= 0                   arbitrage.py:73-74 */
-    CFMM_KIND_GEOMEAN = 2  /* prod x^w >= prod R^w                       arbitrage.py:65    */
+    CFMM_KIND_GEOMEAN = 2, /* prod x^w >= prod R^w                       arbitrage.py:65    */
+    CFMM_KIND_BOUNDED_PRODUCT = 3 /* sqrt((x1+o1)(x2+o2)) >= sqrt((R1+o1)(R2+o2)), x >= 0: constant product on virtual
+                              reserves, one Uniswap-v3 tick range.  Not in the reference (a new atom for the cons list
+                              of arbitrage.py:63-74); cfmm_batch_solve only, offsets passed in `weights`          */
 };
 
 enum {
@@ -195,7 +198,7 @@ typedef struct cfmm_csr_pools {
     const double* weights;     /* [nnz]  normalised like cp.geo_mean(p=...), arbitrage.py:65; 0 on constant-sum pools */
     const double* logrw;       /* [nnz]  log(reserves / weights) (unused on constant-sum pools)      */
     const double* gamma;       /* [n_pools] fees, arbitrage.py:22-28                                 */
-    const uint8_t* kind;       /* [n_pools] CFMM_KIND_SUM, else (PRODUCT | GEOMEAN) weighted geometric mean */
+    const uint8_t* kind;       /* [n_pools] CFMM_KIND_SUM | CFMM_KIND_BOUNDED_PRODUCT, else weighted geometric mean */
 } cfmm_csr_pools;
 
 typedef struct cfmm_batch {

@@ -39,6 +39,8 @@ import numpy as np
 
 KIND_GEOMEAN = 0   # weighted geometric mean; constant product is the (1/2, 1/2) 2-token case
 KIND_CONST_SUM = 1
+KIND_BOUNDED = 3   # constant product on virtual reserves R + o with real reserves >= 0 (one Uniswap-v3 tick range):
+                   # not in the reference; the "more trading functions" extension point of arbitrage.py:63-74
 
 _TINY = 1e-300
 
@@ -52,7 +54,8 @@ class Pools:
     pool_ptr: np.ndarray   # int64 [m+1]
     tok_idx: np.ndarray    # int32 [nnz]   local_indices, concatenated
     reserves: np.ndarray   # f64   [nnz]
-    weights: np.ndarray    # f64   [nnz]   normalised per pool (sum 1); unused for const-sum
+    weights: np.ndarray    # f64   [nnz]   per-slot parameter of the trading function: weight normalised per pool
+                           #               (geomean), unused (const-sum), virtual-reserve offset o_j (bounded product)
     gamma: np.ndarray      # f64   [m]     fees[i] = 1 - fee
     kind: np.ndarray       # uint8 [m]
 
@@ -78,6 +81,9 @@ class Pools:
             if kk in ("sum", KIND_CONST_SUM):
                 kd.append(KIND_CONST_SUM)
                 wts += [0.0] * k
+            elif kk in ("bounded_product", KIND_BOUNDED):
+                kd.append(KIND_BOUNDED)
+                wts += [float(x) for x in weights[i]]        # the virtual offsets, as given
             else:
                 kd.append(KIND_GEOMEAN)
                 w = np.ones(k) if (weights is None or weights[i] is None) else np.asarray(weights[i], float)
@@ -157,6 +163,24 @@ def arb_product_scalar(R, gamma, nu):
     elif gamma * p0 > p1:
         t = np.sqrt(gamma * p0 / p1)
         D[1] = R[1] * (t - 1) / gamma; L[0] = R[0] * (1 - 1 / t)
+    return D, L
+
+
+def arb_bounded_product_scalar(R, o, gamma, nu):
+    """sqrt((x0+o0)(x1+o1)) >= sqrt((R0+o0)(R1+o1)), x = R + gamma D - L >= 0: a constant-product curve on the virtual
+    reserves V = R + o of which only the real part R can be paid out (a Uniswap-v3 position inside its tick range).
+    Optimal trade = the constant-product one on V, with the payout capped at R_b; at the cap the tender follows from
+    the curve: (V_a + gamma D_a)(V_b - R_b) = V_a V_b."""
+    R = np.asarray(R, float); o = np.asarray(o, float)
+    V = R + o
+    D = np.zeros(2); L = np.zeros(2)
+    p = nu * V
+    for a, b in ((0, 1), (1, 0)):
+        if gamma * p[b] > p[a]:
+            t = np.sqrt(gamma * p[b] / p[a])
+            L[b] = V[b] * (1 - 1 / t); D[a] = V[a] * (t - 1) / gamma
+            if L[b] > R[b]:
+                L[b] = R[b]; D[a] = V[a] * R[b] / (o[b] * gamma)
     return D, L
 
 
@@ -254,6 +278,25 @@ def _geomean_group(g, nu, lognu):
     return D, L, M, act
 
 
+def _bounded_group(g, nu):
+    idx, R, o, gam = g["idx"], g["R"], g["w"], g["gamma"]
+    V = R + o
+    D = np.zeros_like(R); L = np.zeros_like(R)
+    p0, p1 = nu[idx[:, 0]] * V[:, 0], nu[idx[:, 1]] * V[:, 1]
+    hcoef = np.zeros(len(gam))
+    for a, b, pa, pb in ((0, 1, p0, p1), (1, 0, p1, p0)):
+        go = gam * pb > pa
+        t = np.sqrt(np.where(go, gam * pb / pa, 1.0))
+        Lb = V[:, b] * (1 - 1 / t)
+        cap = go & (Lb > R[:, b])
+        L[:, b] = np.where(go, np.where(cap, R[:, b], Lb), 0.0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            Dcap = V[:, a] * R[:, b] / (o[:, b] * gam)
+        D[:, a] = np.where(go, np.where(cap, Dcap, V[:, a] * (t - 1) / gam), 0.0)
+        hcoef += np.where(go & ~cap, 0.5 * np.sqrt(p0 * p1 / gam), 0.0)     # = M/4 of the constant-product pool
+    return D, L, hcoef
+
+
 def _sum_group(g, nu, eps):
     assert g["k"] == 2, "constant-sum pools are 2-token (arbitrage.py:11,19)"
     idx, R, gam = g["idx"], g["R"], g["gamma"]
@@ -287,6 +330,8 @@ def evaluate(bk: Buckets, nu, eps=0.0, want_trades=False, want_hess=False):
     for g in bk.groups:
         if g["kind"] == KIND_GEOMEAN:
             D, L, M, act = _geomean_group(g, nu, lognu)
+        elif g["kind"] == KIND_BOUNDED:
+            D, L, hc = _bounded_group(g, nu)
         else:
             D, L, hc = _sum_group(g, nu, eps)
         y = L - D

@@ -29,6 +29,8 @@ def solve_primal(n_tokens, local_indices, reserves, fees, kinds, weights, object
     for i in range(m):
         if kinds[i] == "sum":
             W.append(None)
+        elif kinds[i] == "bounded_product":
+            W.append(np.asarray(weights[i], float))          # virtual offsets o, not weights
         else:
             w = np.ones(sizes[i]) if weights[i] is None else np.asarray(weights[i], float)
             W.append(w / w.sum())
@@ -53,6 +55,11 @@ def solve_primal(n_tokens, local_indices, reserves, fees, kinds, weights, object
     for i in range(m):
         if kinds[i] == "sum":
             cons.append(dict(type="ineq", fun=lambda z, i=i: np.sum(newres(z, i)) - np.sum(R[i])))
+            cons.append(dict(type="ineq", fun=lambda z, i=i: newres(z, i)))
+        elif kinds[i] == "bounded_product":
+            # sqrt((x0+o0)(x1+o1)) >= sqrt((R0+o0)(R1+o1)) in log form, and x >= 0
+            cons.append(dict(type="ineq", fun=lambda z, i=i: np.sum(
+                np.log(np.maximum(newres(z, i) + W[i], 1e-300)) - np.log(R[i] + W[i]))))
             cons.append(dict(type="ineq", fun=lambda z, i=i: newres(z, i)))
         else:
             # log form of geo_mean(x, p=w) >= geo_mean(R, p=w): same feasible set, better scaled

@@ -51,7 +51,7 @@ def solve_raw(hp, c, a, fl, nu, pool_range=None, tol=1e-9, interleave=1):
     shared = pool_range is None
     d = np.zeros((B if shared else 1, nnz)); l = np.zeros_like(d)
     slot_kind = np.repeat(np.asarray(hp.kind), np.diff(hp.pool_ptr))
-    logrw = np.log(hp.reserves / np.where(slot_kind == 1, 1.0, hp.weights))
+    logrw = np.log(np.maximum(hp.reserves, 1e-300) / np.where(slot_kind == 0, hp.weights, 1.0))
     keep = [np.ascontiguousarray(hp.pool_ptr, np.int64), np.ascontiguousarray(hp.tok_idx, np.int32),
             np.ascontiguousarray(hp.reserves, np.float64), np.ascontiguousarray(hp.weights, np.float64),
             np.ascontiguousarray(logrw), np.ascontiguousarray(hp.gamma, np.float64),

@@ -192,3 +192,51 @@ def test_property_const_sum_trades_respect_the_pool(seed, gam, eps, frac):
     x = R + gam * D - L
     assert np.all(D >= -1e-15) and np.all(L >= -1e-15)
     assert x.sum() >= R.sum() * (1 - 1e-13) and np.all(x >= -1e-12 * R.max())
+
+
+def test_bounded_product_closed_form_vs_its_own_program():
+    """constant product on virtual reserves with the payout capped by the real reserves (a v3 tick range): the closed
+    form beats / matches SLSQP on the pool's own program, in range and at the cap; zero offsets = plain product"""
+    rng = np.random.default_rng(4)
+    for trial in range(12):
+        R = np.exp(rng.normal(2, 0.5, 2)); o = np.exp(rng.normal(2, 1.0, 2)); gam = 0.997
+        nu = np.exp(rng.normal(0, 0.6 if trial % 2 else 0.05, 2))
+        D, L = O.arb_bounded_product_scalar(R, o, gam, nu)
+        x = R + gam * D - L
+        assert np.all(x >= -1e-12) and np.prod(x + o) >= np.prod(R + o) * (1 - 1e-12)
+        f = lambda z: -np.dot(nu, z[2:] - z[:2])
+        cons = [dict(type="ineq", fun=lambda z: np.sum(np.log(np.maximum(R + gam * z[:2] - z[2:] + o, 1e-300))
+                                                      - np.log(R + o))),
+                dict(type="ineq", fun=lambda z: R + gam * z[:2] - z[2:])]
+        res = optimize.minimize(f, np.zeros(4), method="SLSQP", bounds=[(0, None)] * 4, constraints=cons,
+                                options=dict(ftol=1e-14, maxiter=500))
+        assert np.dot(nu, L - D) >= -res.fun - 1e-7 * max(1.0, abs(res.fun))
+    D0, L0 = O.arb_bounded_product_scalar([10.0, 20.0], [0.0, 0.0], 0.997, np.array([2.3, 1.0]))
+    D1, L1 = O.arb_product_scalar(np.array([10.0, 20.0]), 0.997, np.array([2.3, 1.0]))
+    np.testing.assert_allclose(D0, D1, rtol=1e-14); np.testing.assert_allclose(L0, L1, rtol=1e-14)
+
+
+def test_bounded_product_instance_dual_solution_matches_slsqp_primal():
+    from cfmm_routing_code_b200 import instances as I
+    from oracle import primal_scipy as PS
+    d = I.v3_instance()
+    P = O.Pools.from_lists(3, d["local_indices"], d["reserves"], d["fees"], d["kinds"], d["weights"])
+    cases = [(O.Utility.arbitrage(d["market_value"]), d["market_value"], [("ge", j, 0.0) for j in range(3)]),
+             (O.Utility.swap(3, 0, 2, 40.0), [0, 0, 1.0], [("ge", 0, 40.0), ("ge", 1, 0.0), ("ge", 2, 0.0)]),
+             (O.Utility.swap(3, 1, 0, 25.0), [1.0, 0, 0], [("ge", 0, 0.0), ("ge", 1, 25.0), ("ge", 2, 0.0)])]
+    for u, obj, cons in cases:
+        r = O.solve(P, u, tol=1e-10)
+        pr = PS.solve_primal(3, d["local_indices"], d["reserves"], d["fees"], d["kinds"], d["weights"], obj, cons)
+        assert r.status == "optimal" and abs(r.gap) <= 1e-9
+        assert abs(r.value - pr["value"]) <= 1e-7 * max(1.0, abs(r.value))
+        np.testing.assert_allclose(r.psi, pr["psi"], atol=2e-5)
+    # finite-difference check of gradient and scaled Hessian with bounded pools in and out of range
+    bk = O.Buckets(P)
+    nu = np.array([1.31, 1.02, 0.47])
+    ev = O.evaluate(bk, nu, want_hess=True)
+    Hs = ev["hess_scaled"] / nu[:, None] / nu[None, :]
+    for j in range(3):
+        h = 1e-6 * nu[j]; e = np.zeros(3); e[j] = h
+        ep, em = O.evaluate(bk, nu + e), O.evaluate(bk, nu - e)
+        assert abs((ep["arb"] - em["arb"]) / (2 * h) - ev["psi"][j]) <= 1e-5 * (abs(ev["psi"][j]) + 1)
+        np.testing.assert_allclose((ep["psi"] - em["psi"]) / (2 * h), Hs[:, j], atol=2e-4 * np.abs(Hs).max())
