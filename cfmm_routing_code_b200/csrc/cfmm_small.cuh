@@ -27,6 +27,7 @@ namespace cfmm_small {
 constexpr int KMAX = 8;              // largest weighted-pool arity (the reference uses 3..5; cfg3/4 use 2..8)
 constexpr int NTOK_MAX = 64;         // dense n x n Newton systems per thread: keep n small
 constexpr double TINY = 1e-300;
+constexpr double DT_MAX = 3.0;       // largest log-price change of one Newton step
 
 struct Pools {                       // CSR problem data (device pointers in the kernel)
     const int64_t* pool_ptr;         // [m+1]
@@ -334,6 +335,11 @@ CFMM_HD inline Stats solve_one(const Pools& P, Problem Q, const Params& prm, dou
                 for (int j = 0; j < n; ++j) mx = fmax(mx, fabs(pg[j]));
                 mx = fmax(mx, TINY);
                 for (int j = 0; j < n; ++j) dt[j] = -pg[j] / mx;
+            }
+            {                                                            // (near-)singular system: keep the direction,
+                double big = 0.0;                                        // bound the step to a price factor of e^3
+                for (int j = 0; j < n; ++j) big = fmax(big, fabs(dt[j]));
+                if (big > DT_MAX) for (int j = 0; j < n; ++j) dt[j] *= DT_MAX / big;
             }
             double alpha = 1.0;
             bool ok = false;

@@ -28,6 +28,9 @@ import numpy as np
 import torch
 
 
+DT_MAX = 3.0      # largest log-price change of one dense Newton step
+
+
 @dataclasses.dataclass
 class DualSpec:
     """Utility in 'linear + box' form (see api.Arbitrage / Liquidate / Swap)."""
@@ -197,6 +200,12 @@ def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 0.1
             slope = torch.dot(pg, dt)     # = grad . (nu*dt)
             if not bool(torch.isfinite(slope)) or float(slope) >= 0.0:
                 dt = -pg / pg.abs().max().clamp(min=1e-300)
+            if linear_solver == "dense":
+                # (near-)singular system, e.g. every pool tying the free prices to a bound is saturated: keep the
+                # direction, bound the step to a price factor of e^3 and let the line search find the kink
+                big = float(dt.abs().max())
+                if big > DT_MAX:
+                    dt = dt * (DT_MAX / big)
             # ---- projected Armijo backtracking along nu * exp(alpha dt)
             alpha = 1.0
             g0 = float(g)

@@ -43,6 +43,7 @@ KIND_BOUNDED = 3   # constant product on virtual reserves R + o with real reserv
                    # not in the reference; the "more trading functions" extension point of arbitrage.py:63-74
 
 _TINY = 1e-300
+DT_MAX = 3.0      # largest log-price change of one Newton step
 
 
 # --------------------------------------------------------------------------------------
@@ -462,6 +463,9 @@ def solve(pools: Pools, util: Utility, nu0=None, tol=1e-9, eps=0.1, eps_min=1e-4
             dt = np.zeros(n); dt[free] = dtf
             if not np.all(np.isfinite(dt)) or np.dot(pg, dt) >= 0:
                 dt = -pg / max(np.abs(pg).max(), 1e-300)
+            big = np.abs(dt).max()
+            if big > DT_MAX:        # (near-)singular system, e.g. every pool that ties the free prices to a bound is
+                dt *= DT_MAX / big  # saturated: keep the direction, bound the step, let the line search find the kink
             alpha = 1.0
             g0 = ev["g"]
             ok = False

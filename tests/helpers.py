@@ -29,3 +29,49 @@ def mixed_host_pools(m, n, seed):
 def random_prices(prices, seed, spread=0.05):
     rng = np.random.default_rng(seed)
     return prices * np.exp(spread * rng.standard_normal(len(prices)))
+
+
+def random_small_problem(rng, all_kinds=True):
+    """A random routing problem of the reference's scale: 3-6 tokens, up to 13 pools of every kind.  A chain of
+    constant-product pools over all tokens comes first, so every utility below is feasible.  Returns (HostPools,
+    list-form dict, token prices)."""
+    n = int(rng.integers(3, 7)); m = int(rng.integers(n, 14))
+    prices = np.exp(rng.normal(0, 1, n))
+    li, res, fees, kinds, w = [], [], [], [], []
+    pool_kinds = ["product", "geomean", "sum", "bounded_product"] if all_kinds else ["product", "geomean", "sum"]
+    probs = [0.4, 0.25, 0.15, 0.2] if all_kinds else [0.5, 0.3, 0.2]
+    for i in range(m):
+        kd = str(rng.choice(pool_kinds, p=probs))
+        k = 2 if kd != "geomean" else int(rng.integers(2, min(n, 5) + 1))
+        toks = rng.choice(n, k, replace=False)
+        if i < n - 1:
+            kd, k, toks = "product", 2, np.array([i, i + 1])
+        liq = np.exp(rng.normal(4, 1.0))
+        noise = np.exp(0.05 * rng.standard_normal(k))
+        if kd == "geomean":
+            ww = rng.dirichlet(np.ones(k)); R = liq * ww / prices[toks] * noise; w.append(list(ww))
+        elif kd == "bounded_product":
+            p = prices[toks[0]] / prices[toks[1]]
+            lo, hi = p * np.exp(-rng.uniform(0.01, 0.3)), p * np.exp(rng.uniform(0.01, 0.3))
+            R, o = I.v3_position(liq / np.sqrt(prices[toks[0]] * prices[toks[1]]), lo, hi,
+                                 p * np.exp(0.02 * rng.standard_normal()))
+            w.append(o)
+        else:
+            R = liq / prices[toks] * noise; w.append(None)
+        li.append([int(t) for t in toks]); res.append([float(x) for x in R]); kinds.append(kd)
+        fees.append(float(rng.choice([0.997, 0.999, 0.9995])))
+    d = dict(n_tokens=n, local_indices=li, reserves=res, fees=fees, kinds=kinds, weights=w)
+    return host_pools(d), d, prices
+
+
+def random_utilities(rng, n, prices):
+    """one of each utility of the reference (arbitrage.py:57,77 / two-asset.py:66,86 / liquidation.py:57,77-80)"""
+    us = [O.Utility.arbitrage(prices * np.exp(0.03 * rng.standard_normal(n)))]
+    i, o = rng.choice(n, 2, replace=False)
+    us.append(O.Utility.swap(n, int(i), int(o), float(np.exp(rng.normal(2, 1.5)) / prices[i])))
+    basket = np.zeros(n); tgt = int(rng.integers(n))
+    for j in rng.choice(n, 2, replace=False):
+        if j != tgt:
+            basket[j] = float(np.exp(rng.normal(1, 1)) / prices[j])
+    us.append(O.Utility.liquidate(n, tgt, basket))
+    return us

@@ -12,6 +12,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import cfmm_routing_code_b200 as cf
+from oracle import cfmm_oracle as O
 from cfmm_routing_code_b200 import _lib, instances as I, pools as PL
 from cfmm_routing_code_b200.solver import Comm, solve_dual
 from cpu_evaluator import OracleEvaluator
@@ -73,6 +74,20 @@ def test_solver_logic_on_synthetic_mixed_pools_certifies_its_answer():
     hp, s = H.mixed_host_pools(3000, 60, seed=4)
     r = solve_dual(OracleEvaluator(hp), cf.Arbitrage(s["prices"]).spec(60), tol=1e-8)
     assert r.status == "optimal" and abs(r.gap) <= 1e-7 and r.primal_infeas <= 1e-7
+
+
+def test_solver_logic_on_random_small_problems_matches_the_oracle():
+    """the product's python outer loop (dense Newton path, look-ahead on) on 45 random problems of the reference's
+    scale, evaluations by the CPU stand-in for PoolStore: same optimal values as the oracle's own solve"""
+    rng = np.random.default_rng(21)
+    for _ in range(15):
+        hp, d, prices = H.random_small_problem(rng, all_kinds=False)
+        op = H.oracle_pools(hp)
+        for u in H.random_utilities(rng, hp.n_tokens, prices):
+            r = solve_dual(OracleEvaluator(hp), cf.DualSpec(u.c, u.a, u.eq, u.pinned), tol=1e-8)
+            ro = O.solve(op, u, tol=1e-8)
+            assert abs(r.primal_value - ro.value) <= 1e-7 * max(abs(ro.dual_value), 1e-300)
+            assert abs(r.gap) <= 1e-7 and r.primal_infeas <= 1e-7
 
 
 def test_utilities_and_input_validation():
