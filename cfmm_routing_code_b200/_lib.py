@@ -9,7 +9,7 @@ import os
 
 from . import build as _build
 
-KIND_PRODUCT, KIND_SUM, KIND_GEOMEAN = 0, 1, 2
+KIND_PRODUCT, KIND_SUM, KIND_GEOMEAN, KIND_BOUNDED = 0, 1, 2, 3
 
 _ERRORS = {
     -1: "CFMM_E_NULL (required pointer is NULL)",

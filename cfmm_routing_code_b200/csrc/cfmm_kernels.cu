@@ -9,6 +9,7 @@
 #include <math.h>
 
 #include "cfmm_dev.cuh"
+#include "cfmm_small.cuh"     // bounded_pair(): the bounded-liquidity pool math, shared with the per-thread solver
 
 namespace cfmm {
 std::atomic<long long> g_launches{0};
@@ -138,6 +139,16 @@ k_eval_pair(long long m, long long ld, int n_tokens, const double* __restrict__ 
         double y0, y1, h;
         if (KIND == CFMM_KIND_PRODUCT) {
             product_pool(R0, R1, g, n0, n1, y0, y1, h);
+        } else if (KIND == CFMM_KIND_BOUNDED_PRODUCT) {
+            // `thbar` carries the per-slot auxiliary array of the bucket: here the virtual-reserve offsets
+            double D[2], L[2];
+            cfmm_small::bounded_pair(R0, R1, thbar[i], thbar[ld + i], g, n0, n1, D, L, h);
+            y0 = L[0] - D[0];
+            y1 = L[1] - D[1];
+            if (TRADES) {
+                delta[i] = D[0]; delta[ld + i] = D[1];
+                lambda[i] = L[0]; lambda[ld + i] = L[1];
+            }
         } else {
             // order A pays out token 1 (tender 0), order B pays out token 0 (tender 1)
             double thA, payA, hA, thB, payB, hB;
@@ -541,8 +552,10 @@ int launch_pair(const cfmm_bucket* b, int n_tokens, const double* nu, double eps
     double* delta = out ? out->delta : nullptr;
     double* lambda = out ? out->lambda : nullptr;
     double* hcoef = out ? out->hcoef : nullptr;
-    if ((g_scatter_mode == 0 || g_scatter_mode == 3) && tma_ok(b)) {
-        auto kern = k_eval_pair_tma<KIND, TRADES, HESS>;
+    // per-slot auxiliary array: fill multipliers of constant-sum orders | virtual-reserve offsets of bounded products
+    const double* aux = KIND == CFMM_KIND_BOUNDED_PRODUCT ? b->weights : b->theta_bar;
+    if (KIND != CFMM_KIND_BOUNDED_PRODUCT && (g_scatter_mode == 0 || g_scatter_mode == 3) && tma_ok(b)) {
+        auto kern = k_eval_pair_tma<KIND == CFMM_KIND_BOUNDED_PRODUCT ? CFMM_KIND_PRODUCT : KIND, TRADES, HESS>;
         const size_t sm = (size_t)kStages * kStageBytes;
         static bool attr_set = false;      // per instantiation
         if (!attr_set) {
@@ -560,11 +573,11 @@ int launch_pair(const cfmm_bucket* b, int n_tokens, const double* nu, double eps
         const size_t sm = (size_t)n_tokens * sizeof(double);
         auto kern = k_eval_pair<KIND, SharedScatter, TRADES, HESS>;
         allow_smem(kern, sm);
-        kern<<<grid_for(m, 2), kThreads, sm, st>>>(m, b->stride, n_tokens, b->reserves, b->tok_idx, b->gamma, b->theta_bar,
+        kern<<<grid_for(m, 2), kThreads, sm, st>>>(m, b->stride, n_tokens, b->reserves, b->tok_idx, b->gamma, aux,
                                                     eps, nu, psi, arb, delta, lambda, hcoef);
     } else {
         k_eval_pair<KIND, GlobalScatter, TRADES, HESS><<<grid_for(m, 8), kThreads, 0, st>>>(
-            m, b->stride, n_tokens, b->reserves, b->tok_idx, b->gamma, b->theta_bar, eps, nu, psi, arb, delta, lambda, hcoef);
+            m, b->stride, n_tokens, b->reserves, b->tok_idx, b->gamma, aux, eps, nu, psi, arb, delta, lambda, hcoef);
     }
     return check_launch();
 }
@@ -627,6 +640,10 @@ int validate(const cfmm_bucket* b, int n_tokens) {
             if (b->arity < 2 || b->arity > 32) return CFMM_E_KIND;
             if (b->n_pools > 0 && (!b->weights || !b->logrw)) return CFMM_E_NULL;
             break;
+        case CFMM_KIND_BOUNDED_PRODUCT:
+            if (b->arity != 2) return CFMM_E_KIND;
+            if (b->n_pools > 0 && !b->weights) return CFMM_E_NULL;       // the offsets
+            break;
         default:
             return CFMM_E_KIND;
     }
@@ -652,6 +669,8 @@ int cfmm_arb_eval(const cfmm_bucket* b, int32_t n_tokens, const double* nu, cons
             return dispatch_pair<CFMM_KIND_PRODUCT>(b, n_tokens, nu, eps, psi, arb, out, st);
         case CFMM_KIND_SUM:
             return dispatch_pair<CFMM_KIND_SUM>(b, n_tokens, nu, eps, psi, arb, out, st);
+        case CFMM_KIND_BOUNDED_PRODUCT:
+            return dispatch_pair<CFMM_KIND_BOUNDED_PRODUCT>(b, n_tokens, nu, eps, psi, arb, out, st);
         default:
             break;
     }

@@ -68,6 +68,35 @@ struct Stats { double value, dual, gap, infeas, err; int iters, evals, status; }
 CFMM_HD inline bool is_eq(const Problem& Q, int j) { return Q.flags[j] & 1; }
 CFMM_HD inline bool is_pinned(const Problem& Q, int j) { return Q.flags[j] & 2; }
 
+// Constant product on virtual reserves V = R + o with the real reserves R >= 0 (one Uniswap-v3 tick range; not a
+// reference atom).  The optimal trade is the constant-product one on V; when it would pay out more than R_b the payout
+// is capped there and the tender follows from the curve, (V_a + gamma D_a)(V_b - R_b) = V_a V_b.  hc = coefficient of
+// [[1,-1],[-1,1]] in the scaled Hessian (0 at the cap: the trade no longer depends on the prices).
+// Shared by the per-thread solver below and the pool-parallel kernel k_eval_pair (cfmm_kernels.cu).
+CFMM_HD inline void bounded_pair(double R0, double R1, double o0, double o1, double gam, double n0, double n1,
+                                 double* D, double* L, double& hc) {
+    const double R[2] = {R0, R1}, o[2] = {o0, o1};
+    const double V[2] = {R0 + o0, R1 + o1};
+    const double pv[2] = {n0 * V[0], n1 * V[1]};
+    D[0] = D[1] = L[0] = L[1] = 0.0;
+    hc = 0.0;
+    for (int dir = 0; dir < 2; ++dir) {
+        const int ta = dir, tb = 1 - dir;
+        if (gam * pv[tb] > pv[ta]) {
+            const double t = sqrt(gam * pv[tb] / pv[ta]);
+            const double lout = V[tb] * (1.0 - 1.0 / t);
+            if (lout > R[tb]) {                                        // payout capped by the real reserve
+                L[tb] = R[tb];
+                D[ta] = V[ta] * R[tb] / (o[tb] * gam);
+            } else {
+                L[tb] = lout;
+                D[ta] = V[ta] * (t - 1.0) / gam;
+                hc += 0.5 * sqrt(pv[0] * pv[1] / gam);
+            }
+        }
+    }
+}
+
 // One dual evaluation of the problem: psi = sum_i A_i (L_i - D_i), returns arb = sum_i nu_i'(L_i - D_i).
 // Hs (n x n, nullable) receives the scaled Hessian (true Hessian = diag(1/nu) Hs diag(1/nu)).
 CFMM_HD inline double evaluate(const Pools& P, const Problem& Q, const Vec& nu, const Vec& lognu, double eps,
@@ -81,26 +110,9 @@ CFMM_HD inline double evaluate(const Pools& P, const Problem& Q, const Vec& nu, 
         const int k = (int)(P.pool_ptr[i + 1] - off);
         const double gam = P.gamma[i];
         double D[KMAX], L[KMAX];
-        if (P.kind[i] == 3) {                                              // constant product on virtual reserves R + o,
-            double hc = 0.0;                                               // real reserves >= 0 (one Uniswap-v3 tick range)
-            D[0] = D[1] = L[0] = L[1] = 0.0;
-            const double V[2] = {P.R[off] + P.w[off], P.R[off + 1] + P.w[off + 1]};
-            const double pv[2] = {nu[P.tok[off]] * V[0], nu[P.tok[off + 1]] * V[1]};
-            for (int dir = 0; dir < 2; ++dir) {
-                const int ta = dir, tb = 1 - dir;
-                if (gam * pv[tb] > pv[ta]) {
-                    const double t = sqrt(gam * pv[tb] / pv[ta]);
-                    const double lb_ = V[tb] * (1.0 - 1.0 / t);
-                    if (lb_ > P.R[off + tb]) {                             // payout capped by the real reserve
-                        L[tb] = P.R[off + tb];
-                        D[ta] = V[ta] * P.R[off + tb] / (P.w[off + tb] * gam);
-                    } else {
-                        L[tb] = lb_;
-                        D[ta] = V[ta] * (t - 1.0) / gam;
-                        hc += 0.5 * sqrt(pv[0] * pv[1] / gam);
-                    }
-                }
-            }
+        if (P.kind[i] == 3) {
+            double hc = 0.0;
+            bounded_pair(P.R[off], P.R[off + 1], P.w[off], P.w[off + 1], gam, nu[P.tok[off]], nu[P.tok[off + 1]], D, L, hc);
             if (Hs && hc != 0.0) {
                 const int t0 = P.tok[off], t1 = P.tok[off + 1];
                 (*Hs)[t0 * n + t0] += hc; (*Hs)[t1 * n + t1] += hc;

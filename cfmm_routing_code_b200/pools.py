@@ -161,9 +161,6 @@ def split_buckets(hp: HostPools, rank: int = 0, world: int = 1) -> List["BucketS
             return [BucketSpec(hp, _lib.KIND_PRODUCT, 2, None)]
         lo, hi = (m * rank) // world, (m * (rank + 1)) // world
         return [BucketSpec(hp, _lib.KIND_PRODUCT, 2, np.arange(lo, hi, dtype=np.int64))]
-    if np.any(hp.kind == KIND_BOUNDED_HOST):
-        raise ValueError("bounded_product pools are only built into the per-thread solver (solve(..., method='thread'), "
-                         "solve_batch, solve_many: <= 64 tokens); the pool-parallel buckets do not take them yet")
     ar = np.diff(hp.pool_ptr)
     first = hp.pool_ptr[:-1]
     is_cp = (hp.kind == KIND_GEOMEAN_HOST) & (ar == 2)
@@ -176,6 +173,11 @@ def split_buckets(hp: HostPools, rank: int = 0, world: int = 1) -> List["BucketS
         if np.any(ar[cs] != 2):
             raise ValueError("constant-sum pools must have 2 tokens")
         keys.append((_lib.KIND_SUM, 2, np.nonzero(cs)[0]))
+    bp = hp.kind == KIND_BOUNDED_HOST
+    if bp.any():
+        if np.any(ar[bp] != 2):
+            raise ValueError("bounded_product pools must have 2 tokens")
+        keys.append((_lib.KIND_BOUNDED, 2, np.nonzero(bp)[0]))
     gm = (hp.kind == KIND_GEOMEAN_HOST) & ~is_cp
     for k in np.unique(ar[gm]).tolist():
         if k < 2 or k > 32:
@@ -228,6 +230,8 @@ class DeviceBucket:
             W = hp.weights[spec.off]
             self.weights = torch.as_tensor(_padded(W, self.stride, 1.0), **f64)
             self.logrw = torch.as_tensor(_padded(np.log(R / W), self.stride, 0.0), **f64)
+        if self.kind == _lib.KIND_BOUNDED:                 # the virtual-reserve offsets ride in the weights slot
+            self.weights = torch.as_tensor(_padded(hp.weights[spec.off], self.stride, 1.0), **f64)
         if self.kind == _lib.KIND_SUM:
             self.theta_bar = torch.zeros((2, self.stride), **f64)
         self.delta = self.lam = self.hcoef = self.hmask = None
@@ -558,7 +562,7 @@ class PoolStore:
         """32 B per 2-token pool, 28k+12 per weighted pool, + nu, psi, arb."""
         n = 0
         for b in self.buckets:
-            n += b.m * (32 if b.kind != _lib.KIND_GEOMEAN else 28 * b.arity + 12)
+            n += b.m * (28 * b.arity + 12 if b.kind == _lib.KIND_GEOMEAN else 48 if b.kind == _lib.KIND_BOUNDED else 32)
         return n + 16 * self.n_tokens + 8
 
     # -- the hot path --------------------------------------------------------------------------

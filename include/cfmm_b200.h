@@ -31,7 +31,7 @@ enum {
     CFMM_KIND_GEOMEAN = 2, /* prod x^w >= prod R^w                       arbitrage.py:65    */
     CFMM_KIND_BOUNDED_PRODUCT = 3 /* sqrt((x1+o1)(x2+o2)) >= sqrt((R1+o1)(R2+o2)), x >= 0: constant product on virtual
                               reserves, one Uniswap-v3 tick range.  Not in the reference (a new atom for the cons list
-                              of arbitrage.py:63-74); cfmm_batch_solve only, offsets passed in `weights`          */
+                              of arbitrage.py:63-74); arity 2, the two offsets passed in `weights`                */
 };
 
 enum {

@@ -327,5 +327,8 @@ def test_batch_kernel_bounded_product_pools_match_oracle():
     for r, g in zip(rs, _v3_golden()):
         assert abs(r.value - g["value"]) <= 1e-6 * max(1.0, abs(g["value"]))
         np.testing.assert_allclose(r.psi, g["psi"], atol=2e-5)
-    with pytest.raises(ValueError):                       # the pool-parallel buckets do not take this kind yet
-        cf.solve_pools(hp, _to_api(specs[0]), method="pools")
+    for u, g in zip(specs[:3], _v3_golden()):            # and the same pools through the pool-parallel kernels
+        r = cf.solve_pools(hp, _to_api(u), method="pools", tol=1e-9)
+        assert r.status == "optimal"
+        assert abs(r.value - g["value"]) <= 1e-6 * max(1.0, abs(g["value"]))
+        np.testing.assert_allclose(r.psi, g["psi"], atol=2e-5)

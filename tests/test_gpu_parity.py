@@ -111,6 +111,40 @@ def test_mixed_eval_matches_oracle(eps):
     _check_eval(hp, H.random_prices(s["prices"], 3, 0.03), eps=eps, theta=theta)
 
 
+def test_bounded_product_bucket_matches_oracle():
+    """the bounded-liquidity product (v3 tick range) in the pool-parallel path: trades, psi, arb and the scaled
+    Hessian of one evaluation, in range / at the payout cap / out of range, alone and next to every other kind"""
+    d = I.v3_instance(); hp = H.host_pools(d)
+    for nu in ([1.31, 1.02, 0.47], [1.0, 1.0, 0.5], [3.0, 1.0, 0.2], [0.3, 1.0, 2.0]):
+        st, ref = _check_eval(hp, np.array(nu))
+        Hs = ref["hess_scaled"]
+        np.testing.assert_allclose(st.hess_dense().cpu().numpy(), Hs, atol=1e-11 * max(np.abs(Hs).max(), 1e-300))
+    rng = np.random.default_rng(17)
+    for _ in range(6):
+        hp, d, prices = H.random_small_problem(rng)
+        st, ref = _check_eval(hp, prices * np.exp(0.1 * rng.standard_normal(hp.n_tokens)))
+        Hs = ref["hess_scaled"]
+        np.testing.assert_allclose(st.hess_dense().cpu().numpy(), Hs, atol=1e-11 * max(np.abs(Hs).max(), 1e-300))
+        v = rng.standard_normal(hp.n_tokens)
+        np.testing.assert_allclose(st.hvp(torch.as_tensor(v, **F64)).cpu().numpy(), Hs @ v,
+                                   atol=1e-10 * max(np.abs(Hs).max(), 1e-300))
+
+
+def test_random_small_problems_of_every_kind_through_the_pool_parallel_path():
+    rng = np.random.default_rng(23)
+    for _ in range(5):
+        hp, d, prices = H.random_small_problem(rng)
+        op = H.oracle_pools(hp)
+        for u in H.random_utilities(rng, hp.n_tokens, prices):
+            class _U:
+                def spec(self, n, u=u):
+                    return cf.DualSpec(u.c, u.a, u.eq, u.pinned)
+            r = cf.solve_pools(hp, _U(), method="pools", tol=1e-8)
+            ro = O.solve(op, u, tol=1e-8)
+            assert abs(r.value - ro.value) <= 1e-7 * max(abs(ro.dual_value), 1e-300)
+            assert abs(r.gap) <= 1e-7 and r.primal_infeas <= 1e-7
+
+
 def test_large_arity_generic_kernel():
     rng = np.random.default_rng(5)
     n, m, k = 64, 300, 13

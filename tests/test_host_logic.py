@@ -81,7 +81,7 @@ def test_solver_logic_on_random_small_problems_matches_the_oracle():
     scale, evaluations by the CPU stand-in for PoolStore: same optimal values as the oracle's own solve"""
     rng = np.random.default_rng(21)
     for _ in range(15):
-        hp, d, prices = H.random_small_problem(rng, all_kinds=False)
+        hp, d, prices = H.random_small_problem(rng)
         op = H.oracle_pools(hp)
         for u in H.random_utilities(rng, hp.n_tokens, prices):
             r = solve_dual(OracleEvaluator(hp), cf.DualSpec(u.c, u.a, u.eq, u.pinned), tol=1e-8)
@@ -126,6 +126,21 @@ def test_bucketing_and_pool_sharding_partition_the_problem():
     hp2, _ = H.cp_host_pools(1000, 16, seed=1)
     (b,) = PL.split_buckets(hp2)
     assert b.identity and b.kind == _lib.KIND_PRODUCT and np.array_equal(b.off[:, 3], [6, 7])
+
+
+def test_bounded_product_pools_get_their_own_bucket():
+    d = I.v3_instance(); hp = H.host_pools(d)
+    hp.validate()
+    specs = PL.split_buckets(hp)
+    by_kind = {(b.kind, b.arity): b for b in specs}
+    assert set(by_kind) == {(_lib.KIND_BOUNDED, 2), (_lib.KIND_PRODUCT, 2), (_lib.KIND_GEOMEAN, 3)}
+    b = by_kind[(_lib.KIND_BOUNDED, 2)]
+    assert b.sel.tolist() == [0, 1, 2] and np.array_equal(hp.weights[b.off], np.array(d["weights"][:3]).T)
+    assert hp.reserves[hp.pool_ptr[1] + 1] == 0.0            # the out-of-range position holds token 0 only
+    with pytest.raises(ValueError):
+        cf.HostPools.from_lists(3, [[0, 1, 2]], [[1, 1, 1]], [0.99], ["bounded_product"], [[1, 1, 1]])
+    with pytest.raises(ValueError):
+        cf.HostPools.from_lists(2, [[0, 1]], [[0.0, 1.0]], [0.99], ["bounded_product"], [[0.0, 1.0]]).validate()
 
 
 def test_blocked_layout_builder_tables_reproduce_the_scatter():
