@@ -131,6 +131,8 @@ def load(build_if_missing: bool = True):
     lib.cfmm_blocked_solve.restype = C.c_int
     lib.cfmm_batch_solve_work_bytes.argtypes = [C.POINTER(CsrPools), i32, i64]
     lib.cfmm_batch_solve_work_bytes.restype = i64
+    lib.cfmm_set_batch_lanes.argtypes = [i32]
+    lib.cfmm_set_batch_lanes.restype = C.c_int
     lib.cfmm_batch_solve.argtypes = [C.POINTER(CsrPools), C.POINTER(Batch), C.POINTER(BatchParams), vp, vp]
     lib.cfmm_batch_solve.restype = C.c_int
     lib.cfmm_allreduce_oneshot.argtypes = [vp, vp, i32, i32, i64, i32, vp, C.c_uint32, i32, vp]
@@ -147,6 +149,8 @@ def load(build_if_missing: bool = True):
     lib.cfmm_reset_launch_count.restype = None
     lib.cfmm_last_cuda_error.restype = C.c_char_p
     lib.cfmm_version.restype = C.c_char_p
+    if os.environ.get("CFMM_BATCH_LANES"):          # 1 | 32 threads per problem in cfmm_batch_solve (experiments)
+        lib.cfmm_set_batch_lanes(int(os.environ["CFMM_BATCH_LANES"]))
     if os.environ.get("CFMM_BLOCKED_CFG"):          # kernel-variant override for experiments / A-B tests
         lib.cfmm_set_blocked_config(int(os.environ["CFMM_BLOCKED_CFG"]))
     _lib = lib

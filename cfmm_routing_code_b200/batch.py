@@ -67,7 +67,7 @@ class CsrStore:
 @torch.no_grad()
 def solve_batch_device(store: CsrStore, c: torch.Tensor, a: torch.Tensor, flags: torch.Tensor, nu: torch.Tensor,
                        tol: float = 1e-8, want_trades: bool = True, pool_range: Optional[torch.Tensor] = None,
-                       max_outer: int = 60, max_inner: int = 100, nnz_max: int = 0):
+                       max_outer: int = 60, max_inner: int = 100, nnz_max: int = 0, lanes: Optional[int] = None):
     """Device-resident form: c, a [B, n] f64, flags [B, n] u8, nu [B, n] f64 (start prices, overwritten with the
     solution).  Returns (psi [B, n], stats [B, 8], delta, lambda [B, nnz] or None).  Asynchronous on the current stream.
     pool_range [B, 2] int64 (device): problem p uses pools [lo, hi) -- disjoint problems packed into one CSR array; then
@@ -84,6 +84,8 @@ def solve_batch_device(store: CsrStore, c: torch.Tensor, a: torch.Tensor, flags:
     if want_trades:
         delta = torch.zeros(B if shared else 1, store.nnz, **f64)
         lam = torch.zeros(B if shared else 1, store.nnz, **f64)
+    if lanes is not None:           # 1 = a problem per thread (default), 32 = a problem per warp (see cfmm_small.cu)
+        _lib.check(store.lib.cfmm_set_batch_lanes(int(lanes)), "cfmm_set_batch_lanes")
     work = store.work(B, nnz_max)
     batch = _lib.Batch(B, None if shared else pool_range.data_ptr(), c.data_ptr(), a.data_ptr(), flags.data_ptr(),
                        nu.data_ptr(), psi.data_ptr(), stats.data_ptr(),

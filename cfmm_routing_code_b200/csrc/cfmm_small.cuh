@@ -97,15 +97,35 @@ CFMM_HD inline void bounded_pair(double R0, double R1, double o0, double o1, dou
     }
 }
 
+#ifdef __CUDA_ARCH__
+// sum over the LANES consecutive lanes that share a problem; x + y == y + x exactly, so every lane ends with the same bits
+template <int LANES>
+__device__ __forceinline__ double lanes_sum(double v) {
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#endif
+
 // One dual evaluation of the problem: psi = sum_i A_i (L_i - D_i), returns arb = sum_i nu_i'(L_i - D_i).
 // Hs (n x n, nullable) receives the scaled Hessian (true Hessian = diag(1/nu) Hs diag(1/nu)).
+//
+// LANES > 1 (device only): LANES threads of one warp own the SAME problem.  Every lane keeps a full private copy of the
+// state and runs the identical instruction stream; only this pool loop is split (lane l takes pools l, l+LANES, ...)
+// and the partial psi / arb / Hessian / fills are then summed over the lanes with an xor butterfly, which leaves
+// bit-identical totals in every lane -- so the lanes never diverge and need no other communication.
+template <int LANES>
 CFMM_HD inline double evaluate(const Pools& P, const Problem& Q, const Vec& nu, const Vec& lognu, double eps,
-                               const Vec& psi, const Vec* Hs, bool trades, bool store_fill) {
+                               const Vec& psi, const Vec* Hs, bool trades, bool store_fill, int lane) {
     const int n = Q.n;
     for (int j = 0; j < n; ++j) { lognu[j] = log(nu[j]); psi[j] = 0.0; }
     if (Hs) for (int e = 0; e < n * n; ++e) (*Hs)[e] = 0.0;
+    if (LANES > 1 && store_fill) {
+        const int64_t nnz = P.pool_ptr[Q.p1] - Q.off0;
+        for (int64_t x = 0; x < nnz; ++x) Q.theta_new[x] = 0.0;
+    }
     double arb = 0.0;
-    for (int64_t i = Q.p0; i < Q.p1; ++i) {
+    for (int64_t i = Q.p0 + (LANES > 1 ? lane : 0); i < Q.p1; i += LANES) {
         const int64_t off = P.pool_ptr[i];
         const int k = (int)(P.pool_ptr[i + 1] - off);
         const double gam = P.gamma[i];
@@ -209,6 +229,17 @@ CFMM_HD inline double evaluate(const Pools& P, const Problem& Q, const Vec& nu, 
             if (trades && Q.delta) { Q.delta[off + j] = D[j]; Q.lam[off + j] = L[j]; }
         }
     }
+#ifdef __CUDA_ARCH__
+    if (LANES > 1) {
+        arb = lanes_sum<LANES>(arb);
+        for (int j = 0; j < n; ++j) psi[j] = lanes_sum<LANES>(psi[j]);
+        if (Hs) for (int e = 0; e < n * n; ++e) (*Hs)[e] = lanes_sum<LANES>((*Hs)[e]);
+        if (store_fill) {
+            const int64_t nnz = P.pool_ptr[Q.p1] - Q.off0;
+            for (int64_t x = 0; x < nnz; ++x) Q.theta_new[x] = lanes_sum<LANES>(Q.theta_new[x]);
+        }
+    }
+#endif
     return arb;
 }
 
@@ -285,8 +316,9 @@ CFMM_HD inline bool newton_direction(int n, uint64_t free_mask, const Vec& Hs, c
 CFMM_HD inline int64_t work_doubles(int n, int64_t nnz) { return 12LL * n + 2LL * n * n + (int64_t)n * (n + 1) + 2 * nnz; }
 
 // The solve.  nu_io [n]: start prices in, optimal prices out.  psi_out [n].  `work`/`stride`: interleaved workspace.
+template <int LANES = 1>
 CFMM_HD inline Stats solve_one(const Pools& P, Problem Q, const Params& prm, double* nu_io, double* psi_out,
-                               double* work, int64_t stride) {
+                               double* work, int64_t stride, int lane = 0) {
     const int n = Q.n;
     const int64_t nnz = P.pool_ptr[Q.p1] - Q.off0;
     int64_t e = 0;
@@ -331,7 +363,7 @@ CFMM_HD inline Stats solve_one(const Pools& P, Problem Q, const Params& prm, dou
     uint64_t free_mask = 0, fm_t = 0;
 
     for (int outer = 0; outer < prm.max_outer; ++outer) {
-        g = dual_value(Q, nuv[cur], evaluate(P, Q, nuv[cur], lognu, eps_t, psiv[cur], &Hsv[cur], false, false));
+        g = dual_value(Q, nuv[cur], evaluate<LANES>(P, Q, nuv[cur], lognu, eps_t, psiv[cur], &Hsv[cur], false, false, lane));
         ++evals;
         int inner_status = 1;
         const double inner_tol = has_sum ? fmax(prm.tol, fmin(1e-3, 1e-2 * move)) : prm.tol;
@@ -365,7 +397,7 @@ CFMM_HD inline Stats solve_one(const Pools& P, Problem Q, const Params& prm, dou
                     nuv[nxt][j] = v;
                     lin += grad[j] * (v - nuv[cur][j]);
                 }
-                g_t = dual_value(Q, nuv[nxt], evaluate(P, Q, nuv[nxt], lognu, eps_t, psiv[nxt], &Hsv[nxt], false, false));
+                g_t = dual_value(Q, nuv[nxt], evaluate<LANES>(P, Q, nuv[nxt], lognu, eps_t, psiv[nxt], &Hsv[nxt], false, false, lane));
                 ++evals;
                 if (g_t <= g + 1e-4 * lin) { ok = true; break; }
                 if (fabs(g_t - g) <= 1e-13 * fabs(g) || fabs(lin) <= 1e-9 * fabs(g)) {   // g cannot resolve this step
@@ -385,8 +417,8 @@ CFMM_HD inline Stats solve_one(const Pools& P, Problem Q, const Params& prm, dou
         status = inner_status;
         if (!has_sum) break;
         // exact duality gap at the current prices (trades from the smoothed problem, dual with eps = 0)
-        evaluate(P, Q, nuv[cur], lognu, eps_t, psiv[cur ^ 1], nullptr, false, true);
-        const double g_exact = dual_value(Q, nuv[cur], evaluate(P, Q, nuv[cur], lognu, 0.0, grad_t, nullptr, false, false));
+        evaluate<LANES>(P, Q, nuv[cur], lognu, eps_t, psiv[cur ^ 1], nullptr, false, true, lane);
+        const double g_exact = dual_value(Q, nuv[cur], evaluate<LANES>(P, Q, nuv[cur], lognu, 0.0, grad_t, nullptr, false, false, lane));
         evals += 2;
         double primal = 0.0;
         for (int j = 0; j < n; ++j) primal += Q.c[j] * psiv[cur ^ 1][j];
@@ -410,8 +442,8 @@ CFMM_HD inline Stats solve_one(const Pools& P, Problem Q, const Params& prm, dou
 
     // final read-out: trades and psi from the (smoothed) problem, dual value from the exact one
     const Vec& psi_f = psiv[cur ^ 1];
-    evaluate(P, Q, nuv[cur], lognu, eps_t, psi_f, nullptr, true, false);
-    const double dval = dual_value(Q, nuv[cur], evaluate(P, Q, nuv[cur], lognu, 0.0, grad_t, nullptr, false, false));
+    evaluate<LANES>(P, Q, nuv[cur], lognu, eps_t, psi_f, nullptr, true, false, lane);
+    const double dval = dual_value(Q, nuv[cur], evaluate<LANES>(P, Q, nuv[cur], lognu, 0.0, grad_t, nullptr, false, false, lane));
     evals += 2;
     double primal = 0.0, viol = 0.0;
     for (int j = 0; j < n; ++j) {
@@ -419,8 +451,7 @@ CFMM_HD inline Stats solve_one(const Pools& P, Problem Q, const Params& prm, dou
         const double v = is_pinned(Q, j) ? 0.0 : (is_eq(Q, j) ? fabs(s) : fmax(-s, 0.0));
         viol += nuv[cur][j] * v;
         primal += Q.c[j] * psi_f[j];
-        nu_io[j] = nuv[cur][j];
-        psi_out[j] = psi_f[j];
+        if (LANES == 1 || lane == 0) { nu_io[j] = nuv[cur][j]; psi_out[j] = psi_f[j]; }
     }
     Stats st;
     st.value = primal; st.dual = dval;

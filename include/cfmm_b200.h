@@ -224,6 +224,10 @@ typedef struct cfmm_batch_params {
 
 /* nnz_max: CSR slots of the largest single problem (<= 0: every problem may use all pools->nnz slots) */
 int64_t cfmm_batch_solve_work_bytes(const cfmm_csr_pools* pools, int32_t n_problems, int64_t nnz_max);
+/* threads per problem: 1 (default; throughput of large batches) or 32 (one warp per problem, the pool loop of every
+ * evaluation split over the lanes: latency of small batches / problems with many pools).  Set before sizing the work
+ * buffer: it scales with the lane count. */
+int cfmm_set_batch_lanes(int32_t lanes);
 int cfmm_batch_solve(const cfmm_csr_pools* pools, const cfmm_batch* batch, const cfmm_batch_params* prm, void* work,
                      void* stream);
 

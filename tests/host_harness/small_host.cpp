@@ -1,6 +1,8 @@
 // Test-only host build of csrc/cfmm_small.cuh: the same solve_one() the CUDA kernel runs per thread, looped over the
 // problems of a batch, so the control flow can be checked against oracle/cfmm_oracle.py without a GPU.  Not part of the
 // product: nothing under cfmm_routing_code_b200/ loads this.
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include "../../cfmm_routing_code_b200/csrc/cfmm_small.cuh"
 
@@ -12,6 +14,7 @@ extern "C" int small_host_solve(int n_tokens, long long n_pools, const long long
     using namespace cfmm_small;
     Pools P{(const int64_t*)pool_ptr, tok, R, w, logrw, gamma, kind};
     Params prm{tol, 0.1, 1e-4, 0.25, 1e-12, 60, 100};
+    if (const char* e = getenv("SMALL_HOST_EPS")) sscanf(e, "%lf,%lf,%lf", &prm.eps0, &prm.eps_min, &prm.eps_shrink);   // experiments
     const int64_t nnz = pool_ptr[n_pools];
     const int64_t stride = interleave ? ((n_problems + 31) / 32) * 32 : 1;    // exercise the strided workspace too
     std::vector<double> work((size_t)work_doubles(n_tokens, nnz) * (interleave ? stride : n_problems));
