@@ -38,6 +38,19 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
     b = _lib.Bucket(9, 2, 0, 0, 1, 1, 1, None, None, None)
     assert lib.cfmm_arb_eval(ctypes.byref(b), 4, None, None, 0.0, None, None, None, None) == -2
     assert lib.cfmm_blocked_eval(None, 4, None, None, None, None, None, 0, None) == -1
+    # batch entry points: NULL / size / kind checks, work-buffer arithmetic (12 n + 2 n^2 + n(n+1) + 2 nnz doubles per lane)
+    assert lib.cfmm_batch_solve(None, None, None, None, None) == -1
+    cp = _lib.CsrPools(3, 5, 13, None, None, None, None, None, None, None)
+    assert lib.cfmm_batch_solve_work_bytes(ctypes.byref(cp), 50, 0) == 8 * (36 + 18 + 12 + 26) * 64
+    assert lib.cfmm_batch_solve_work_bytes(ctypes.byref(cp), 50, 6) == 8 * (36 + 18 + 12 + 12) * 64
+    assert lib.cfmm_set_batch_lanes(5) == -2 and lib.cfmm_set_batch_lanes(32) == 0
+    assert lib.cfmm_batch_solve_work_bytes(ctypes.byref(cp), 50, 0) == 8 * (36 + 18 + 12 + 26) * 64 * 32
+    assert lib.cfmm_set_batch_lanes(1) == 0
+    big = _lib.CsrPools(65, 5, 13, None, None, None, None, None, None, None)
+    assert lib.cfmm_batch_solve_work_bytes(ctypes.byref(big), 50, 0) == -3
+    bt = _lib.Batch(1, None, None, None, None, None, None, None, None, None, 0)
+    prm = _lib.BatchParams(1e-8, 0.1, 1e-4, 0.25, 1e-12, 60, 100)
+    assert lib.cfmm_batch_solve(ctypes.byref(cp), ctypes.byref(bt), ctypes.byref(prm), None, None) == -1
 
 
 def test_product_path_fails_loudly_without_a_gpu():
