@@ -152,7 +152,8 @@ def load(build_if_missing: bool = True):
     if os.environ.get("CFMM_BATCH_LANES"):          # 1 | 32 threads per problem in cfmm_batch_solve (experiments)
         lib.cfmm_set_batch_lanes(int(os.environ["CFMM_BATCH_LANES"]))
     if os.environ.get("CFMM_BLOCKED_CFG"):          # kernel-variant override for experiments / A-B tests
-        lib.cfmm_set_blocked_config(int(os.environ["CFMM_BLOCKED_CFG"]))
+        for c in os.environ["CFMM_BLOCKED_CFG"].split(","):       # e.g. "1296" = tiles of 896 pools, "3,1296"
+            lib.cfmm_set_blocked_config(int(c))
     _lib = lib
     return lib
 

@@ -514,8 +514,14 @@ k_blocked_regs(const BlockedArgs A) {
     if (AR) fused_allreduce_tail<THREADS>(A);      // compiled only into the pool-sharded instantiations
 }
 
-// ---- configuration of the TMA-staged variant (the register-fed variant uses the same tile size)
-struct Cfg0 { static constexpr int P = 1024, T = 512, S = 2, CTAS = 2; };   // 2 x (85 + 24) KB smem per SM
+// ---- configuration of the TMA-staged variant (the register-fed variant uses the same tile size): two pools per thread,
+// two ring stages, two CTAs per SM.  P = 1024: 2 x (85 + 24) KB of shared memory per SM.  The smaller tile sizes exist for
+// load balance: a launch walks ceil(n_tiles / (2 SMs)) tiles on its critical path, e.g. 1M pools = 977 tiles of 1024 over
+// 296 CTAs -> 4 x 1024 = 4096 pools, but 1117 tiles of 896 -> 4 x 896 = 3584 (cfmm_set_blocked_config(400 + P)).
+template <int P_>
+struct CfgP { static constexpr int P = P_, T = P_ / 2, S = 2, CTAS = 2; };
+using Cfg0 = CfgP<1024>;
+int g_tile_pools = 1024;      // what cfmm_blocked_layout_info tells the layout builder
 int g_cfg = -1;
 int g_pdl = 1;
 int g_row_cap = 32;
@@ -547,9 +553,9 @@ int launch_cfg(const BlockedArgs& A, cudaStream_t st) {
     return check_launch();
 }
 
-template <int MODE, bool TRADES, bool HESS>
+template <int P, int MODE, bool TRADES, bool HESS>
 int launch_regs(const BlockedArgs& A, cudaStream_t st) {
-    constexpr int P = 1024, T = 512, S = 4;
+    constexpr int T = P / 2, S = 4;
     const bool ar = A.peer.world > 1;
     auto kern = ar ? k_blocked_regs<P, T, S, MODE, TRADES, HESS, true> : k_blocked_regs<P, T, S, MODE, TRADES, HESS, false>;
     const size_t sm = (size_t)S * sizeof(TabStage<P>) + (size_t)(2 * P + 4 * P) * sizeof(double);
@@ -570,19 +576,28 @@ int launch_regs(const BlockedArgs& A, cudaStream_t st) {
     return check_launch();
 }
 
-template <int MODE, bool TRADES, bool HESS>
-int launch_blocked(const BlockedArgs& A, cudaStream_t st) {
+template <int P, int MODE, bool TRADES, bool HESS>
+int launch_blocked_p(const BlockedArgs& A, cudaStream_t st) {
     // default (-1): evaluation through the TMA-staged slabs, Hessian products / diagonal (1 slab, less data per tile)
     // through the register-fed single-barrier variant -- each is the faster one for its mode (profiles/r1f_*)
-    if (g_cfg == 3 || (g_cfg < 0 && MODE != 0)) return launch_regs<MODE, TRADES, HESS>(A, st);
-    return launch_cfg<Cfg0, MODE, TRADES, HESS>(A, st);
+    if (g_cfg == 3 || (g_cfg < 0 && MODE != 0)) return launch_regs<P, MODE, TRADES, HESS>(A, st);
+    return launch_cfg<CfgP<P>, MODE, TRADES, HESS>(A, st);
 }
 
-int cfg_P() { return Cfg0::P; }
+bool tile_pools_ok(long long P) { return P == 1024 || P == 960 || P == 896; }
+
+template <int MODE, bool TRADES, bool HESS>
+int launch_blocked(const BlockedArgs& A, cudaStream_t st) {
+    switch (A.n_tiles ? A.M / A.n_tiles : 1024) {          // pools per tile of THIS layout (validated by fill_args)
+        case 960: return launch_blocked_p<960, MODE, TRADES, HESS>(A, st);
+        case 896: return launch_blocked_p<896, MODE, TRADES, HESS>(A, st);
+        default: return launch_blocked_p<1024, MODE, TRADES, HESS>(A, st);
+    }
+}
 
 int fill_args(const cfmm_blocked_pairs* b, BlockedArgs& A) {
     if (!b) return CFMM_E_NULL;
-    if (b->pools_per_tile != cfg_P()) return CFMM_E_KIND;
+    if (!tile_pools_ok(b->pools_per_tile)) return CFMM_E_KIND;
     const int64_t P = b->pools_per_tile;
     if (b->n_tiles < 0 || b->n_pools < 0 || b->n_pools > b->n_tiles * P) return CFMM_E_SIZE;
     if (b->n_tiles > 0 && (!b->lid || !b->pos || !b->rows || !b->tok || !b->desc)) return CFMM_E_NULL;
@@ -603,7 +618,7 @@ extern "C" {
 
 int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int32_t* tok_stride, int32_t* row_cap,
                              int32_t* ent_stride) {
-    const int P = cfg_P();
+    const int P = g_tile_pools;
     const int rows = P + 2 * P / 8 + 8;
     if (pools_per_tile) *pools_per_tile = P;
     if (rows_stride) *rows_stride = rows;
@@ -614,6 +629,11 @@ int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int3
 }
 
 int cfmm_set_blocked_config(int32_t cfg) {
+    if (cfg >= 400) {                                           // 400 + P: pools per tile of layouts built from now on
+        if (!tile_pools_ok(cfg - 400)) return CFMM_E_KIND;
+        g_tile_pools = cfg - 400;
+        return CFMM_OK;
+    }
     if (cfg >= 300) { const int c = cfg - 300; if (c < 8 || c > 32) return CFMM_E_KIND; g_row_cap = c; return CFMM_OK; }
     if (cfg >= 200) { g_pdl = cfg - 200; return CFMM_OK; }      // 200 / 201: programmatic dependent launch off / on
     if (cfg != -1 && cfg != 0 && cfg != 3) return CFMM_E_KIND;

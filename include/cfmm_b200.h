@@ -119,7 +119,8 @@ int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int3
                              int32_t* ent_stride);
 /* tuning: -1 = default (evaluation: TMA-staged slabs; Hessian products / diagonal: register-fed variant),
  * 0 = TMA-staged for everything, 3 = register-fed for everything; 200/201 = programmatic dependent launch off/on;
- * 300+c = row cap c (8..32) for layouts built afterwards. */
+ * 300+c = row cap c (8..32) for layouts built afterwards; 400+P = pools per tile P (1024 default | 960 | 896) of
+ * layouts built afterwards (load balance: a launch's critical path is ceil(n_tiles / (2 SMs)) tiles). */
 int cfmm_set_blocked_config(int32_t cfg);
 
 /* Same contract as cfmm_arb_eval for a blocked constant-product bucket: psi/arb ACCUMULATE (one red.add per row

@@ -64,6 +64,26 @@ def test_blocked_product_eval_matches_oracle(m, n):
     assert any(getattr(b, "blocked", False) for b in st.buckets)
 
 
+@pytest.mark.xfail(strict=False, reason="alternative tile sizes (cfmm_set_blocked_config(400 + P)) were instantiated after this "
+                                        "round's GPU budget was spent: off by default, first run on hardware")
+@pytest.mark.parametrize("tile_pools", [960, 896])
+def test_blocked_kernels_with_smaller_tiles_match_oracle(tile_pools):
+    lib = _lib.load()
+    assert lib.cfmm_set_blocked_config(400 + tile_pools) == 0
+    try:
+        for m, n in ((20_000, 97), (70_000, 4096)):
+            hp, s = H.cp_host_pools(m, n, seed=m % 97)
+            st, ref = _check_eval(hp, H.random_prices(s["prices"], 1))
+            assert st.buckets[0].c_blocked.pools_per_tile == tile_pools
+            v = np.random.default_rng(2).standard_normal(n)
+            Hs = ref["hess_scaled"]
+            np.testing.assert_allclose(st.hvp(torch.as_tensor(v, **F64)).cpu().numpy(), Hs @ v,
+                                       atol=1e-10 * np.abs(Hs).max())
+            np.testing.assert_allclose(st.hess_diag().cpu().numpy(), np.diag(Hs), atol=1e-11 * np.abs(Hs).max())
+    finally:
+        lib.cfmm_set_blocked_config(400 + 1024)
+
+
 def test_blocked_layout_falls_back_when_tiles_touch_too_many_tokens():
     """every pool on its own pair of tokens: no tile can stay under the per-tile token cap -> plain bucket"""
     m = 3000

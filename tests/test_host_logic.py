@@ -156,10 +156,18 @@ def test_bounded_product_pools_get_their_own_bucket():
         cf.HostPools.from_lists(2, [[0, 1]], [[0.0, 1.0]], [0.99], ["bounded_product"], [[0.0, 1.0]]).validate()
 
 
-def test_blocked_layout_builder_tables_reproduce_the_scatter():
-    """build_blocked_pairs on CPU tensors: emulate the kernel's row sums and compare with index_add."""
+@pytest.mark.parametrize("tile_pools", [1024, 960, 896])
+def test_blocked_layout_builder_tables_reproduce_the_scatter(tile_pools):
+    """build_blocked_pairs on CPU tensors: emulate the kernel's row sums and compare with index_add; for every tile
+    size the kernels are instantiated for (cfmm_set_blocked_config(400 + P))."""
     lib = _lib.load()
-    P, rs, ts, cap, es = PL.blocked_layout_info(lib)
+    assert lib.cfmm_set_blocked_config(400 + 1000) == -2               # not an instantiated tile size
+    assert lib.cfmm_set_blocked_config(400 + tile_pools) == 0
+    try:
+        P, rs, ts, cap, es = PL.blocked_layout_info(lib)
+    finally:
+        lib.cfmm_set_blocked_config(400 + 1024)
+    assert P == tile_pools and rs == P + P // 4 + 8 and ts == P
     for m, n in ((5000, 300), (700, 3), (40_000, 2000)):
         s = I.synth_const_product(m, n, 0)
         idx = torch.as_tensor(s["idx"].T.astype(np.int64).copy())
