@@ -71,21 +71,29 @@ struct BlockedArgs {
     double* lambda;
     double* hcoef;                // eval, optional: [M]
     PeerLL peer;                  // optional fused all-reduce of `out` (world > 1): done by the last CTA to finish
+    int tile_pools;               // pools per tile of this layout; only the VAR instantiations read it (<= P, multiple of 4)
 };
 
 __device__ __forceinline__ unsigned round16(unsigned bytes) { return (bytes + 15u) & ~15u; }
 
-template <int P, int NF>
+// VAR: the layout's tiles hold A.tile_pools <= P pools (runtime, multiple of 4 so every copy stays a multiple of 16 B);
+// P is then only the capacity of the shared-memory stage.  Lets the builder cut the pool list into equal tiles, a whole
+// number per resident CTA (see cfmm_blocked_layout_info / pools.py: balanced_tile_pools).
+template <int P, bool VAR>
+__device__ __forceinline__ int tile_pools(const BlockedArgs& A) { return VAR ? A.tile_pools : P; }
+
+template <int P, int NF, bool VAR = false>
 __device__ __forceinline__ void issue_tile(Stage<P, NF>* st, uint64_t* bar, const BlockedArgs& A, long long tile,
                                            const int4 d) {
     const unsigned rows_b = round16(4u * (unsigned)d.y);
     const unsigned tok_b = round16(4u * (unsigned)d.x);
-    mbar_expect_tx(bar, (unsigned)(NF * P * 8 + P * 4 + P * 4 + 16) + rows_b + tok_b);
+    const int tp = tile_pools<P, VAR>(A);
+    mbar_expect_tx(bar, (unsigned)(NF * tp * 8 + tp * 4 + tp * 4 + 16) + rows_b + tok_b);
     bulk_g2s(&st->desc, A.desc + tile, 16, bar);
 #pragma unroll
-    for (int k = 0; k < NF; ++k) bulk_g2s(st->a[k], A.slab[k] + tile * P, P * 8, bar);
-    bulk_g2s(st->lid, A.lid + tile * P, P * 4, bar);
-    bulk_g2s(st->pos, A.pos + tile * P, P * 4, bar);
+    for (int k = 0; k < NF; ++k) bulk_g2s(st->a[k], A.slab[k] + tile * tp, tp * 8, bar);
+    bulk_g2s(st->lid, A.lid + tile * tp, tp * 4, bar);
+    bulk_g2s(st->pos, A.pos + tile * tp, tp * 4, bar);
     bulk_g2s(st->rows, A.rows + tile * BlockedCfg<P>::kRowsMax, rows_b, bar);
     bulk_g2s(st->tok, A.tok + tile * BlockedCfg<P>::kTokMax, tok_b, bar);
 }
@@ -174,10 +182,12 @@ __device__ __forceinline__ int row_start(uint32_t r) { return (int)(r & 0xffffu)
 __device__ __forceinline__ int row_len(uint32_t r) { return (int)((r >> 16) & 0x3fu); }
 __device__ __forceinline__ int row_tok(uint32_t r) { return (int)(r >> 22); }
 
-template <int P, int THREADS, int STAGES, int MODE /*0 eval, 1 hvp, 2 diag*/, bool TRADES, bool HESS, bool AR = false>
+template <int P, int THREADS, int STAGES, int MODE /*0 eval, 1 hvp, 2 diag*/, bool TRADES, bool HESS, bool AR = false,
+          bool VAR = false>
 __global__ void __launch_bounds__(THREADS)
 k_blocked(const BlockedArgs A) {
     constexpr int NF = (MODE == 0) ? 3 : 1;
+    const int tp = tile_pools<P, VAR>(A);
     using St = Stage<P, NF>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     St* stages = reinterpret_cast<St*>(smem_raw);
@@ -199,7 +209,7 @@ k_blocked(const BlockedArgs A) {
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             const long long t = t_beg + s;
-            if (t < t_end) issue_tile<P, NF>(&stages[s], &full[s], A, t, __ldg(A.desc + t));
+            if (t < t_end) issue_tile<P, NF, VAR>(&stages[s], &full[s], A, t, __ldg(A.desc + t));
         }
     }
     // Programmatic dependent launch: everything above touches only this launch's own shared memory and the
@@ -238,10 +248,15 @@ k_blocked(const BlockedArgs A) {
 #pragma unroll
             for (int u = 0; u < NPOOL; ++u) {
                 const int l = tid + u * THREADS;
+                if (VAR && l >= tp) {                   // lane beyond the tile: zero flows into the scratch slots past 2 tp
+                    f0[u] = f1[u] = 0.0;
+                    ps[u] = (uint32_t)(2 * tp) | ((uint32_t)(2 * tp + 1) << 16);
+                    continue;
+                }
                 const uint32_t li = S.lid[l];
                 ps[u] = S.pos[l];
                 if (MODE == 0) {
-                    EvalOp::apply<TRADES, HESS>(A, tile * P + l, S.a[0][l], S.a[1][l], S.a[2][l], nul[li & 0xffffu],
+                    EvalOp::apply<TRADES, HESS>(A, tile * tp + l, S.a[0][l], S.a[1][l], S.a[2][l], nul[li & 0xffffu],
                                                 nul[li >> 16], f0[u], f1[u], acc);
                 } else if (MODE == 1) {
                     f0[u] = S.a[0][l] * (nul[li & 0xffffu] - nul[li >> 16]);
@@ -302,7 +317,7 @@ k_blocked(const BlockedArgs A) {
         __syncthreads();                 // stage and f are free again; nu_local of the next tile is in place
         if (tid == 0 && far < t_end) {
             fence_proxy_async();
-            issue_tile<P, NF>(&S, &full[stage], A, far, dfar);
+            issue_tile<P, NF, VAR>(&S, &full[stage], A, far, dfar);
         }
         stage = nstage; parity = nparity;
     }
@@ -351,11 +366,19 @@ struct PoolRegs {
     uint32_t lid, pos;
 };
 
-template <int P, int THREADS, int NF, int NPOOL>
+template <int P, int THREADS, int NF, int NPOOL, bool VAR = false>
 __device__ __forceinline__ void load_pools(PoolRegs<NF> (&r)[NPOOL], const BlockedArgs& A, long long tile, int tid) {
+    const int tp = tile_pools<P, VAR>(A);
 #pragma unroll
     for (int u = 0; u < NPOOL; ++u) {
-        const long long q = tile * P + tid + u * THREADS;
+        if (VAR && tid + u * THREADS >= tp) {           // lane beyond the tile: inert entry, flows go to the scratch slots
+#pragma unroll
+            for (int k = 0; k < NF; ++k) r[u].a[k] = 0.0;
+            r[u].lid = 0u;
+            r[u].pos = (uint32_t)(2 * tp) | ((uint32_t)(2 * tp + 1) << 16);
+            continue;
+        }
+        const long long q = tile * tp + tid + u * THREADS;
 #pragma unroll
         for (int k = 0; k < NF; ++k) r[u].a[k] = __ldg(A.slab[k] + q);
         r[u].lid = __ldg(A.lid + q);
@@ -364,18 +387,20 @@ __device__ __forceinline__ void load_pools(PoolRegs<NF> (&r)[NPOOL], const Block
 }
 
 // pull the slabs of `tile` from HBM into L2 ahead of the register loads (one thread, 5 bulk prefetches)
-template <int P, int NF>
+template <int P, int NF, bool VAR = false>
 __device__ __forceinline__ void prefetch_pools_l2(const BlockedArgs& A, long long tile) {
+    const int tp = tile_pools<P, VAR>(A);
 #pragma unroll
-    for (int k = 0; k < NF; ++k) bulk_prefetch_l2(A.slab[k] + tile * P, P * 8);
-    bulk_prefetch_l2(A.lid + tile * P, P * 4);
-    bulk_prefetch_l2(A.pos + tile * P, P * 4);
+    for (int k = 0; k < NF; ++k) bulk_prefetch_l2(A.slab[k] + tile * tp, tp * 8);
+    bulk_prefetch_l2(A.lid + tile * tp, tp * 4);
+    bulk_prefetch_l2(A.pos + tile * tp, tp * 4);
 }
 
-template <int P, int THREADS, int STAGES, int MODE, bool TRADES, bool HESS, bool AR = false>
+template <int P, int THREADS, int STAGES, int MODE, bool TRADES, bool HESS, bool AR = false, bool VAR = false>
 __global__ void __launch_bounds__(THREADS, 2)
 k_blocked_regs(const BlockedArgs A) {
     constexpr int NF = (MODE == 0) ? 3 : 1;
+    const int tp = tile_pools<P, VAR>(A);
     constexpr int NPOOL = P / THREADS;
     constexpr int NPRE = (P + THREADS - 1) / THREADS;
     using St = TabStage<P>;
@@ -398,11 +423,11 @@ k_blocked_regs(const BlockedArgs A) {
             const long long t = t_beg + s;
             if (t < t_end) issue_tables<P>(&stages[s], &full[s], A, t, __ldg(A.desc + t));
         }
-        if (t_beg + 1 < t_end) prefetch_pools_l2<P, NF>(A, t_beg + 1);
-        if (t_beg + 2 < t_end) prefetch_pools_l2<P, NF>(A, t_beg + 2);
+        if (t_beg + 1 < t_end) prefetch_pools_l2<P, NF, VAR>(A, t_beg + 1);
+        if (t_beg + 2 < t_end) prefetch_pools_l2<P, NF, VAR>(A, t_beg + 2);
     }
     PoolRegs<NF> cur[NPOOL], nxt[NPOOL];
-    if (t_beg < t_end) load_pools<P, THREADS, NF, NPOOL>(cur, A, t_beg, tid);      // constant tables: before the PDL wait
+    if (t_beg < t_end) load_pools<P, THREADS, NF, NPOOL, VAR>(cur, A, t_beg, tid);      // constant tables: before the PDL wait
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     for (int j = blockIdx.x * THREADS + tid; j < A.n_zero; j += gridDim.x * THREADS) A.zero_next[j] = 0.0;
@@ -428,9 +453,9 @@ k_blocked_regs(const BlockedArgs A) {
         // 1. pool slabs of the next tile -> registers; nu_local of the next tile -> registers (both land while we compute)
         double pre[NPRE];
         int ntok_n = 0;
-        if (tid == 0 && tile + 3 < t_end) prefetch_pools_l2<P, NF>(A, tile + 3);      // HBM -> L2, 3 tiles ahead
+        if (tid == 0 && tile + 3 < t_end) prefetch_pools_l2<P, NF, VAR>(A, tile + 3);      // HBM -> L2, 3 tiles ahead
         if (nx < t_end) {
-            load_pools<P, THREADS, NF, NPOOL>(nxt, A, nx, tid);
+            load_pools<P, THREADS, NF, NPOOL, VAR>(nxt, A, nx, tid);
             mbar_wait(&full[nstage], nparity);
             if (MODE != 2) {
                 ntok_n = stages[nstage].desc.x;
@@ -447,8 +472,10 @@ k_blocked_regs(const BlockedArgs A) {
 #pragma unroll
             for (int u = 0; u < NPOOL; ++u) {
                 const uint32_t li = cur[u].lid;
-                if (MODE == 0) {
-                    EvalOp::apply<TRADES, HESS>(A, tile * P + tid + u * THREADS, cur[u].a[0], cur[u].a[NF > 1 ? 1 : 0],
+                if (VAR && MODE == 0 && tid + u * THREADS >= tp) {       // inert lane: no pool behind it
+                    f0[u] = f1[u] = 0.0;
+                } else if (MODE == 0) {
+                    EvalOp::apply<TRADES, HESS>(A, tile * tp + tid + u * THREADS, cur[u].a[0], cur[u].a[NF > 1 ? 1 : 0],
                                                 cur[u].a[NF > 2 ? 2 : 0], nul[li & 0xffffu], nul[li >> 16], f0[u], f1[u],
                                                 acc);
                 } else if (MODE == 1) {
@@ -526,11 +553,12 @@ int g_cfg = -1;
 int g_pdl = 1;
 int g_row_cap = 32;
 
-template <class C, int MODE, bool TRADES, bool HESS>
+template <class C, int MODE, bool TRADES, bool HESS, bool VAR = false>
 int launch_cfg(const BlockedArgs& A, cudaStream_t st) {
     constexpr int NF = (MODE == 0) ? 3 : 1;
     const bool ar = A.peer.world > 1;
-    auto kern = ar ? k_blocked<C::P, C::T, C::S, MODE, TRADES, HESS, true> : k_blocked<C::P, C::T, C::S, MODE, TRADES, HESS, false>;
+    auto kern = ar ? k_blocked<C::P, C::T, C::S, MODE, TRADES, HESS, true, VAR>
+                   : k_blocked<C::P, C::T, C::S, MODE, TRADES, HESS, false, VAR>;
     const size_t sm = (size_t)C::S * sizeof(Stage<C::P, NF>) + (size_t)(3 * C::P) * sizeof(double);
     static bool attr[2] = {false, false};
     if (!attr[ar]) {
@@ -553,11 +581,12 @@ int launch_cfg(const BlockedArgs& A, cudaStream_t st) {
     return check_launch();
 }
 
-template <int P, int MODE, bool TRADES, bool HESS>
+template <int P, int MODE, bool TRADES, bool HESS, bool VAR = false>
 int launch_regs(const BlockedArgs& A, cudaStream_t st) {
     constexpr int T = P / 2, S = 4;
     const bool ar = A.peer.world > 1;
-    auto kern = ar ? k_blocked_regs<P, T, S, MODE, TRADES, HESS, true> : k_blocked_regs<P, T, S, MODE, TRADES, HESS, false>;
+    auto kern = ar ? k_blocked_regs<P, T, S, MODE, TRADES, HESS, true, VAR>
+                   : k_blocked_regs<P, T, S, MODE, TRADES, HESS, false, VAR>;
     const size_t sm = (size_t)S * sizeof(TabStage<P>) + (size_t)(2 * P + 4 * P) * sizeof(double);
     static bool attr[2] = {false, false};
     if (!attr[ar]) {
@@ -576,22 +605,25 @@ int launch_regs(const BlockedArgs& A, cudaStream_t st) {
     return check_launch();
 }
 
-template <int P, int MODE, bool TRADES, bool HESS>
+template <int P, int MODE, bool TRADES, bool HESS, bool VAR = false>
 int launch_blocked_p(const BlockedArgs& A, cudaStream_t st) {
     // default (-1): evaluation through the TMA-staged slabs, Hessian products / diagonal (1 slab, less data per tile)
     // through the register-fed single-barrier variant -- each is the faster one for its mode (profiles/r1f_*)
-    if (g_cfg == 3 || (g_cfg < 0 && MODE != 0)) return launch_regs<P, MODE, TRADES, HESS>(A, st);
-    return launch_cfg<CfgP<P>, MODE, TRADES, HESS>(A, st);
+    if (g_cfg == 3 || (g_cfg < 0 && MODE != 0)) return launch_regs<P, MODE, TRADES, HESS, VAR>(A, st);
+    return launch_cfg<CfgP<P>, MODE, TRADES, HESS, VAR>(A, st);
 }
 
-bool tile_pools_ok(long long P) { return P == 1024 || P == 960 || P == 896; }
+// compile-time tile sizes, or any multiple of 4 in [256, 1024] through the runtime-sized (VAR) instantiations of P = 1024
+bool tile_pools_fixed(long long P) { return P == 1024 || P == 960 || P == 896; }
+bool tile_pools_ok(long long P) { return tile_pools_fixed(P) || (P >= 256 && P < 1024 && P % 4 == 0); }
 
 template <int MODE, bool TRADES, bool HESS>
 int launch_blocked(const BlockedArgs& A, cudaStream_t st) {
-    switch (A.n_tiles ? A.M / A.n_tiles : 1024) {          // pools per tile of THIS layout (validated by fill_args)
+    switch (A.tile_pools) {                                 // pools per tile of THIS layout (validated by fill_args)
+        case 1024: return launch_blocked_p<1024, MODE, TRADES, HESS>(A, st);
         case 960: return launch_blocked_p<960, MODE, TRADES, HESS>(A, st);
         case 896: return launch_blocked_p<896, MODE, TRADES, HESS>(A, st);
-        default: return launch_blocked_p<1024, MODE, TRADES, HESS>(A, st);
+        default: return launch_blocked_p<1024, MODE, TRADES, HESS, true>(A, st);
     }
 }
 
@@ -602,6 +634,7 @@ int fill_args(const cfmm_blocked_pairs* b, BlockedArgs& A) {
     if (b->n_tiles < 0 || b->n_pools < 0 || b->n_pools > b->n_tiles * P) return CFMM_E_SIZE;
     if (b->n_tiles > 0 && (!b->lid || !b->pos || !b->rows || !b->tok || !b->desc)) return CFMM_E_NULL;
     A.n_tiles = b->n_tiles;
+    A.tile_pools = (int)P;
     A.M = b->n_tiles * P;
     A.lid = b->lid; A.pos = b->pos; A.rows = b->rows; A.tok = b->tok;
     A.desc = reinterpret_cast<const int4*>(b->desc);
@@ -618,11 +651,14 @@ extern "C" {
 
 int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int32_t* tok_stride, int32_t* row_cap,
                              int32_t* ent_stride) {
+    // 0 = "balanced": the builder picks the tile size per bucket (any multiple of 4 in [256, 1024]; runtime-sized
+    // kernels, whose row / token tables have the strides of the 1024 layout)
     const int P = g_tile_pools;
-    const int rows = P + 2 * P / 8 + 8;
+    const int cap = P ? P : 1024;
+    const int rows = cap + 2 * cap / 8 + 8;
     if (pools_per_tile) *pools_per_tile = P;
     if (rows_stride) *rows_stride = rows;
-    if (tok_stride) *tok_stride = P;
+    if (tok_stride) *tok_stride = cap;
     if (row_cap) *row_cap = g_row_cap;
     if (ent_stride) *ent_stride = 0;          /* unused since the row-ordered scatter (kept for ABI stability) */
     return CFMM_OK;
@@ -630,7 +666,8 @@ int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int3
 
 int cfmm_set_blocked_config(int32_t cfg) {
     if (cfg >= 400) {                                           // 400 + P: pools per tile of layouts built from now on
-        if (!tile_pools_ok(cfg - 400)) return CFMM_E_KIND;
+        if (cfg == 400) { g_tile_pools = 0; return CFMM_OK; }   // 400: balanced (the builder picks per bucket)
+        if (!tile_pools_fixed(cfg - 400)) return CFMM_E_KIND;
         g_tile_pools = cfg - 400;
         return CFMM_OK;
     }

@@ -276,6 +276,19 @@ def blocked_layout_info(lib):
     return tuple(int(x.value) for x in v)      # pools_per_tile, rows_stride, tok_stride, row_cap, ent_stride
 
 
+def balanced_tile_pools(m: int, n_ctas: int, cap: int = 1024, lo: int = 256) -> int:
+    """Tile size for the runtime-sized blocked kernels: the kernels walk ceil(n_tiles / n_ctas) tiles on their critical
+    path, so cut the m pools into n_ctas * k equal tiles (k = tiles per CTA at the capacity `cap`) instead of tiles of
+    `cap` pools with a ragged last round.  1M pools on 296 CTAs: 1180 tiles of 848 (4 per CTA) instead of 977 of 1024
+    (3 or 4 per CTA).  Multiple of 4 so every bulk copy stays a multiple of 16 bytes."""
+    if m <= 0:
+        return cap
+    k = -(-m // (n_ctas * cap))
+    t = -(-m // (n_ctas * k))
+    t = -(-t // 4) * 4
+    return int(min(cap, max(lo, t)))
+
+
 def build_blocked_pairs(idx: torch.Tensor, n_tokens: int, P: int, rows_stride: int, tok_stride: int, row_cap: int,
                         ent_stride: int):
     """Layout builder for cfmm_blocked_pairs (see csrc/cfmm_blocked.cu).  idx: (2, m) int64 token ids on the
@@ -379,6 +392,8 @@ class BlockedBucket:
     def __init__(self, hp: HostPools, spec, device, lib):
         self.spec = spec
         P, rows_stride, tok_stride, row_cap, ent_stride = blocked_layout_info(lib)
+        if P == 0:                              # "balanced" (cfmm_set_blocked_config(400)): equal tiles, a whole number per CTA
+            P = balanced_tile_pools(spec.m, 2 * torch.cuda.get_device_properties(device).multi_processor_count)
         f64 = dict(dtype=torch.float64, device=device)
         if spec.identity:                       # raw arrays go up as they are; all reordering happens on the GPU
             R = torch.from_numpy(hp.reserves).to(device, non_blocking=True).view(-1, 2)

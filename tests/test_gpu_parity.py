@@ -64,9 +64,9 @@ def test_blocked_product_eval_matches_oracle(m, n):
     assert any(getattr(b, "blocked", False) for b in st.buckets)
 
 
-@pytest.mark.xfail(strict=False, reason="alternative tile sizes (cfmm_set_blocked_config(400 + P)) were instantiated after this "
+@pytest.mark.xfail(strict=False, reason="alternative / runtime tile sizes (cfmm_set_blocked_config(400 + P | 400)) were added after this "
                                         "round's GPU budget was spent: off by default, first run on hardware")
-@pytest.mark.parametrize("tile_pools", [960, 896])
+@pytest.mark.parametrize("tile_pools", [960, 896, 0])
 def test_blocked_kernels_with_smaller_tiles_match_oracle(tile_pools):
     lib = _lib.load()
     assert lib.cfmm_set_blocked_config(400 + tile_pools) == 0
@@ -74,7 +74,8 @@ def test_blocked_kernels_with_smaller_tiles_match_oracle(tile_pools):
         for m, n in ((20_000, 97), (70_000, 4096)):
             hp, s = H.cp_host_pools(m, n, seed=m % 97)
             st, ref = _check_eval(hp, H.random_prices(s["prices"], 1))
-            assert st.buckets[0].c_blocked.pools_per_tile == tile_pools
+            got = st.buckets[0].c_blocked.pools_per_tile       # 0 = balanced: the builder's choice, runtime-sized kernels
+            assert got == tile_pools or (tile_pools == 0 and got % 4 == 0 and 256 <= got < 1024)
             v = np.random.default_rng(2).standard_normal(n)
             Hs = ref["hess_scaled"]
             np.testing.assert_allclose(st.hvp(torch.as_tensor(v, **F64)).cpu().numpy(), Hs @ v,

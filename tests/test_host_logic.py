@@ -156,10 +156,21 @@ def test_bounded_product_pools_get_their_own_bucket():
         cf.HostPools.from_lists(2, [[0, 1]], [[0.0, 1.0]], [0.99], ["bounded_product"], [[0.0, 1.0]]).validate()
 
 
-@pytest.mark.parametrize("tile_pools", [1024, 960, 896])
+def test_balanced_tile_size_rule():
+    """equal tiles, a whole number per resident CTA (the blocked kernels' critical path is ceil(n_tiles / n_ctas) tiles)"""
+    t = PL.balanced_tile_pools(1_000_000, 296)
+    assert t == 848 and -(-1_000_000 // t) <= 4 * 296               # cfg5: 1180 tiles, 4 per CTA (1024: 977 -> 3 or 4)
+    for m in (1, 255, 10_000, 303_104, 303_105, 2_000_000, 10 ** 9):
+        t = PL.balanced_tile_pools(m, 296)
+        assert t % 4 == 0 and 256 <= t <= 1024
+        k = -(-m // (296 * 1024))
+        assert -(-m // t) <= 296 * k or t == 256                      # never more rounds than tiles of 1024 would need
+
+
+@pytest.mark.parametrize("tile_pools", [1024, 960, 896, 0])
 def test_blocked_layout_builder_tables_reproduce_the_scatter(tile_pools):
     """build_blocked_pairs on CPU tensors: emulate the kernel's row sums and compare with index_add; for every tile
-    size the kernels are instantiated for (cfmm_set_blocked_config(400 + P))."""
+    size the kernels are instantiated for (cfmm_set_blocked_config(400 + P)) and for the runtime-sized ones (400)."""
     lib = _lib.load()
     assert lib.cfmm_set_blocked_config(400 + 1000) == -2               # not an instantiated tile size
     assert lib.cfmm_set_blocked_config(400 + tile_pools) == 0
@@ -167,7 +178,11 @@ def test_blocked_layout_builder_tables_reproduce_the_scatter(tile_pools):
         P, rs, ts, cap, es = PL.blocked_layout_info(lib)
     finally:
         lib.cfmm_set_blocked_config(400 + 1024)
-    assert P == tile_pools and rs == P + P // 4 + 8 and ts == P
+    if tile_pools == 0:                                                 # balanced: tables keep the strides of 1024
+        assert P == 0 and rs == 1024 + 256 + 8 and ts == 1024
+        P = 848
+    else:
+        assert P == tile_pools and rs == P + P // 4 + 8 and ts == P
     for m, n in ((5000, 300), (700, 3), (40_000, 2000)):
         s = I.synth_const_product(m, n, 0)
         idx = torch.as_tensor(s["idx"].T.astype(np.int64).copy())
