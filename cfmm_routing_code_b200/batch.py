@@ -91,7 +91,7 @@ def solve_batch_device(store: CsrStore, c: torch.Tensor, a: torch.Tensor, flags:
                        nu.data_ptr(), psi.data_ptr(), stats.data_ptr(),
                        delta.data_ptr() if want_trades else None, lam.data_ptr() if want_trades else None,
                        store.nnz if shared else 0)
-    prm = _lib.BatchParams(float(tol), 0.1, 1e-4, 0.25, 1e-12, int(max_outer), int(max_inner))
+    prm = _lib.BatchParams(float(tol), 0.1, 1e-4, 0.5, 1e-12, int(max_outer), int(max_inner))
     st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(store.lib.cfmm_batch_solve(C.byref(store.c_pools), C.byref(batch), C.byref(prm), work.data_ptr(), st),
                "cfmm_batch_solve")

@@ -388,7 +388,7 @@ CFMM_HD inline Stats solve_one(const Pools& P, Problem Q, const Params& prm, dou
             double alpha = 1.0;
             bool ok = false;
             const int nxt = cur ^ 1;
-            double g_t = g;
+            double g_t = g, lin1 = 0.0;                                    // lin1: predicted decrease of the FULL step
             for (int ls = 0; ls < 50; ++ls) {
                 double lin = 0.0;
                 for (int j = 0; j < n; ++j) {
@@ -399,8 +399,9 @@ CFMM_HD inline Stats solve_one(const Pools& P, Problem Q, const Params& prm, dou
                 }
                 g_t = dual_value(Q, nuv[nxt], evaluate<LANES>(P, Q, nuv[nxt], lognu, eps_t, psiv[nxt], &Hsv[nxt], false, false, lane));
                 ++evals;
+                if (ls == 0) lin1 = lin;
                 if (g_t <= g + 1e-4 * lin) { ok = true; break; }
-                if (fabs(g_t - g) <= 1e-13 * fabs(g) || fabs(lin) <= 1e-9 * fabs(g)) {   // g cannot resolve this step
+                if (fabs(g_t - g) <= 1e-13 * fabs(g) || fabs(lin1) <= 1e-9 * fabs(g)) {  // g cannot resolve this step
                     if (kkt(Q, nuv[nxt], psiv[nxt], lb, g_t, err, grad_t, pg_t, &fm_t) < 0.99 * err) { ok = true; break; }
                     if (alpha < 1e-3) break;
                 }

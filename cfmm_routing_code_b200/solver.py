@@ -86,7 +86,7 @@ def default_nu0(spec: DualSpec) -> np.ndarray:
 
 
 def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 0.1, eps_min: float = 1e-4,
-               eps_shrink: float = 0.25, max_outer: int = 60, max_inner: int = 100, linear_solver: str = "auto", cg_max: int = 200, comm: Optional[Comm] = None,
+               eps_shrink: float = 0.5, max_outer: int = 60, max_inner: int = 100, linear_solver: str = "auto", cg_max: int = 200, comm: Optional[Comm] = None,
                verbose: bool = False, final_trades: bool = True, lookahead: Optional[int] = None) -> SolveInfo:
     t_start = time.perf_counter()
     comm = comm or Comm()
@@ -215,13 +215,15 @@ def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 0.1
                 nu_t = torch.where(fixed, c, nu_t)
                 psi_t, g_t = G(nu_t)
                 lin = float(torch.dot(grad, nu_t - nu))
+                if _ls == 0:
+                    lin1 = lin             # predicted decrease of the FULL step
                 gt = float(g_t)
                 if gt <= g0 + 1e-4 * lin:
                     ok = True
                     break
-                if abs(gt - g0) <= 1e-13 * abs(g0) or abs(lin) <= 1e-9 * abs(g0):
-                    # the step is below what g resolves in fp64 (g is a sum of cancelling flows: the Armijo decrease
-                    # 1e-4 |lin| would be under 1e-13 |g|): judge it by the KKT residual instead
+                if abs(gt - g0) <= 1e-13 * abs(g0) or abs(lin1) <= 1e-9 * abs(g0):
+                    # the (full) step is below what g resolves in fp64 (g is a sum of cancelling flows: the Armijo
+                    # decrease 1e-4 |lin| would be under 1e-13 |g|): judge it by the KKT residual instead
                     if kkt(nu_t, psi_t, g_t, err)[0] < 0.99 * err:
                         ok = True
                         break

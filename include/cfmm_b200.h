@@ -221,7 +221,7 @@ typedef struct cfmm_batch {
 
 typedef struct cfmm_batch_params {
     double tol;                /* KKT residual and relative duality gap                              */
-    double eps0, eps_min, eps_shrink; /* constant-sum ramp continuation (0.1, 1e-4, 0.25)              */
+    double eps0, eps_min, eps_shrink; /* constant-sum ramp continuation (0.1, 1e-4, 0.5)               */
     double floor_rel;          /* lower bound of free prices relative to max |c| (1e-12)             */
     int32_t max_outer, max_inner;
 } cfmm_batch_params;

@@ -397,7 +397,7 @@ def residuals(util: Utility, nu, psi, dual):
     return primal, infeas
 
 
-def solve(pools: Pools, util: Utility, nu0=None, tol=1e-9, eps=0.1, eps_min=1e-4, eps_shrink=0.25,
+def solve(pools: Pools, util: Utility, nu0=None, tol=1e-9, eps=0.1, eps_min=1e-4, eps_shrink=0.5,
           max_outer=60, max_inner=100, verbose=False) -> Result:
     """Method of multipliers on the constant-sum fills (outer, ramp width eps shrinking geometrically)
     around a projected (active-set) Newton method in log-price coordinates on the smooth dual g_t(nu)
@@ -474,10 +474,12 @@ def solve(pools: Pools, util: Utility, nu0=None, tol=1e-9, eps=0.1, eps_min=1e-4
                 nu_t[fixed] = util.c[fixed]
                 ev_t = G(nu_t, want_hess=True)
                 lin = np.dot(grad, nu_t - nu)
+                if _ls == 0:
+                    lin1 = lin                 # predicted decrease of the FULL step
                 if ev_t["g"] <= g0 + 1e-4 * lin:
                     ok = True
                     break
-                if abs(ev_t["g"] - g0) <= 1e-13 * abs(g0) or abs(lin) <= 1e-9 * abs(g0):   # g cannot resolve this step
+                if abs(ev_t["g"] - g0) <= 1e-13 * abs(g0) or abs(lin1) <= 1e-9 * abs(g0):   # g cannot resolve this step
                     if kkt(nu_t, ev_t, err)[0] < 0.99 * err:
                         ok = True
                         break

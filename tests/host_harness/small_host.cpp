@@ -13,7 +13,7 @@ extern "C" int small_host_solve(int n_tokens, long long n_pools, const long long
                                 double* delta, double* lam, long long trade_stride, double tol, int interleave) {
     using namespace cfmm_small;
     Pools P{(const int64_t*)pool_ptr, tok, R, w, logrw, gamma, kind};
-    Params prm{tol, 0.1, 1e-4, 0.25, 1e-12, 60, 100};
+    Params prm{tol, 0.1, 1e-4, 0.5, 1e-12, 60, 100};
     if (const char* e = getenv("SMALL_HOST_EPS")) sscanf(e, "%lf,%lf,%lf", &prm.eps0, &prm.eps_min, &prm.eps_shrink);   // experiments
     const int64_t nnz = pool_ptr[n_pools];
     const int64_t stride = interleave ? ((n_problems + 31) / 32) * 32 : 1;    // exercise the strided workspace too
