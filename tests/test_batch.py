@@ -224,6 +224,53 @@ def test_host_build_infeasible_liquidation_is_not_reported_optimal():
     assert int(out["stats"][0][7]) != 0 and not abs(out["stats"][0][2]) <= 1e-6
 
 
+class _HostStore:
+    """stand-in for batch.CsrStore in the plumbing test below: keeps the HostPools, owns no device memory"""
+    def __init__(self, hp, device="cuda"):
+        import torch
+        self.hp, self.device = hp, torch.device("cpu")
+        self.n_tokens, self.m, self.nnz = hp.n_tokens, hp.m, int(len(hp.tok_idx))
+
+
+def _host_solve_batch_device(store, c, a, flags, nu, tol=1e-8, want_trades=True, pool_range=None, max_outer=60,
+                             max_inner=100, nnz_max=0, lanes=None):
+    import torch
+    out = small_host.solve_raw(store.hp, c.numpy(), a.numpy(), flags.numpy(), nu.numpy(),
+                               None if pool_range is None else pool_range.numpy(), tol=tol)
+    nu.copy_(torch.as_tensor(out["nu"]))
+    t = torch.as_tensor
+    return t(out["psi"]), t(out["stats"]), (t(out["delta"]) if want_trades else None), (t(out["lam"]) if want_trades else None)
+
+
+def test_python_plumbing_of_batch_entry_points_with_the_host_build(monkeypatch, golden):
+    """solve(method='thread'), solve_sweep(batched), solve_batch and solve_many: packing, routing and unpacking of the
+    results, with the kernel launch replaced by the host build of the same solver (no GPU here)"""
+    from cfmm_routing_code_b200 import batch as B
+    monkeypatch.setattr(B, "CsrStore", _HostStore)
+    monkeypatch.setattr(B, "solve_batch_device", _host_solve_batch_device)
+    d = I.arbitrage_instance()
+    r = cf.solve(d["local_indices"], d["reserves"], d["fees"], d["kinds"], d["weights"],
+                 utility=cf.Arbitrage(d["market_value"]), tol=1e-9, method="thread")
+    assert r.status == "optimal" and abs(r.value - golden["survey_8c"]["arbitrage"]) <= 1e-8 * 21.5
+    assert len(r.deltas) == 5 and r.deltas[0].shape == (4,) and r.info is None
+    np.testing.assert_allclose(r.lambdas[4], golden["arbitrage"]["lambdas"][4], atol=5e-5)
+    d = I.two_asset_instance()
+    rs = cf.solve_sweep(d["local_indices"], d["reserves"], d["fees"], d["kinds"], d["weights"],
+                        [cf.Swap(d["tok_in"], d["tok_out"], t) for t in d["amounts"]], tol=1e-9)
+    assert len(rs) == 50 and all(x.status == "optimal" for x in rs)
+    for j, x in enumerate(rs):
+        assert abs(x.value - golden["two_asset"][j]["value"]) <= 1e-6 * max(1.0, golden["two_asset"][j]["value"])
+    probs = _many_problems()
+    out = cf.solve_many(probs, tol=1e-9)
+    for (hp, u), x in zip(probs, out):
+        ro = _oracle_for(hp, u)
+        assert x.status == "optimal" and x.psi.shape == (hp.n_tokens,) and len(x.lambdas) == hp.m
+        assert abs(x.value - ro.value) <= 1e-8 * max(abs(ro.dual_value), 1e-300)
+        for i in range(hp.m):
+            np.testing.assert_allclose(x.lambdas[i], ro.lambdas[i], atol=1e-5 * max(1.0, np.abs(ro.psi).max()))
+    assert cf.solve_batch(probs[0][0], []) == [] and cf.solve_many([]) == []
+
+
 # ------------------------------------------------------------------------------------------------- GPU (the product)
 def _to_api(u):
     class _U:
