@@ -150,6 +150,12 @@ def test_bounded_product_pools_get_their_own_bucket():
     b = by_kind[(_lib.KIND_BOUNDED, 2)]
     assert b.sel.tolist() == [0, 1, 2] and np.array_equal(hp.weights[b.off], np.array(d["weights"][:3]).T)
     assert hp.reserves[hp.pool_ptr[1] + 1] == 0.0            # the out-of-range position holds token 0 only
+    db = PL.DeviceBucket(hp, b, "cpu")                        # slot-major SoA the kernel reads (tensors only, no launch)
+    assert db.kind == _lib.KIND_BOUNDED and db.stride == 1024 and db.theta_bar is None and db.logrw is None
+    np.testing.assert_array_equal(db.weights[:, :3].numpy(), np.array(d["weights"][:3]).T)      # offsets ride in weights
+    np.testing.assert_array_equal(db.reserves[:, :3].numpy(), np.array(d["reserves"][:3]).T)
+    np.testing.assert_array_equal(db.tok_idx[:, :3].numpy(), np.array(d["local_indices"][:3]).T)
+    assert db.c_bucket.kind == 3 and db.c_bucket.arity == 2 and db.c_bucket.n_pools == 3 and db.c_bucket.weights
     with pytest.raises(ValueError):
         cf.HostPools.from_lists(3, [[0, 1, 2]], [[1, 1, 1]], [0.99], ["bounded_product"], [[1, 1, 1]])
     with pytest.raises(ValueError):
