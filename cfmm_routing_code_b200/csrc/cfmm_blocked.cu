@@ -71,29 +71,33 @@ struct BlockedArgs {
     double* lambda;
     double* hcoef;                // eval, optional: [M]
     PeerLL peer;                  // optional fused all-reduce of `out` (world > 1): done by the last CTA to finish
-    int tile_pools;               // pools per tile of this layout; only the VAR instantiations read it (<= P, multiple of 4)
+    int tile_pools;               // pools per tile of this layout (host-side dispatch only); 0 = per-tile sizes in desc (VAR)
 };
 
 __device__ __forceinline__ unsigned round16(unsigned bytes) { return (bytes + 15u) & ~15u; }
 
-// VAR: the layout's tiles hold A.tile_pools <= P pools (runtime, multiple of 4 so every copy stays a multiple of 16 B);
-// P is then only the capacity of the shared-memory stage.  Lets the builder cut the pool list into equal tiles, a whole
-// number per resident CTA (see cfmm_blocked_layout_info / pools.py: balanced_tile_pools).
+// VAR: tiles of ANY size <= P.  The descriptor of a tile then carries (ntok, nrow, pools in the tile, offset of its first pool
+// in the slab arrays); offsets are multiples of 4 pools so every bulk copy stays 16-byte aligned, and P is only the capacity
+// of the shared-memory stage.  Lets the builder cut the pool list into a whole number of tiles per resident CTA, with a small
+// first tile so a CTA's compute starts before the bulk of its data has landed (pools.py: plan_tiles).
 template <int P, bool VAR>
-__device__ __forceinline__ int tile_pools(const BlockedArgs& A) { return VAR ? A.tile_pools : P; }
+__device__ __forceinline__ int tile_count(const int4 d) { return VAR ? d.z : P; }
+template <int P, bool VAR>
+__device__ __forceinline__ long long tile_offset(const int4 d, long long tile) { return VAR ? (long long)d.w : tile * P; }
 
 template <int P, int NF, bool VAR = false>
 __device__ __forceinline__ void issue_tile(Stage<P, NF>* st, uint64_t* bar, const BlockedArgs& A, long long tile,
                                            const int4 d) {
     const unsigned rows_b = round16(4u * (unsigned)d.y);
     const unsigned tok_b = round16(4u * (unsigned)d.x);
-    const int tp = tile_pools<P, VAR>(A);
+    const int tp = VAR ? ((d.z + 3) & ~3) : P;                 // pools copied (the slabs are padded to a multiple of 4)
+    const long long off = tile_offset<P, VAR>(d, tile);
     mbar_expect_tx(bar, (unsigned)(NF * tp * 8 + tp * 4 + tp * 4 + 16) + rows_b + tok_b);
     bulk_g2s(&st->desc, A.desc + tile, 16, bar);
 #pragma unroll
-    for (int k = 0; k < NF; ++k) bulk_g2s(st->a[k], A.slab[k] + tile * tp, tp * 8, bar);
-    bulk_g2s(st->lid, A.lid + tile * tp, tp * 4, bar);
-    bulk_g2s(st->pos, A.pos + tile * tp, tp * 4, bar);
+    for (int k = 0; k < NF; ++k) bulk_g2s(st->a[k], A.slab[k] + off, tp * 8, bar);
+    bulk_g2s(st->lid, A.lid + off, tp * 4, bar);
+    bulk_g2s(st->pos, A.pos + off, tp * 4, bar);
     bulk_g2s(st->rows, A.rows + tile * BlockedCfg<P>::kRowsMax, rows_b, bar);
     bulk_g2s(st->tok, A.tok + tile * BlockedCfg<P>::kTokMax, tok_b, bar);
 }
@@ -187,7 +191,6 @@ template <int P, int THREADS, int STAGES, int MODE /*0 eval, 1 hvp, 2 diag*/, bo
 __global__ void __launch_bounds__(THREADS)
 k_blocked(const BlockedArgs A) {
     constexpr int NF = (MODE == 0) ? 3 : 1;
-    const int tp = tile_pools<P, VAR>(A);
     using St = Stage<P, NF>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     St* stages = reinterpret_cast<St*>(smem_raw);
@@ -234,7 +237,9 @@ k_blocked(const BlockedArgs A) {
     __syncthreads();
     for (long long tile = t_beg; tile < t_end; ++tile) {
         St& S = stages[stage];                          // full (waited for when its nu_local was fetched)
-        const int4 d = S.desc;                          // (ntok, nrow, groups, -)
+        const int4 d = S.desc;                          // (ntok, nrow, pools, first pool) -- the last two only read by VAR
+        const int tp = tile_count<P, VAR>(d);
+        const long long toff = tile_offset<P, VAR>(d, tile);
         // the producer thread fetches the descriptor of the tile it will issue at the end of this iteration
         const long long far = tile + STAGES;
         int4 dfar = make_int4(0, 0, 0, 0);
@@ -256,7 +261,7 @@ k_blocked(const BlockedArgs A) {
                 const uint32_t li = S.lid[l];
                 ps[u] = S.pos[l];
                 if (MODE == 0) {
-                    EvalOp::apply<TRADES, HESS>(A, tile * tp + l, S.a[0][l], S.a[1][l], S.a[2][l], nul[li & 0xffffu],
+                    EvalOp::apply<TRADES, HESS>(A, toff + l, S.a[0][l], S.a[1][l], S.a[2][l], nul[li & 0xffffu],
                                                 nul[li >> 16], f0[u], f1[u], acc);
                 } else if (MODE == 1) {
                     f0[u] = S.a[0][l] * (nul[li & 0xffffu] - nul[li >> 16]);
@@ -368,7 +373,10 @@ struct PoolRegs {
 
 template <int P, int THREADS, int NF, int NPOOL, bool VAR = false>
 __device__ __forceinline__ void load_pools(PoolRegs<NF> (&r)[NPOOL], const BlockedArgs& A, long long tile, int tid) {
-    const int tp = tile_pools<P, VAR>(A);
+    int4 d = make_int4(0, 0, 0, 0);
+    if (VAR) d = __ldg(A.desc + tile);                  // the ring stage of this tile may not have landed yet: read it directly
+    const int tp = tile_count<P, VAR>(d);
+    const long long toff = tile_offset<P, VAR>(d, tile);
 #pragma unroll
     for (int u = 0; u < NPOOL; ++u) {
         if (VAR && tid + u * THREADS >= tp) {           // lane beyond the tile: inert entry, flows go to the scratch slots
@@ -378,7 +386,7 @@ __device__ __forceinline__ void load_pools(PoolRegs<NF> (&r)[NPOOL], const Block
             r[u].pos = (uint32_t)(2 * tp) | ((uint32_t)(2 * tp + 1) << 16);
             continue;
         }
-        const long long q = tile * tp + tid + u * THREADS;
+        const long long q = toff + tid + u * THREADS;
 #pragma unroll
         for (int k = 0; k < NF; ++k) r[u].a[k] = __ldg(A.slab[k] + q);
         r[u].lid = __ldg(A.lid + q);
@@ -389,18 +397,20 @@ __device__ __forceinline__ void load_pools(PoolRegs<NF> (&r)[NPOOL], const Block
 // pull the slabs of `tile` from HBM into L2 ahead of the register loads (one thread, 5 bulk prefetches)
 template <int P, int NF, bool VAR = false>
 __device__ __forceinline__ void prefetch_pools_l2(const BlockedArgs& A, long long tile) {
-    const int tp = tile_pools<P, VAR>(A);
+    int4 d = make_int4(0, 0, 0, 0);
+    if (VAR) d = __ldg(A.desc + tile);
+    const int tp = VAR ? ((d.z + 3) & ~3) : P;
+    const long long toff = tile_offset<P, VAR>(d, tile);
 #pragma unroll
-    for (int k = 0; k < NF; ++k) bulk_prefetch_l2(A.slab[k] + tile * tp, tp * 8);
-    bulk_prefetch_l2(A.lid + tile * tp, tp * 4);
-    bulk_prefetch_l2(A.pos + tile * tp, tp * 4);
+    for (int k = 0; k < NF; ++k) bulk_prefetch_l2(A.slab[k] + toff, tp * 8);
+    bulk_prefetch_l2(A.lid + toff, tp * 4);
+    bulk_prefetch_l2(A.pos + toff, tp * 4);
 }
 
 template <int P, int THREADS, int STAGES, int MODE, bool TRADES, bool HESS, bool AR = false, bool VAR = false>
 __global__ void __launch_bounds__(THREADS, 2)
 k_blocked_regs(const BlockedArgs A) {
     constexpr int NF = (MODE == 0) ? 3 : 1;
-    const int tp = tile_pools<P, VAR>(A);
     constexpr int NPOOL = P / THREADS;
     constexpr int NPRE = (P + THREADS - 1) / THREADS;
     using St = TabStage<P>;
@@ -472,10 +482,10 @@ k_blocked_regs(const BlockedArgs A) {
 #pragma unroll
             for (int u = 0; u < NPOOL; ++u) {
                 const uint32_t li = cur[u].lid;
-                if (VAR && MODE == 0 && tid + u * THREADS >= tp) {       // inert lane: no pool behind it
+                if (VAR && MODE == 0 && tid + u * THREADS >= S.desc.z) {  // inert lane: no pool behind it
                     f0[u] = f1[u] = 0.0;
                 } else if (MODE == 0) {
-                    EvalOp::apply<TRADES, HESS>(A, tile * tp + tid + u * THREADS, cur[u].a[0], cur[u].a[NF > 1 ? 1 : 0],
+                    EvalOp::apply<TRADES, HESS>(A, tile_offset<P, VAR>(S.desc, tile) + tid + u * THREADS, cur[u].a[0], cur[u].a[NF > 1 ? 1 : 0],
                                                 cur[u].a[NF > 2 ? 2 : 0], nul[li & 0xffffu], nul[li >> 16], f0[u], f1[u],
                                                 acc);
                 } else if (MODE == 1) {
@@ -613,9 +623,10 @@ int launch_blocked_p(const BlockedArgs& A, cudaStream_t st) {
     return launch_cfg<CfgP<P>, MODE, TRADES, HESS, VAR>(A, st);
 }
 
-// compile-time tile sizes, or any multiple of 4 in [256, 1024] through the runtime-sized (VAR) instantiations of P = 1024
+// compile-time tile sizes, or 0 = every tile carries its own size and offset in its descriptor (VAR instantiations of
+// P = 1024, whose stage capacity bounds the tile size)
 bool tile_pools_fixed(long long P) { return P == 1024 || P == 960 || P == 896; }
-bool tile_pools_ok(long long P) { return tile_pools_fixed(P) || (P >= 256 && P < 1024 && P % 4 == 0); }
+bool tile_pools_ok(long long P) { return tile_pools_fixed(P) || P == 0; }
 
 template <int MODE, bool TRADES, bool HESS>
 int launch_blocked(const BlockedArgs& A, cudaStream_t st) {
@@ -631,11 +642,11 @@ int fill_args(const cfmm_blocked_pairs* b, BlockedArgs& A) {
     if (!b) return CFMM_E_NULL;
     if (!tile_pools_ok(b->pools_per_tile)) return CFMM_E_KIND;
     const int64_t P = b->pools_per_tile;
-    if (b->n_tiles < 0 || b->n_pools < 0 || b->n_pools > b->n_tiles * P) return CFMM_E_SIZE;
+    if (b->n_tiles < 0 || b->n_pools < 0 || b->n_pools > b->n_tiles * (P ? P : 1024)) return CFMM_E_SIZE;
     if (b->n_tiles > 0 && (!b->lid || !b->pos || !b->rows || !b->tok || !b->desc)) return CFMM_E_NULL;
     A.n_tiles = b->n_tiles;
     A.tile_pools = (int)P;
-    A.M = b->n_tiles * P;
+    A.M = P ? b->n_tiles * P : ((b->n_pools + 3) & ~(int64_t)3);      // slab stride (= where slot 1 of delta / lambda starts)
     A.lid = b->lid; A.pos = b->pos; A.rows = b->rows; A.tok = b->tok;
     A.desc = reinterpret_cast<const int4*>(b->desc);
     A.zero_next = nullptr; A.n_zero = 0;

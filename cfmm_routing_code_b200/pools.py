@@ -276,30 +276,51 @@ def blocked_layout_info(lib):
     return tuple(int(x.value) for x in v)      # pools_per_tile, rows_stride, tok_stride, row_cap, ent_stride
 
 
-def balanced_tile_pools(m: int, n_ctas: int, cap: int = 1024, lo: int = 256) -> int:
-    """Tile size for the runtime-sized blocked kernels: the kernels walk ceil(n_tiles / n_ctas) tiles on their critical
-    path, so cut the m pools into n_ctas * k equal tiles (k = tiles per CTA at the capacity `cap`) instead of tiles of
-    `cap` pools with a ragged last round.  1M pools on 296 CTAs: 1180 tiles of 848 (4 per CTA) instead of 977 of 1024
-    (3 or 4 per CTA).  Multiple of 4 so every bulk copy stays a multiple of 16 bytes."""
+def plan_tiles(m: int, n_ctas: int, cap: int = 1024, first: int = 256, lo: int = 256) -> np.ndarray:
+    """Tile sizes (in order, sum = m) for the descriptor-sized blocked kernels (cfmm_set_blocked_config(400)).
+
+    The kernels give CTA b the tiles [T b / G, T (b+1) / G) of a launch (G = min(T, n_ctas) CTAs) and their run time is
+    ramp + the longest chain of tiles.  Tiles of `cap` pools leave a ragged last round (1M pools on 296 CTAs: 977 tiles,
+    89 CTAs walk 4096 pools, the others 3072).  Instead every CTA gets the same number of pools (+-4), cut into the same
+    number k of tiles, the FIRST one small so that compute starts before the bulk of the CTA's data has landed:
+    1M pools -> 296 x (256 + 4 x ~781).  Every size but the last is a multiple of 4 (16-byte aligned bulk copies)."""
     if m <= 0:
-        return cap
-    k = -(-m // (n_ctas * cap))
-    t = -(-m // (n_ctas * k))
-    t = -(-t // 4) * 4
-    return int(min(cap, max(lo, t)))
+        return np.zeros(0, np.int64)
+    if m <= n_ctas * lo:                                    # fewer tiles than CTAs: one small tile each
+        t = np.full(-(-m // lo), lo, np.int64)
+        t[-1] = m - lo * (len(t) - 1)
+        return t
+    bounds = (np.arange(n_ctas + 1, dtype=np.int64) * m // n_ctas) // 4 * 4     # pools of CTA b: [bounds[b], bounds[b+1])
+    bounds[-1] = m
+    per = int(np.diff(bounds).max())
+    if per <= cap:                                          # a single round: one tile per CTA
+        return np.diff(bounds)
+    k = 1 + -(-(per - first) // (cap - 8))                  # tiles per CTA (8 pools of slack for the rounding below)
+    sizes = np.empty((n_ctas, k), np.int64)
+    rest = np.diff(bounds) - first
+    base = rest // (k - 1) // 4 * 4
+    extra = rest - base * (k - 1)                           # < 4 (k - 1): handed out 4 at a time, the odd rest to the last tile
+    sizes[:, 0] = first
+    sizes[:, 1:] = base[:, None] + 4 * (np.arange(k - 1)[None, :] < (extra // 4)[:, None])
+    sizes[:, -1] += extra % 4
+    assert sizes.min() > 0 and sizes.max() <= cap and int(sizes.sum()) == m
+    return sizes.reshape(-1)
 
 
 def build_blocked_pairs(idx: torch.Tensor, n_tokens: int, P: int, rows_stride: int, tok_stride: int, row_cap: int,
-                        ent_stride: int):
+                        ent_stride: int, n_ctas: int = 0):
     """Layout builder for cfmm_blocked_pairs (see csrc/cfmm_blocked.cu).  idx: (2, m) int64 token ids on the
     device.  Pools are sorted by (token block of slot 0, token block of slot 1) and cut into tiles of P; each
     tile gets its distinct-token list, 16-bit local ids, and a CSR of rows (token, <= row_cap entries).
     Returns (order, residual, tables): `order` = bucket-local pool index at each blocked position, `residual` =
-    pools left out because their tile would touch more than tok_stride tokens (they go to a plain bucket)."""
+    pools left out because their tile would touch more than tok_stride tokens (they go to a plain bucket).
+    P == 0: planned tiles (plan_tiles(m, n_ctas)): any size <= tok_stride, (size, first pool) in desc[:, 2:4]."""
     dev = idx.device
     m = idx.shape[1]
     i64 = dict(dtype=torch.int64, device=dev)
-    nb = max(1, int(round((m / P) ** 0.5)))
+    planned = P == 0
+    cap_pools = tok_stride if planned else P            # most pools a tile can hold
+    nb = max(1, int(round((m / cap_pools) ** 0.5)))
     a, b = idx[0], idx[1]
     # primary: (token block of slot 0, token block of slot 1); secondary: slot-0 token, so that the lanes of a warp
     # read the same nu_local entry (shared-memory broadcast) and scatter slot-0 flows to consecutive positions
@@ -310,10 +331,17 @@ def build_blocked_pairs(idx: torch.Tensor, n_tokens: int, P: int, rows_stride: i
         mm = order.numel()
         if mm == 0:
             break
-        ntiles = -(-mm // P)
         pos = torch.arange(mm, **i64)
-        tile = pos // P
-        l = pos - tile * P
+        if planned:
+            sizes = torch.as_tensor(plan_tiles(mm, n_ctas, cap=cap_pools), **i64)
+            ntiles = int(sizes.numel())
+            starts = torch.cumsum(sizes, 0) - sizes
+            tile = torch.bucketize(pos, starts[1:].contiguous(), right=True)
+            l = pos - starts[tile]
+        else:
+            ntiles = -(-mm // P)
+            tile = pos // P
+            l = pos - tile * P
         he_tok = torch.cat([a[order], b[order]])
         he_tile = torch.cat([tile, tile])
         he_code = torch.cat([2 * l, 2 * l + 1])
@@ -338,7 +366,7 @@ def build_blocked_pairs(idx: torch.Tensor, n_tokens: int, P: int, rows_stride: i
     ltok_u = torch.arange(U, **i64) - tok_off[u_tile]
     he_ltok = torch.empty(2 * mm, **i64)
     he_ltok[perm] = ltok_u[inv]
-    M = ntiles * P
+    M = -(-mm // 4) * 4 if planned else ntiles * P
     lid = torch.zeros(M, dtype=torch.int32, device=dev)
     lid[:mm] = (he_ltok[:mm] | (he_ltok[mm:] << 16)).to(torch.int32)
     tok = torch.zeros((ntiles, tok_stride), dtype=torch.int32, device=dev)
@@ -369,15 +397,18 @@ def build_blocked_pairs(idx: torch.Tensor, n_tokens: int, P: int, rows_stride: i
     he_pos[perm] = row_start[he_row] + he_o % row_cap                           # back to (pool, slot) order
     pos = torch.zeros(M, dtype=torch.int32, device=dev)
     # padding pools (last tile) write their zero flows to slots past the real entries of that tile
-    pad_base = 2 * (mm - (ntiles - 1) * P)
-    if M > mm:
+    pad_base = 0 if planned else 2 * (mm - (ntiles - 1) * P)
+    if M > mm and not planned:            # (planned tiles: lanes beyond a tile's pool count never run)
         padl = torch.arange(M - mm, **i64)
         pos[mm:] = ((pad_base + 2 * padl) | ((pad_base + 2 * padl + 1) << 16)).to(torch.int32)
     pos[:mm] = (he_pos[:mm] | (he_pos[mm:] << 16)).to(torch.int32)
     rows = torch.zeros((ntiles, rows_stride), dtype=torch.int32, device=dev)
     word = row_start | (row_len << 16) | (row_ltok << 22)          # start:16 | len:6 | ltok:10 (may set bit 31)
     rows[row_tile, r_local] = torch.where(word >= 2 ** 31, word - 2 ** 32, word).to(torch.int32)
-    desc = torch.stack([ntok, nrow, torch.zeros_like(ntok), torch.zeros_like(ntok)], 1).to(torch.int32).contiguous()
+    if planned:
+        desc = torch.stack([ntok, nrow, sizes, starts], 1).to(torch.int32).contiguous()
+    else:
+        desc = torch.stack([ntok, nrow, torch.zeros_like(ntok), torch.zeros_like(ntok)], 1).to(torch.int32).contiguous()
     tables = dict(n_tiles=ntiles, M=M, lid=lid, tok=tok, pos=pos, rows=rows, desc=desc,
                   rows_per_pool=n_rows / mm, tok_per_tile=float(ntok.double().mean()))
     return order, residual, tables
@@ -392,8 +423,9 @@ class BlockedBucket:
     def __init__(self, hp: HostPools, spec, device, lib):
         self.spec = spec
         P, rows_stride, tok_stride, row_cap, ent_stride = blocked_layout_info(lib)
-        if P == 0:                              # "balanced" (cfmm_set_blocked_config(400)): equal tiles, a whole number per CTA
-            P = balanced_tile_pools(spec.m, 2 * torch.cuda.get_device_properties(device).multi_processor_count)
+        n_ctas = 0
+        if P == 0:                              # planned tiles (cfmm_set_blocked_config(400)): sizes in the descriptors
+            n_ctas = 2 * torch.cuda.get_device_properties(device).multi_processor_count
         f64 = dict(dtype=torch.float64, device=device)
         if spec.identity:                       # raw arrays go up as they are; all reordering happens on the GPU
             R = torch.from_numpy(hp.reserves).to(device, non_blocking=True).view(-1, 2)
@@ -409,7 +441,8 @@ class BlockedBucket:
             R = torch.as_tensor(np.ascontiguousarray(hp.reserves[spec.off].T), **f64)
             idx = torch.as_tensor(np.ascontiguousarray(hp.tok_idx[spec.off].T).astype(np.int64), device=device)
             gam = torch.as_tensor(np.ascontiguousarray(hp.gamma[spec.sel]), **f64)
-        order, residual, t = build_blocked_pairs(idx.t(), hp.n_tokens, P, rows_stride, tok_stride, row_cap, ent_stride)
+        order, residual, t = build_blocked_pairs(idx.t(), hp.n_tokens, P, rows_stride, tok_stride, row_cap, ent_stride,
+                                                 n_ctas=n_ctas)
         self.order = order                               # blocked position -> bucket-local pool index (device)
         self.residual = residual.cpu().numpy() if residual.numel() else np.zeros(0, np.int64)
         self.m = int(order.numel())

@@ -112,7 +112,7 @@ typedef struct cfmm_blocked_pairs {
                                  pos(slot 0) | pos(slot 1) << 16, each < 2P                              */
     const uint32_t* rows;     /* [n_tiles][rows_stride] start :16 | length 1..32 :6 | local token :10, longest first */
     const int32_t* tok;       /* [n_tiles][tok_stride] local token id -> global token id                 */
-    const int32_t* desc;      /* [n_tiles][4] (ntok, nrow, 0, 0)                                         */
+    const int32_t* desc;      /* [n_tiles][4] (ntok, nrow, 0, 0); planned tiles: (ntok, nrow, pools, first pool) */
 } cfmm_blocked_pairs;
 
 int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int32_t* tok_stride, int32_t* row_cap,
@@ -120,10 +120,10 @@ int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int3
 /* tuning: -1 = default (evaluation: TMA-staged slabs; Hessian products / diagonal: register-fed variant),
  * 0 = TMA-staged for everything, 3 = register-fed for everything; 200/201 = programmatic dependent launch off/on;
  * 300+c = row cap c (8..32) for layouts built afterwards; 400+P = pools per tile P (1024 default | 960 | 896) of
- * layouts built afterwards (load balance: a launch's critical path is ceil(n_tiles / (2 SMs)) tiles); 400 = balanced:
- * cfmm_blocked_layout_info then reports pools_per_tile 0 and the builder picks any multiple of 4 in [256, 1024] per
- * bucket (runtime-sized kernels; table strides of the 1024 layout). cfmm_blocked_pairs.pools_per_tile carries the
- * choice to the kernels. */
+ * layouts built afterwards (load balance: a launch's critical path is ceil(n_tiles / (2 SMs)) tiles); 400 = planned
+ * tiles: cfmm_blocked_layout_info then reports pools_per_tile 0 and the builder cuts tiles of any size <= 1024
+ * (offsets multiples of 4), writing (pools, first pool) into desc[2], desc[3] of every tile; such a layout is passed
+ * with cfmm_blocked_pairs.pools_per_tile = 0, slabs of ceil4(n_pools) entries, table strides of the 1024 layout. */
 int cfmm_set_blocked_config(int32_t cfg);
 
 /* Same contract as cfmm_arb_eval for a blocked constant-product bucket: psi/arb ACCUMULATE (one red.add per row

@@ -71,11 +71,10 @@ def test_blocked_kernels_with_smaller_tiles_match_oracle(tile_pools):
     lib = _lib.load()
     assert lib.cfmm_set_blocked_config(400 + tile_pools) == 0
     try:
-        for m, n in ((20_000, 97), (70_000, 4096)):
+        for m, n in ((20_000, 97), (70_000, 4096), (400_000, 512)):       # the last: several tiles per CTA
             hp, s = H.cp_host_pools(m, n, seed=m % 97)
             st, ref = _check_eval(hp, H.random_prices(s["prices"], 1))
-            got = st.buckets[0].c_blocked.pools_per_tile       # 0 = balanced: the builder's choice, runtime-sized kernels
-            assert got == tile_pools or (tile_pools == 0 and got % 4 == 0 and 256 <= got < 1024)
+            assert st.buckets[0].c_blocked.pools_per_tile == tile_pools      # 0 = planned tiles, sizes in the descriptors
             v = np.random.default_rng(2).standard_normal(n)
             Hs = ref["hess_scaled"]
             np.testing.assert_allclose(st.hvp(torch.as_tensor(v, **F64)).cpu().numpy(), Hs @ v,

@@ -162,21 +162,28 @@ def test_bounded_product_pools_get_their_own_bucket():
         cf.HostPools.from_lists(2, [[0, 1]], [[0.0, 1.0]], [0.99], ["bounded_product"], [[0.0, 1.0]]).validate()
 
 
-def test_balanced_tile_size_rule():
-    """equal tiles, a whole number per resident CTA (the blocked kernels' critical path is ceil(n_tiles / n_ctas) tiles)"""
-    t = PL.balanced_tile_pools(1_000_000, 296)
-    assert t == 848 and -(-1_000_000 // t) <= 4 * 296               # cfg5: 1180 tiles, 4 per CTA (1024: 977 -> 3 or 4)
-    for m in (1, 255, 10_000, 303_104, 303_105, 2_000_000, 10 ** 9):
-        t = PL.balanced_tile_pools(m, 296)
-        assert t % 4 == 0 and 256 <= t <= 1024
-        k = -(-m // (296 * 1024))
-        assert -(-m // t) <= 296 * k or t == 256                      # never more rounds than tiles of 1024 would need
+def test_tile_plan_gives_every_cta_the_same_work():
+    """planned tiles (cfmm_set_blocked_config(400)): same pool count (+-4) and same tile count for every CTA, small first
+    tile, 16-byte aligned offsets; the kernels' tile -> CTA map is [T b / G, T (b + 1) / G)"""
+    G = 296
+    t = PL.plan_tiles(1_000_000, G)
+    assert t.sum() == 1_000_000 and len(t) == G * 5 and t.max() <= 1024 and t.min() >= 256
+    per_cta = t.reshape(G, 5)
+    assert np.all(per_cta[:, 0] == 256) and per_cta.sum(1).max() - per_cta.sum(1).min() <= 4
+    assert np.all((np.cumsum(t) - t) % 4 == 0)
+    for m in (1, 3, 255, 257, 10_000, 75_776, 75_780, 303_104, 303_108, 2_000_000, 12_345_679):
+        t = PL.plan_tiles(m, G)
+        T = len(t)
+        assert t.sum() == m and t.min() > 0 and t.max() <= 1024 and np.all((np.cumsum(t) - t) % 4 == 0)
+        g = min(T, G)
+        chains = [t[T * b // g: T * (b + 1) // g].sum() for b in range(g)]
+        assert max(chains) <= -(-m // g) + 1024 and (T <= G or max(chains) - min(chains) <= 8), (m, max(chains), min(chains))
 
 
 @pytest.mark.parametrize("tile_pools", [1024, 960, 896, 0])
 def test_blocked_layout_builder_tables_reproduce_the_scatter(tile_pools):
     """build_blocked_pairs on CPU tensors: emulate the kernel's row sums and compare with index_add; for every tile
-    size the kernels are instantiated for (cfmm_set_blocked_config(400 + P)) and for the runtime-sized ones (400)."""
+    size the kernels are instantiated for (cfmm_set_blocked_config(400 + P)) and for planned tiles (400)."""
     lib = _lib.load()
     assert lib.cfmm_set_blocked_config(400 + 1000) == -2               # not an instantiated tile size
     assert lib.cfmm_set_blocked_config(400 + tile_pools) == 0
@@ -184,36 +191,47 @@ def test_blocked_layout_builder_tables_reproduce_the_scatter(tile_pools):
         P, rs, ts, cap, es = PL.blocked_layout_info(lib)
     finally:
         lib.cfmm_set_blocked_config(400 + 1024)
-    if tile_pools == 0:                                                 # balanced: tables keep the strides of 1024
+    planned = tile_pools == 0
+    if planned:                                                         # tables keep the strides of the 1024 layout
         assert P == 0 and rs == 1024 + 256 + 8 and ts == 1024
-        P = 848
     else:
         assert P == tile_pools and rs == P + P // 4 + 8 and ts == P
-    for m, n in ((5000, 300), (700, 3), (40_000, 2000)):
+    for m, n, G in ((5000, 300, 8), (700, 3, 296), (40_000, 2000, 16), (9_000, 50, 2)):
         s = I.synth_const_product(m, n, 0)
         idx = torch.as_tensor(s["idx"].T.astype(np.int64).copy())
-        order, res, t = PL.build_blocked_pairs(idx, n, P, rs, ts, cap, es)
+        order, res, t = PL.build_blocked_pairs(idx, n, P, rs, ts, cap, es, n_ctas=G)
         assert len(order) + len(res) == m and t is not None
-        M = t["n_tiles"] * P
-        f = torch.randn(M, 2, dtype=torch.float64)                     # flows of (pool, slot), blocked order
-        f[len(order):] = 0.0                                            # padding pools produce zero flows
-        pos = t["pos"].to(torch.int64) & 0xffffffff
-        g = torch.zeros(t["n_tiles"], 2 * P, dtype=torch.float64)       # the pool phase scatters into row order
-        tl_all = torch.arange(M) // P
-        g[tl_all, pos & 0xffff] = f[:, 0]
-        g[tl_all, pos >> 16] = f[:, 1]
+        M, T = t["M"], t["n_tiles"]
+        desc = t["desc"].to(torch.int64)
+        if planned:
+            sizes, starts = desc[:, 2], desc[:, 3]
+            assert M == -(-len(order) // 4) * 4 and int(sizes.sum()) == len(order) and int(sizes.max()) <= 1024
+            assert bool((starts == torch.cumsum(sizes, 0) - sizes).all()) and bool((starts % 4 == 0).all())
+            assert T <= G or T % G == 0                                  # a whole number of tiles per CTA
+        else:
+            assert M == T * P
+            starts = torch.arange(T) * P
+        q = torch.arange(len(order))
+        tl = torch.bucketize(q, starts[1:].contiguous(), right=True)
+        l = q - starts[tl]
+        f = torch.randn(len(order), 2, dtype=torch.float64)            # flows of (pool, slot), blocked order
+        pos = t["pos"].to(torch.int64)[:len(order)] & 0xffffffff
+        g = torch.zeros(T, 2 * 1024, dtype=torch.float64)               # the pool phase scatters into row order
+        g[tl, pos & 0xffff] = f[:, 0]
+        g[tl, pos >> 16] = f[:, 1]
         rows = t["rows"].to(torch.int64) & 0xffffffff
         out = torch.zeros(n, dtype=torch.float64)
-        for tile in range(t["n_tiles"]):
-            ntok, nrow, _, _ = t["desc"][tile].tolist()
+        for tile in range(T):
+            ntok, nrow = desc[tile, 0].item(), desc[tile, 1].item()
             assert ntok <= ts and nrow <= rs
             w = rows[tile, :nrow]
             st, ln, lt = w & 0xffff, (w >> 16) & 0x3f, w >> 22
             assert bool((ln[:-1] >= ln[1:]).all()) and int(ln.max()) <= cap     # longest rows first
+            cnt = int(sizes[tile]) if planned else P
+            assert int((st + ln).max()) <= 2 * cnt                      # rows stay inside the tile's 2 cnt flow slots
             for r in range(nrow):
                 out[t["tok"][tile, lt[r]]] += g[tile, st[r]:st[r] + ln[r]].sum()
         a, b = idx[0][order], idx[1][order]
-        q = torch.arange(len(order)); tl, l = q // P, q % P
         ref = torch.zeros(n, dtype=torch.float64)
         ref.index_add_(0, a, f[q, 0]); ref.index_add_(0, b, f[q, 1])
         assert float((out - ref).abs().max()) <= 1e-12 * float(ref.abs().max())
