@@ -240,3 +240,21 @@ def test_bounded_product_instance_dual_solution_matches_slsqp_primal():
         ep, em = O.evaluate(bk, nu + e), O.evaluate(bk, nu - e)
         assert abs((ep["arb"] - em["arb"]) / (2 * h) - ev["psi"][j]) <= 1e-5 * (abs(ev["psi"][j]) + 1)
         np.testing.assert_allclose((ep["psi"] - em["psi"]) / (2 * h), Hs[:, j], atol=2e-4 * np.abs(Hs).max())
+
+
+def test_v3_position_helper_invariants():
+    """instances.v3_position: (x + o_x)(y + o_y) = L^2, marginal price (y + o_y)/(x + o_x) = p, the real reserves are what
+    is left when the price runs to either end of the range"""
+    from cfmm_routing_code_b200 import instances as I
+    for L, lo, hi, p in ((100.0, 0.8, 1.25, 1.0), (7.0, 1900.0, 2100.0, 2000.0), (3.0, 0.5, 0.6, 0.55)):
+        (x, y), (ox, oy) = I.v3_position(L, lo, hi, p)
+        assert x > 0 and y > 0
+        assert abs((x + ox) * (y + oy) - L * L) <= 1e-12 * L * L
+        assert abs((y + oy) / (x + ox) - p) <= 1e-12 * p
+        assert abs((x + ox) - L / np.sqrt(p)) <= 1e-12 * L and abs(ox - L / np.sqrt(hi)) <= 1e-12 * L
+        # draining token 1 completely moves the price to the lower end of the range: x_virtual = L / sqrt(lo)
+        assert abs(L * L / oy - L / np.sqrt(lo)) <= 1e-12 * L / np.sqrt(lo)
+    (x, y), _ = I.v3_position(5.0, 1.25, 1.6, 1.0)          # price below the range: all in token 0
+    assert y == 0.0 and x > 0
+    (x, y), _ = I.v3_position(5.0, 0.5, 0.8, 1.0)           # above: all in token 1
+    assert x == 0.0 and y > 0
