@@ -97,6 +97,21 @@ def solve(local_indices, reserves, fees, kinds, weights=None, utility=None, n_to
                        **solver_kw)
 
 
+def _check_structurally_feasible(hp: HostPools, spec) -> None:
+    """A token that must change hands (psi_j + a_j == 0 with a_j != 0, or psi_j + a_j >= 0 with a_j < 0) but sits in no
+    pool makes the program infeasible (cvxpy would set prob.status = 'infeasible'; the scripts never look at it).  The
+    dual method would only see that token's price drift to its floor, so it is rejected up front."""
+    a = np.asarray(spec.a, float)
+    need = ((np.asarray(spec.eq, bool) & (a != 0)) | (~np.asarray(spec.eq, bool) & ~np.asarray(spec.pinned, bool) & (a < 0)))
+    if need.any():
+        present = np.zeros(hp.n_tokens, bool)
+        present[np.asarray(hp.tok_idx)] = True
+        bad = np.nonzero(need & ~present)[0]
+        if len(bad):
+            raise ValueError(f"infeasible problem: token(s) {bad.tolist()} must be traded (non-zero endowment / demand) "
+                             "but appear in no pool")
+
+
 SMALL_POOLS = 256        # up to here one GPU thread walks all pools of a problem faster than a launch per evaluation
 
 
@@ -157,6 +172,7 @@ def solve_pools(hp: HostPools, utility, nu0=None, tol: float = 1e-8, max_iter: i
     comm = Comm()
     if method not in ("auto", "pools", "thread"):
         raise ValueError("method must be 'auto', 'pools' or 'thread'")
+    _check_structurally_feasible(hp, utility.spec(hp.n_tokens))
     if method == "thread" or (method == "auto" and store is None and _small_applicable(hp, comm, verbose, solver_kw)):
         # problems of the reference's own size (5 pools): the whole solve in one launch of the per-thread solver
         # (csrc/cfmm_small.cu) instead of one launch per dual evaluation -- 10x less latency, same certificate

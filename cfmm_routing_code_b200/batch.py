@@ -115,6 +115,9 @@ def solve_batch(hp: HostPools, utilities: Sequence, nu0=None, tol: float = 1e-8,
     """All problems (same pools, one utility each) in one launch.  Returns a list of api.Result."""
     from .api import Result
     t0 = time.perf_counter()
+    from .api import _check_structurally_feasible
+    for u in utilities:
+        _check_structurally_feasible(hp, u.spec(hp.n_tokens))
     store = store or CsrStore(hp, device=device)
     n, dev = hp.n_tokens, store.device
     c, a, fl, nu = pack_utilities(utilities, n, nu0)

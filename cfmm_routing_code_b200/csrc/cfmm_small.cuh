@@ -270,17 +270,19 @@ CFMM_HD inline double kkt(const Problem& Q, const Vec& nu, const Vec& psi, const
     return num / fmax(fmax(fabs(g), 1e-3 * wsum), TINY);
 }
 
-// Solve (Hs[free,free] + reg I) x = -pg[free] by Gaussian elimination with partial pivoting; dt = 0 off the free set.
-// Returns false when the system is singular or the result is not a descent direction.
-CFMM_HD inline bool newton_direction(int n, uint64_t free_mask, const Vec& Hs, const Vec& pg, const Vec& A,
-                                     const Vec& dt) {
+// Solve (Hs[free,free] + mu dbar I) x = -pg[free] (dbar = mean diagonal) by Gaussian elimination with partial pivoting;
+// dt = 0 off the free set.  Returns 0 = descent direction, 1 = solved but not a descent direction, 2 = singular / not finite;
+// *big = largest |x_j| (the caller climbs the damping ladder while it is not a sane log-price change).
+CFMM_HD inline int newton_direction(int n, uint64_t free_mask, const Vec& Hs, const Vec& pg, const Vec& A,
+                                     const Vec& dt, double mu, double* big) {
     int fidx[NTOK_MAX];
     int nf = 0;
     for (int j = 0; j < n; ++j) { dt[j] = 0.0; if (free_mask >> j & 1) fidx[nf++] = j; }
-    if (nf == 0) return false;
+    *big = 0.0;
+    if (nf == 0) return 1;
     double tr = 0.0;
     for (int x = 0; x < nf; ++x) tr += Hs[fidx[x] * n + fidx[x]];
-    const double reg = 1e-14 * fmax(tr / nf, TINY);
+    const double reg = mu * fmax(tr / nf, TINY);
     const int ld = nf + 1;                                                  // augmented [A | rhs], row-major in A
     for (int x = 0; x < nf; ++x) {
         for (int y = 0; y < nf; ++y) A[x * ld + y] = Hs[fidx[x] * n + fidx[y]] + (x == y ? reg : 0.0);
@@ -290,7 +292,7 @@ CFMM_HD inline bool newton_direction(int n, uint64_t free_mask, const Vec& Hs, c
         int piv = col;
         double best = fabs(A[col * ld + col]);
         for (int r = col + 1; r < nf; ++r) { const double v = fabs(A[r * ld + col]); if (v > best) { best = v; piv = r; } }
-        if (!(best > 0.0) || !isfinite(best)) return false;
+        if (!(best > 0.0) || !isfinite(best)) return 2;
         if (piv != col)
             for (int y = col; y <= nf; ++y) { const double t = A[col * ld + y]; A[col * ld + y] = A[piv * ld + y]; A[piv * ld + y] = t; }
         const double inv = 1.0 / A[col * ld + col];
@@ -307,9 +309,11 @@ CFMM_HD inline bool newton_direction(int n, uint64_t free_mask, const Vec& Hs, c
         v /= A[x * ld + x];
         dt[fidx[x]] = v;
         finite = finite && isfinite(v);
+        *big = fmax(*big, fabs(v));
     }
     for (int x = 0; x < nf; ++x) slope += pg[fidx[x]] * dt[fidx[x]];
-    return finite && slope < 0.0;
+    if (!finite) return 2;
+    return slope < 0.0 ? 0 : 1;
 }
 
 // Workspace elements one problem needs (doubles): 12 n-vectors, 2 Hessians, the augmented system, 2 multiplier sets.
@@ -374,7 +378,17 @@ CFMM_HD inline Stats solve_one(const Pools& P, Problem Q, const Params& prm, dou
             printf("outer=%d it=%d g=%.15g err=%.3e free=%d\n", outer, iters, g, err, __builtin_popcountll(free_mask));
 #endif
             if (err <= inner_tol) { inner_status = 0; break; }
-            if (!newton_direction(n, free_mask, Hsv[cur], pg, A, dt)) {      // fall back to scaled steepest descent
+            // (near-)singular free-set systems (every pool tying some free prices to the rest saturated) give an enormous
+            // step along the null directions: climb the damping ladder (Levenberg-Marquardt shift mu * mean diagonal)
+            // until the step is a sane price change; the null directions then get a scaled gradient step
+            int code = 2;
+            for (int rung = 0; rung < 6; ++rung) {
+                const double mus[6] = {1e-14, 1e-8, 1e-6, 1e-4, 1e-2, 1.0};
+                double big = 0.0;
+                code = newton_direction(n, free_mask, Hsv[cur], pg, A, dt, mus[rung], &big);
+                if (code != 2 && big <= DT_MAX) break;                   // a sane step (or nothing free): stop damping
+            }
+            if (code != 0) {                                             // fall back to scaled steepest descent
                 double mx = 0.0;
                 for (int j = 0; j < n; ++j) mx = fmax(mx, fabs(pg[j]));
                 mx = fmax(mx, TINY);

@@ -29,6 +29,7 @@ import torch
 
 
 DT_MAX = 3.0      # largest log-price change of one dense Newton step
+LM_SHIFTS = (1e-14, 1e-8, 1e-6, 1e-4, 1e-2, 1.0)     # damping ladder of the dense Newton system, times the mean diagonal
 
 
 @dataclasses.dataclass
@@ -164,14 +165,23 @@ def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 0.1
 
             def newton_dir(fr_, x0=None):
                 if linear_solver == "dense":
-                    Hm = Hs * fr_[:, None] * fr_[None, :]
-                    reg = 1e-14 * float(torch.diagonal(Hm).sum()) / max(int(fr_.sum()), 1)
-                    Hm = Hm + torch.diag((1.0 - fr_) + reg * fr_)
-                    L, info = torch.linalg.cholesky_ex(Hm)
-                    if int(info) == 0:
-                        d_ = torch.cholesky_solve((-pgfull * fr_)[:, None], L)[:, 0]
-                    else:
-                        d_ = torch.linalg.lstsq(Hm, (-pgfull * fr_)[:, None]).solution[:, 0]
+                    H0 = Hs * fr_[:, None] * fr_[None, :]
+                    dbar = max(float(torch.diagonal(H0).sum()) / max(int(fr_.sum()), 1), 1e-300)
+                    rhs_ = (-pgfull * fr_)[:, None]
+                    d_ = None
+                    # (near-)singular free-set systems (every pool tying some free prices to the rest saturated) give an
+                    # enormous step along the null directions: climb the damping ladder (Levenberg-Marquardt shift
+                    # mu * mean diagonal) until the step is a sane price change
+                    for mu in LM_SHIFTS:
+                        Hm = H0 + torch.diag((1.0 - fr_) + (mu * dbar) * fr_)
+                        L, info = torch.linalg.cholesky_ex(Hm)
+                        if int(info) != 0:
+                            continue
+                        d_ = torch.cholesky_solve(rhs_, L)[:, 0]
+                        if float(d_.abs().max()) <= DT_MAX:
+                            break
+                    if d_ is None:
+                        d_ = torch.linalg.lstsq(H0 + torch.diag((1.0 - fr_) + dbar * fr_), rhs_).solution[:, 0]
                     return d_ * fr_
                 return _pcg(ev, comm, -pgfull * fr_, fr_, diag, eta=min(0.1, err ** 0.5), max_it=cg_max, x0=x0)
 

@@ -44,6 +44,7 @@ KIND_BOUNDED = 3   # constant product on virtual reserves R + o with real reserv
 
 _TINY = 1e-300
 DT_MAX = 3.0      # largest log-price change of one Newton step
+LM_SHIFTS = (1e-14, 1e-8, 1e-6, 1e-4, 1e-2, 1.0)     # damping ladder of the Newton system, times the mean diagonal
 
 
 # --------------------------------------------------------------------------------------
@@ -455,17 +456,23 @@ def solve(pools: Pools, util: Utility, nu0=None, tol=1e-9, eps=0.1, eps_min=1e-4
                 break
             Hs = ev["hess_scaled"][np.ix_(free, free)]
             rhs = -pg[free]
-            reg = 1e-14 * max(np.trace(Hs) / max(free.sum(), 1), 1e-300)
-            try:
-                dtf = np.linalg.solve(Hs + reg * np.eye(len(rhs)), rhs)
-            except np.linalg.LinAlgError:
-                dtf = np.linalg.lstsq(Hs, rhs, rcond=None)[0]
+            dbar = max(np.trace(Hs) / max(free.sum(), 1), 1e-300)
+            # (near-)singular free-set systems (e.g. every pool tying some free prices to the rest is saturated) give an
+            # enormous step along the null directions: damp the system (Levenberg-Marquardt, shift mu * mean diagonal)
+            # until the step is a sane price change; the null directions then get a scaled gradient step
+            for mu in LM_SHIFTS:
+                try:
+                    dtf = np.linalg.solve(Hs + mu * dbar * np.eye(len(rhs)), rhs)
+                except np.linalg.LinAlgError:
+                    dtf = np.full(len(rhs), np.inf)
+                if np.all(np.isfinite(dtf)) and np.abs(dtf).max(initial=0.0) <= DT_MAX:
+                    break
             dt = np.zeros(n); dt[free] = dtf
             if not np.all(np.isfinite(dt)) or np.dot(pg, dt) >= 0:
                 dt = -pg / max(np.abs(pg).max(), 1e-300)
             big = np.abs(dt).max()
-            if big > DT_MAX:        # (near-)singular system, e.g. every pool that ties the free prices to a bound is
-                dt *= DT_MAX / big  # saturated: keep the direction, bound the step, let the line search find the kink
+            if big > DT_MAX:        # still too long after the largest shift: keep the direction, bound the step
+                dt *= DT_MAX / big
             alpha = 1.0
             g0 = ev["g"]
             ok = False

@@ -221,7 +221,12 @@ def test_host_build_infeasible_liquidation_is_not_reported_optimal():
     hp = cf.HostPools.from_lists(3, [[0, 1]], [[10.0, 10.0]], [0.997], ["product"], [None])
     u = O.Utility.liquidate(3, 0, [0.0, 1.0, 2.0])                # token 2 is in no pool
     out = small_host.solve(hp, [u], tol=1e-8)
-    assert int(out["stats"][0][7]) != 0 and not abs(out["stats"][0][2]) <= 1e-6
+    assert int(out["stats"][0][7]) != 0                          # the price of token 2 just drifts towards its floor
+    assert abs(out["psi"][0][2] + 2.0) > 1.0                      # and the basket constraint is not met
+    with pytest.raises(ValueError, match="infeasible"):          # the API refuses such problems before any launch
+        cf.solve_pools(hp, cf.Liquidate(0, [0.0, 1.0, 2.0]))
+    with pytest.raises(ValueError, match="infeasible"):
+        cf.solve_batch(hp, [cf.Liquidate(0, [0.0, 1.0, 2.0])])
 
 
 class _HostStore:
