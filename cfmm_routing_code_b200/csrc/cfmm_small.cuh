@@ -381,45 +381,52 @@ CFMM_HD inline Stats solve_one(const Pools& P, Problem Q, const Params& prm, dou
             // (near-)singular free-set systems (every pool tying some free prices to the rest saturated) give an enormous
             // step along the null directions: climb the damping ladder (Levenberg-Marquardt shift mu * mean diagonal)
             // until the step is a sane price change; the null directions then get a scaled gradient step
-            int code = 2;
-            for (int rung = 0; rung < 6; ++rung) {
-                const double mus[6] = {1e-14, 1e-8, 1e-6, 1e-4, 1e-2, 1.0};
-                double big = 0.0;
-                code = newton_direction(n, free_mask, Hsv[cur], pg, A, dt, mus[rung], &big);
-                if (code != 2 && big <= DT_MAX) break;                   // a sane step (or nothing free): stop damping
-            }
-            if (code != 0) {                                             // fall back to scaled steepest descent
-                double mx = 0.0;
-                for (int j = 0; j < n; ++j) mx = fmax(mx, fabs(pg[j]));
-                mx = fmax(mx, TINY);
-                for (int j = 0; j < n; ++j) dt[j] = -pg[j] / mx;
-            }
-            {                                                            // (near-)singular system: keep the direction,
-                double big = 0.0;                                        // bound the step to a price factor of e^3
-                for (int j = 0; j < n; ++j) big = fmax(big, fabs(dt[j]));
-                if (big > DT_MAX) for (int j = 0; j < n; ++j) dt[j] *= DT_MAX / big;
-            }
-            double alpha = 1.0;
-            bool ok = false;
+            const double mus[6] = {1e-14, 1e-8, 1e-6, 1e-4, 1e-2, 1.0};
             const int nxt = cur ^ 1;
-            double g_t = g, lin1 = 0.0;                                    // lin1: predicted decrease of the FULL step
-            for (int ls = 0; ls < 50; ++ls) {
-                double lin = 0.0;
-                for (int j = 0; j < n; ++j) {
-                    const double st = fmin(fmax(alpha * dt[j], -20.0), 20.0);
-                    const double v = is_pinned(Q, j) ? Q.c[j] : fmax(nuv[cur][j] * exp(st), lb[j]);
-                    nuv[nxt][j] = v;
-                    lin += grad[j] * (v - nuv[cur][j]);
+            double alpha = 1.0, g_t = g;
+            bool ok = false;
+            for (int rung = 0;;) {
+                int code = 2;
+                for (;; ++rung) {                                        // climb until the step is a sane price change
+                    double big = 0.0;
+                    code = newton_direction(n, free_mask, Hsv[cur], pg, A, dt, mus[rung], &big);
+                    if ((code != 2 && big <= DT_MAX) || rung == 5) break;
                 }
-                g_t = dual_value(Q, nuv[nxt], evaluate<LANES>(P, Q, nuv[nxt], lognu, eps_t, psiv[nxt], &Hsv[nxt], false, false, lane));
-                ++evals;
-                if (ls == 0) lin1 = lin;
-                if (g_t <= g + 1e-4 * lin) { ok = true; break; }
-                if (fabs(g_t - g) <= 1e-13 * fabs(g) || fabs(lin1) <= 1e-9 * fabs(g)) {  // g cannot resolve this step
-                    if (kkt(Q, nuv[nxt], psiv[nxt], lb, g_t, err, grad_t, pg_t, &fm_t) < 0.99 * err) { ok = true; break; }
-                    if (alpha < 1e-3) break;
+                if (code != 0) {                                         // fall back to scaled steepest descent
+                    double mx = 0.0;
+                    for (int j = 0; j < n; ++j) mx = fmax(mx, fabs(pg[j]));
+                    mx = fmax(mx, TINY);
+                    for (int j = 0; j < n; ++j) dt[j] = -pg[j] / mx;
                 }
-                alpha *= 0.5;
+                {                                                        // still too long after the largest shift:
+                    double big = 0.0;                                    // keep the direction, bound the step
+                    for (int j = 0; j < n; ++j) big = fmax(big, fabs(dt[j]));
+                    if (big > DT_MAX) for (int j = 0; j < n; ++j) dt[j] *= DT_MAX / big;
+                }
+                alpha = 1.0;
+                double lin1 = 0.0;                                       // predicted decrease of the FULL step
+                for (int ls = 0; ls < 50; ++ls) {
+                    double lin = 0.0;
+                    for (int j = 0; j < n; ++j) {
+                        const double st = fmin(fmax(alpha * dt[j], -20.0), 20.0);
+                        const double v = is_pinned(Q, j) ? Q.c[j] : fmax(nuv[cur][j] * exp(st), lb[j]);
+                        nuv[nxt][j] = v;
+                        lin += grad[j] * (v - nuv[cur][j]);
+                    }
+                    g_t = dual_value(Q, nuv[nxt], evaluate<LANES>(P, Q, nuv[nxt], lognu, eps_t, psiv[nxt], &Hsv[nxt], false, false, lane));
+                    ++evals;
+                    if (ls == 0) lin1 = lin;
+                    if (g_t <= g + 1e-4 * lin) { ok = true; break; }
+                    if (fabs(g_t - g) <= 1e-13 * fabs(g) || fabs(lin1) <= 1e-9 * fabs(g)) {  // g cannot resolve this step
+                        if (kkt(Q, nuv[nxt], psiv[nxt], lb, g_t, err, grad_t, pg_t, &fm_t) < 0.99 * err) { ok = true; break; }
+                        if (alpha < 1e-3) break;
+                    }
+                    alpha *= 0.5;
+                }
+                // a failed search along a barely damped direction (null-space dominated: long step, no predicted gain):
+                // damp harder and try again before giving up
+                if (ok || rung == 5) break;
+                ++rung;
             }
 #ifdef CFMM_SMALL_TRACE
             { double mx = 0; int jm = 0; for (int j = 0; j < n; ++j) if (fabs(pg[j]) > mx) { mx = fabs(pg[j]); jm = j; }

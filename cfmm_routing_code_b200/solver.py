@@ -172,8 +172,9 @@ def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 0.1
                     # (near-)singular free-set systems (every pool tying some free prices to the rest saturated) give an
                     # enormous step along the null directions: climb the damping ladder (Levenberg-Marquardt shift
                     # mu * mean diagonal) until the step is a sane price change
-                    for mu in LM_SHIFTS:
-                        Hm = H0 + torch.diag((1.0 - fr_) + (mu * dbar) * fr_)
+                    for r_ in range(rung0, len(LM_SHIFTS)):
+                        rung_used[0] = max(rung_used[0], r_)
+                        Hm = H0 + torch.diag((1.0 - fr_) + (LM_SHIFTS[r_] * dbar) * fr_)
                         L, info = torch.linalg.cholesky_ex(Hm)
                         if int(info) != 0:
                             continue
@@ -185,61 +186,69 @@ def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 0.1
                     return d_ * fr_
                 return _pcg(ev, comm, -pgfull * fr_, fr_, diag, eta=min(0.1, err ** 0.5), max_it=cg_max, x0=x0)
 
-            dt = newton_dir(fr)
-            # ---- look-ahead on the active set: a token held at its bound (grad > 0) whose PREDICTED gradient after
-            # this step, nu*grad + Hs dt, is negative would be released at the next iteration anyway; release it now
-            # and re-solve (warm started).  Costs Hessian-vector products only, saves whole Newton iterations
-            # (the all-at-bound start of the arbitrage utility otherwise frees tokens layer by layer).
-            bound_act = (fr == 0) & ~fixed
-            for _la in range(lookahead if linear_solver == "dense" else 0):   # with CG the extra HVPs eat the gain
-                if not bool(bound_act.any()):
-                    break
-                Hd = (Hs @ dt) if linear_solver == "dense" else _reduce_hvp(ev, comm, dt)
-                newly = bound_act & ((pgfull + Hd) < 0)
-                if not bool(newly.any()):
-                    break
-                fr2 = fr + newly.to(fr.dtype)
-                dt2 = newton_dir(fr2, x0=dt)
-                bad = newly & (dt2 <= 0)                 # would be pushed below its bound after all: keep it active
-                if bool(bad.any()):
-                    fr2 = fr2 - bad.to(fr.dtype)
-                    dt2 = dt2 * fr2
-                fr, dt = fr2, dt2
+            fr0 = fr
+            rung0, rung_used = 0, [0]
+            while True:          # a failed search along a barely damped (null-space dominated) direction is retried with
+                fr = fr0         # the next rung of the damping ladder before the iteration is declared stalled
+                rung_used[0] = rung0
+                dt = newton_dir(fr)
+                # ---- look-ahead on the active set: a token held at its bound (grad > 0) whose PREDICTED gradient after
+                # this step, nu*grad + Hs dt, is negative would be released at the next iteration anyway; release it now
+                # and re-solve (warm started).  Costs Hessian-vector products only, saves whole Newton iterations
+                # (the all-at-bound start of the arbitrage utility otherwise frees tokens layer by layer).
                 bound_act = (fr == 0) & ~fixed
-            pg = pgfull * fr
-            slope = torch.dot(pg, dt)     # = grad . (nu*dt)
-            if not bool(torch.isfinite(slope)) or float(slope) >= 0.0:
-                dt = -pg / pg.abs().max().clamp(min=1e-300)
-            if linear_solver == "dense":
-                # (near-)singular system, e.g. every pool tying the free prices to a bound is saturated: keep the
-                # direction, bound the step to a price factor of e^3 and let the line search find the kink
-                big = float(dt.abs().max())
-                if big > DT_MAX:
-                    dt = dt * (DT_MAX / big)
-            # ---- projected Armijo backtracking along nu * exp(alpha dt)
-            alpha = 1.0
-            g0 = float(g)
-            ok = False
-            for _ls in range(50):
-                nu_t = torch.maximum(nu * torch.exp(torch.clamp(alpha * dt, -20.0, 20.0)), lb)
-                nu_t = torch.where(fixed, c, nu_t)
-                psi_t, g_t = G(nu_t)
-                lin = float(torch.dot(grad, nu_t - nu))
-                if _ls == 0:
-                    lin1 = lin             # predicted decrease of the FULL step
-                gt = float(g_t)
-                if gt <= g0 + 1e-4 * lin:
-                    ok = True
-                    break
-                if abs(gt - g0) <= 1e-13 * abs(g0) or abs(lin1) <= 1e-9 * abs(g0):
-                    # the (full) step is below what g resolves in fp64 (g is a sum of cancelling flows: the Armijo
-                    # decrease 1e-4 |lin| would be under 1e-13 |g|): judge it by the KKT residual instead
-                    if kkt(nu_t, psi_t, g_t, err)[0] < 0.99 * err:
+                for _la in range(lookahead if linear_solver == "dense" else 0):   # with CG the extra HVPs eat the gain
+                    if not bool(bound_act.any()):
+                        break
+                    Hd = (Hs @ dt) if linear_solver == "dense" else _reduce_hvp(ev, comm, dt)
+                    newly = bound_act & ((pgfull + Hd) < 0)
+                    if not bool(newly.any()):
+                        break
+                    fr2 = fr + newly.to(fr.dtype)
+                    dt2 = newton_dir(fr2, x0=dt)
+                    bad = newly & (dt2 <= 0)                 # would be pushed below its bound after all: keep it active
+                    if bool(bad.any()):
+                        fr2 = fr2 - bad.to(fr.dtype)
+                        dt2 = dt2 * fr2
+                    fr, dt = fr2, dt2
+                    bound_act = (fr == 0) & ~fixed
+                pg = pgfull * fr
+                slope = torch.dot(pg, dt)     # = grad . (nu*dt)
+                if not bool(torch.isfinite(slope)) or float(slope) >= 0.0:
+                    dt = -pg / pg.abs().max().clamp(min=1e-300)
+                if linear_solver == "dense":
+                    # (near-)singular system, e.g. every pool tying the free prices to a bound is saturated: keep the
+                    # direction, bound the step to a price factor of e^3 and let the line search find the kink
+                    big = float(dt.abs().max())
+                    if big > DT_MAX:
+                        dt = dt * (DT_MAX / big)
+                # ---- projected Armijo backtracking along nu * exp(alpha dt)
+                alpha = 1.0
+                g0 = float(g)
+                ok = False
+                for _ls in range(50):
+                    nu_t = torch.maximum(nu * torch.exp(torch.clamp(alpha * dt, -20.0, 20.0)), lb)
+                    nu_t = torch.where(fixed, c, nu_t)
+                    psi_t, g_t = G(nu_t)
+                    lin = float(torch.dot(grad, nu_t - nu))
+                    if _ls == 0:
+                        lin1 = lin             # predicted decrease of the FULL step
+                    gt = float(g_t)
+                    if gt <= g0 + 1e-4 * lin:
                         ok = True
                         break
-                    if alpha < 1e-3:
-                        break
-                alpha *= 0.5
+                    if abs(gt - g0) <= 1e-13 * abs(g0) or abs(lin1) <= 1e-9 * abs(g0):
+                        # the (full) step is below what g resolves in fp64 (g is a sum of cancelling flows: the Armijo
+                        # decrease 1e-4 |lin| would be under 1e-13 |g|): judge it by the KKT residual instead
+                        if kkt(nu_t, psi_t, g_t, err)[0] < 0.99 * err:
+                            ok = True
+                            break
+                        if alpha < 1e-3:
+                            break
+                    alpha *= 0.5
+                if ok or linear_solver != "dense" or rung_used[0] >= len(LM_SHIFTS) - 1:
+                    break
+                rung0 = rung_used[0] + 1
             if not ok:
                 inner_status = "stalled"
                 break

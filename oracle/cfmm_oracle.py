@@ -460,39 +460,48 @@ def solve(pools: Pools, util: Utility, nu0=None, tol=1e-9, eps=0.1, eps_min=1e-4
             # (near-)singular free-set systems (e.g. every pool tying some free prices to the rest is saturated) give an
             # enormous step along the null directions: damp the system (Levenberg-Marquardt, shift mu * mean diagonal)
             # until the step is a sane price change; the null directions then get a scaled gradient step
-            for mu in LM_SHIFTS:
-                try:
-                    dtf = np.linalg.solve(Hs + mu * dbar * np.eye(len(rhs)), rhs)
-                except np.linalg.LinAlgError:
-                    dtf = np.full(len(rhs), np.inf)
-                if np.all(np.isfinite(dtf)) and np.abs(dtf).max(initial=0.0) <= DT_MAX:
-                    break
-            dt = np.zeros(n); dt[free] = dtf
-            if not np.all(np.isfinite(dt)) or np.dot(pg, dt) >= 0:
-                dt = -pg / max(np.abs(pg).max(), 1e-300)
-            big = np.abs(dt).max()
-            if big > DT_MAX:        # still too long after the largest shift: keep the direction, bound the step
-                dt *= DT_MAX / big
-            alpha = 1.0
-            g0 = ev["g"]
-            ok = False
-            for _ls in range(50):
-                nu_t = np.maximum(nu * np.exp(np.clip(alpha * dt, -20, 20)), lb)
-                nu_t[fixed] = util.c[fixed]
-                ev_t = G(nu_t, want_hess=True)
-                lin = np.dot(grad, nu_t - nu)
-                if _ls == 0:
-                    lin1 = lin                 # predicted decrease of the FULL step
-                if ev_t["g"] <= g0 + 1e-4 * lin:
-                    ok = True
-                    break
-                if abs(ev_t["g"] - g0) <= 1e-13 * abs(g0) or abs(lin1) <= 1e-9 * abs(g0):   # g cannot resolve this step
-                    if kkt(nu_t, ev_t, err)[0] < 0.99 * err:
+            rung = 0
+            while True:
+                # climb the ladder from `rung` until the step is a sane price change
+                while True:
+                    try:
+                        dtf = np.linalg.solve(Hs + LM_SHIFTS[rung] * dbar * np.eye(len(rhs)), rhs)
+                    except np.linalg.LinAlgError:
+                        dtf = np.full(len(rhs), np.inf)
+                    if (np.all(np.isfinite(dtf)) and np.abs(dtf).max(initial=0.0) <= DT_MAX) or rung == len(LM_SHIFTS) - 1:
+                        break
+                    rung += 1
+                dt = np.zeros(n); dt[free] = dtf
+                if not np.all(np.isfinite(dt)) or np.dot(pg, dt) >= 0:
+                    dt = -pg / max(np.abs(pg).max(), 1e-300)
+                big = np.abs(dt).max()
+                if big > DT_MAX:        # still too long after the largest shift: keep the direction, bound the step
+                    dt *= DT_MAX / big
+                alpha = 1.0
+                g0 = ev["g"]
+                ok = False
+                for _ls in range(50):
+                    nu_t = np.maximum(nu * np.exp(np.clip(alpha * dt, -20, 20)), lb)
+                    nu_t[fixed] = util.c[fixed]
+                    ev_t = G(nu_t, want_hess=True)
+                    lin = np.dot(grad, nu_t - nu)
+                    if _ls == 0:
+                        lin1 = lin                 # predicted decrease of the FULL step
+                    if ev_t["g"] <= g0 + 1e-4 * lin:
                         ok = True
                         break
-                    if alpha < 1e-3:
-                        break
-                alpha *= 0.5
+                    if abs(ev_t["g"] - g0) <= 1e-13 * abs(g0) or abs(lin1) <= 1e-9 * abs(g0):   # g cannot resolve this step
+                        if kkt(nu_t, ev_t, err)[0] < 0.99 * err:
+                            ok = True
+                            break
+                        if alpha < 1e-3:
+                            break
+                    alpha *= 0.5
+                # a failed search along a barely damped direction (null-space dominated: long step, no predicted gain):
+                # damp harder and try again before giving up
+                if ok or rung == len(LM_SHIFTS) - 1:
+                    break
+                rung += 1
             if not ok:
                 inner_status = "stalled"
                 break
