@@ -14,4 +14,8 @@ for lanes in 1 32; do
   echo "== CFMM_BATCH_LANES=$lanes" >> gpurun_out/r2_batch_lanes.txt
   CFMM_BATCH_LANES=$lanes timeout 300 python scripts/time_batch.py >> gpurun_out/r2_batch_lanes.txt 2>&1
 done
-tail -5 gpurun_out/r2_pytest_gpu.txt; cat gpurun_out/r2_tiles.txt; grep -E '"ms"|LANES|B[0-9]+"' gpurun_out/r2_batch_lanes.txt | head -40
+for cfg in -1 400 1296; do          # the bench line itself with the default layout, planned tiles, tiles of 896
+  echo "== CFMM_BLOCKED_CFG=$cfg" >> gpurun_out/r2_bench_cfgs.txt
+  CFMM_BLOCKED_CFG=$cfg timeout 300 python bench.py --steps 16000 --no-cpu 2>/dev/null | cut -c1-600 >> gpurun_out/r2_bench_cfgs.txt
+done
+tail -5 gpurun_out/r2_pytest_gpu.txt; cat gpurun_out/r2_bench_cfgs.txt; cat gpurun_out/r2_tiles.txt; grep -E '"ms"|LANES|B[0-9]+"' gpurun_out/r2_batch_lanes.txt | head -40
