@@ -333,7 +333,10 @@ def build_blocked_pairs(idx: torch.Tensor, n_tokens: int, P: int, rows_stride: i
             break
         pos = torch.arange(mm, **i64)
         if planned:
-            sizes = torch.as_tensor(plan_tiles(mm, n_ctas, cap=cap_pools), **i64)
+            plan = plan_tiles(mm, n_ctas, cap=cap_pools)
+            if np.any(plan[:-1] % 4) or plan.max() > cap_pools or int(plan.sum()) != mm:
+                raise _lib.CfmmError("blocked layout: bad tile plan (sizes must be multiples of 4, <= the stage capacity)")
+            sizes = torch.as_tensor(plan, **i64)
             ntiles = int(sizes.numel())
             starts = torch.cumsum(sizes, 0) - sizes
             tile = torch.bucketize(pos, starts[1:].contiguous(), right=True)
