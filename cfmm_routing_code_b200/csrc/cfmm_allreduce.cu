@@ -19,8 +19,10 @@ constexpr int kArMaxCtas = 64;      // signal-pad slots reserved per channel: kA
 constexpr int kPadBase = 512;       // first signal-pad word we use (torch's own barriers live below)
 constexpr int kMaxWorld = 16;
 
-__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
-    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// release: orders this rank's partial vector (the pool kernels' red.adds, made visible to this grid by
+// griddepcontrol.wait) before the "ready" flag; pairs with the peer's ld.acquire.sys on its pad
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     uint32_t v;
@@ -45,7 +47,7 @@ k_allreduce_oneshot(const double* const* __restrict__ bufs, uint32_t* const* __r
     const int tid = threadIdx.x;
     const int slot0 = kPadBase + (channel * kArMaxCtas + blockIdx.x) * world;
     if (tid < world && tid != rank) {
-        st_relaxed_sys(pads[tid] + slot0 + rank, seq);                       // "my partial `seq` is ready"
+        st_release_sys(pads[tid] + slot0 + rank, seq);                       // "my partial `seq` is ready"
         const uint32_t* mine = pads[rank] + slot0 + tid;
         while ((int)(ld_acquire_sys(mine) - seq) < 0) { }                    // peer `tid` is ready too
     }

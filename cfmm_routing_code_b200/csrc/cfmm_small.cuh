@@ -254,7 +254,7 @@ CFMM_HD inline double kkt(const Problem& Q, const Vec& nu, const Vec& psi, const
                           const Vec& grad, const Vec& pg, uint64_t* free_mask) {
     const double ep = isfinite(err_prev) ? err_prev : 1e-2;
     const double thr = fmin(1e-2, fmax(ep, 1e-14));
-    double num = 0.0, wsum = 0.0;
+    double num = 0.0, wsum = 0.0, gmax = 0.0, scl = 0.0;
     uint64_t fm = 0;
     for (int j = 0; j < Q.n; ++j) {
         const double gr = Q.a[j] + psi[j];
@@ -265,9 +265,13 @@ CFMM_HD inline double kkt(const Problem& Q, const Vec& nu, const Vec& psi, const
         if (fr) fm |= (uint64_t)1 << j;
         num += fabs(v);
         wsum += nu[j] * fabs(gr);
+        if (fr) gmax = fmax(gmax, fabs(gr));
+        scl = fmax(scl, fmax(fabs(Q.a[j]), is_pinned(Q, j) ? 0.0 : fabs(psi[j])));   // scale: constrained flows only
     }
     *free_mask = fm;
-    return num / fmax(fmax(fabs(g), 1e-3 * wsum), TINY);
+    // max of the value-weighted residual and the per-token one (the reference constrains psi token by token,
+    // liquidation.py:77-80 / arbitrage.py:77: a cheap token must not hide a large residual behind its price)
+    return fmax(num / fmax(fmax(fabs(g), 1e-3 * wsum), TINY), gmax / fmax(scl, TINY));
 }
 
 // Solve (Hs[free,free] + mu dbar I) x = -pg[free] (dbar = mean diagonal) by Gaussian elimination with partial pivoting;
@@ -436,8 +440,7 @@ CFMM_HD inline Stats solve_one(const Pools& P, Problem Q, const Params& prm, dou
             cur = nxt; g = g_t;
             err = kkt(Q, nuv[cur], psiv[cur], lb, g, err, grad, pg, &free_mask);
         }
-        status = inner_status;
-        if (!has_sum) break;
+        if (!has_sum) { status = inner_status; break; }
         // exact duality gap at the current prices (trades from the smoothed problem, dual with eps = 0)
         evaluate<LANES>(P, Q, nuv[cur], lognu, eps_t, psiv[cur ^ 1], nullptr, false, true, lane);
         const double g_exact = dual_value(Q, nuv[cur], evaluate<LANES>(P, Q, nuv[cur], lognu, 0.0, grad_t, nullptr, false, false, lane));
@@ -445,7 +448,8 @@ CFMM_HD inline Stats solve_one(const Pools& P, Problem Q, const Params& prm, dou
         double primal = 0.0;
         for (int j = 0; j < n; ++j) primal += Q.c[j] * psiv[cur ^ 1][j];
         const double gap_now = (g_exact - primal) / fmax(fabs(g_exact), TINY);
-        if (inner_status == 0 && err <= prm.tol && fabs(gap_now) <= prm.tol) break;
+        if (inner_status == 0 && err <= prm.tol && fabs(gap_now) <= prm.tol) { status = 0; break; }   // the only certified exit
+        status = inner_status != 0 ? inner_status : 1;
         // the ramp cannot get narrower and the inner solve failed twice in a row: fp64 resolution of the price
         // ratio / eps bounds the reachable residual, more passes would not help
         if (inner_status != 0 && failed_before && eps_t <= prm.eps_min) break;

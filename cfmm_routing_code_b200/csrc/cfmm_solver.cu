@@ -59,7 +59,7 @@ struct Vecs {
 // KKT residual / free set at (nu, acc = [psi | arb]):  err = sum_free |nu (a+psi)| / max(|g|, 1e-3 nu'|grad|)
 __global__ void __launch_bounds__(kVT) k_kkt(Vecs V, const double* nu, const double* acc, double thr) {
     __shared__ double sh[33];
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, m0 = 0, m1 = 0;
     for (int j = threadIdx.x; j < V.n; j += kVT) {
         const double g = V.a[j] + acc[j];
         const bool near = (nu[j] <= V.lb[j] * (1.0 + thr)) && !V.eq[j];
@@ -74,13 +74,17 @@ __global__ void __launch_bounds__(kVT) k_kkt(Vecs V, const double* nu, const dou
         const double sl = acc[j] + V.a[j];
         const double viol = V.fixed[j] ? 0.0 : (V.eq[j] ? fabs(sl) : fmax(-sl, 0.0));
         s4 += nu[j] * viol;
+        m0 = fmax(m0, fabs(g) * f);                          // per-token residual on the free set
+        m1 = fmax(m1, fmax(fabs(V.a[j]), V.fixed[j] ? 0.0 : fabs(acc[j])));   // its scale: max(|a|_inf, constrained |psi_j|)
     }
     s0 = block_sum(s0, sh); s1 = block_sum(s1, sh); s2 = block_sum(s2, sh); s3 = block_sum(s3, sh);
     s4 = block_sum(s4, sh);
+    m0 = block_max(m0, sh); m1 = block_max(m1, sh);
     if (threadIdx.x == 0) {
         const double g = s1 + acc[V.n];
         V.sc[S_ABS_PG] = s0; V.sc[S_G] = g; V.sc[S_NU_ABS_GRAD] = s2; V.sc[S_ARB] = acc[V.n];
-        V.sc[S_ERR] = s0 / fmax(fmax(fabs(g), 1e-3 * s2), 1e-300);
+        // max of the value-weighted residual and the per-token one (liquidation.py:77-80 constrains psi token by token)
+        V.sc[S_ERR] = fmax(s0 / fmax(fmax(fabs(g), 1e-3 * s2), 1e-300), m0 / fmax(m1, 1e-300));
         V.sc[S_PRIMAL] = s3; V.sc[S_INFEAS] = s4 / fmax(fabs(g), 1e-300);
     }
 }
@@ -179,6 +183,12 @@ __global__ void __launch_bounds__(kVT) k_bounds(int n, const double* c, const un
 
 inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// slab stride of a blocked layout = what cfmm_blocked.cu's fill_args uses: n_tiles * P for fixed tiles, the pool count
+// rounded up to 4 for planned tiles (pools_per_tile == 0, sizes in the descriptors)
+inline size_t hcoef_stride(const cfmm_blocked_pairs* b) {
+    return b->pools_per_tile ? (size_t)b->n_tiles * (size_t)b->pools_per_tile : (((size_t)b->n_pools + 3) & ~(size_t)3);
+}
+
 }  // namespace
 
 extern "C" {
@@ -186,7 +196,7 @@ extern "C" {
 int64_t cfmm_blocked_solve_work_bytes(const cfmm_blocked_pairs* b, int32_t n_tokens) {
     if (!b || n_tokens <= 0) return CFMM_E_SIZE;
     const size_t n = (size_t)n_tokens;
-    const size_t M = (size_t)b->n_tiles * (size_t)b->pools_per_tile;
+    const size_t M = hcoef_stride(b);
     size_t bytes = 0;
     bytes += align_up(8 * M);                 // hcoef
     bytes += 2 * align_up(8 * (n + 1));       // [psi | arb] ping-pong
@@ -203,7 +213,7 @@ int cfmm_blocked_solve(const cfmm_blocked_pairs* b, int32_t n_tokens, const doub
     if (n_tokens <= 0 || b->n_tiles <= 0) return CFMM_E_SIZE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int n = n_tokens;
-    const size_t M = (size_t)b->n_tiles * (size_t)b->pools_per_tile;
+    const size_t M = hcoef_stride(b);
     // ---- carve the work buffer
     unsigned char* w = static_cast<unsigned char*>(work);
     auto take = [&](size_t bytes) { unsigned char* p = w; w += align_up(bytes); return p; };
@@ -285,7 +295,7 @@ int cfmm_blocked_solve(const cfmm_blocked_pairs* b, int32_t n_tokens, const doub
         k_direction<<<1, kVT, 0, st>>>(V);
         // ---- projected Armijo backtracking along nu * exp(alpha dt); the KKT data of the trial point is computed
         // speculatively behind it, so an accepted step (the rule) costs one synchronisation
-        double alpha = 1.0;
+        double alpha = 1.0, lin1 = 0.0;
         bool ok = false;
         for (int ls = 0; ls < 50; ++ls) {
             k_step<<<1, kVT, 0, st>>>(V, cur_nu, alpha, oth_nu);
@@ -295,11 +305,13 @@ int cfmm_blocked_solve(const cfmm_blocked_pairs* b, int32_t n_tokens, const doub
             k_kkt<<<1, kVT, 0, st>>>(V, oth_nu, acct, thr);
             if (!fetch()) return CFMM_E_CUDA;
             const double gt = hsc[S_GT], lin = hsc[S_LIN];
+            if (ls == 0) lin1 = lin;                 // predicted decrease of the FULL step
             if (gt <= g0 + 1e-4 * lin) { ok = true; cur_acc = acct; break; }
-            if (fabs(gt - g0) <= 1e-13 * fabs(g0)) {
-                // below the resolution of g: accept if the KKT residual improves, else give up (stalled)
-                if (hsc[S_ERR] < err) { ok = true; cur_acc = acct; }
-                break;
+            if (fabs(gt - g0) <= 1e-13 * fabs(g0) || fabs(lin1) <= 1e-9 * fabs(g0)) {
+                // the (full) step is below what g resolves in fp64 (a sum of cancelling flows): judge it by the KKT
+                // residual instead (same rule as solver.py)
+                if (hsc[S_ERR] < 0.99 * err) { ok = true; cur_acc = acct; break; }
+                if (alpha < 1e-3) break;
             }
             // rejected: the gradient buffers now belong to the trial -- restore them at the current point
             cur_acc = eval(cur_nu);

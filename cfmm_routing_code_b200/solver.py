@@ -115,6 +115,8 @@ def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 0.1
         # evaluator in the tests), not where a 1000 x 1000 Cholesky costs more than a pool pass (measured on cfg3)
         lookahead = 3 if (n <= 64 or dev.type == "cpu") else 0
     evals0, hvps0 = ev.evals, ev.hvps
+    a_inf = float(np.abs(np.asarray(spec.a, float)).max())
+    notfixed = (~fixed).to(torch.float64)
     history = []
     internal = bool(getattr(ev, "reduces_internally", False))     # PoolStore.enable_peer_allreduce(): no NCCL needed
 
@@ -127,14 +129,21 @@ def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 0.1
         return psi, g
 
     def kkt(nu_, psi_, g_, err_prev):
-        """free set + scaled KKT residual: sum_free |nu_j (a_j+psi_j)| / |g|  (bounds gap AND infeasibility)."""
+        """free set + KKT residual = max of
+          * value-weighted: sum_free |nu_j (a_j+psi_j)| / |g|  (bounds the relative gap and the value of the infeasibility)
+          * per token:      max_free |a_j+psi_j| / max(|a|_inf, max over the CONSTRAINED tokens |psi_j|)  -- the reference
+            enforces psi_j + a_j == 0 / complementarity token by token (liquidation.py:77-80, arbitrage.py:77), so a
+            cheap token must not hide a large residual behind its small price, nor behind the (unconstrained,
+            objective-only) output of the target token."""
         grad_ = a + psi_
         thr = min(1e-2, max(err_prev if np.isfinite(err_prev) else 1e-2, 1e-14))
         near = (nu_ <= lb * (1.0 + thr)) & ~eq
         fr_ = (~(fixed | (near & (grad_ > 0)))).to(torch.float64)
         pg_ = nu_ * grad_ * fr_
-        st = torch.stack([pg_.abs().sum(), g_.abs(), torch.dot(nu_, grad_.abs())]).tolist()
-        return st[0] / max(st[1], 1e-3 * st[2], 1e-300), grad_, fr_, pg_
+        st = torch.stack([pg_.abs().sum(), g_.abs(), torch.dot(nu_, grad_.abs()), (grad_ * fr_).abs().max(),
+                          (psi_ * notfixed).abs().max()]).tolist()
+        feas = st[3] / max(a_inf, st[4], 1e-300)
+        return max(st[0] / max(st[1], 1e-3 * st[2], 1e-300), feas), grad_, fr_, pg_
 
     iters = 0
     status = "max_iter"
@@ -254,8 +263,8 @@ def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 0.1
                 break
             nu, psi, g = nu_t, psi_t, g_t
             err, grad, fr, pg = kkt(nu, psi, g, err)
-        status = inner_status
         if not has_sum:
+            status = inner_status
             break
         # method of multipliers.  The smoothed trades are pool-feasible, so (exact dual - primal) at this nu
         # is a true optimality certificate; stop on it rather than on the multiplier step, whose floor is
@@ -268,7 +277,10 @@ def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 0.1
         if verbose:
             print(f"outer {outer}: eps {eps_t:.1e} last move {move:.3e} gap {gap_now:.3e}")
         if inner_status == "optimal" and err <= tol and abs(gap_now) <= tol:
+            status = "optimal"      # the only certified exit: KKT residual AND exact duality gap within tol
             break           # multipliers stay as they are: the read-back below reproduces psi_s
+        # not certified (loose inner tolerance, or multipliers / ramp still moving): falling out of the loop is 'max_iter'
+        status = inner_status if inner_status != "optimal" else "max_iter"
         if inner_status != "optimal" and failed_before and eps_t <= float(eps_min):
             break           # ramp at its narrowest, two failed passes: residual is at the fp64 floor (ratio / eps)
         failed_before = inner_status != "optimal"

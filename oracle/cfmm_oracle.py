@@ -430,14 +430,21 @@ def solve(pools: Pools, util: Utility, nu0=None, tol=1e-9, eps=0.1, eps_min=1e-4
         ev["g"] = dual_value(util, nu_, ev["arb"])
         return ev
 
+    a_inf = float(np.abs(util.a).max(initial=0.0))
+
     def kkt(nu_, ev_, err_prev):
+        """max of the value-weighted residual sum_free |nu_j (a_j+psi_j)| / |g| and the per-token one
+        max_free |a_j+psi_j| / max(|a|_inf, max over constrained tokens |psi_j|): the reference constrains psi token
+        by token (liquidation.py:77-80, arbitrage.py:77), so a cheap token must not hide a large residual (nor may
+        the unconstrained output of an objective-only token set the scale)."""
         grad = util.a + ev_["psi"]
         thr = min(1e-2, max(err_prev if np.isfinite(err_prev) else 1e-2, 1e-14))
         near = (nu_ <= lb * (1 + thr)) & ~util.eq
         free = ~(fixed | (near & (grad > 0)))
         pg = np.where(free, nu_ * grad, 0.0)
         den = max(abs(ev_["g"]), 1e-3 * np.dot(nu_, np.abs(grad)), 1e-300)
-        return np.abs(pg).sum() / den, grad, free, pg
+        feas = np.abs(np.where(free, grad, 0.0)).max(initial=0.0) / max(a_inf, np.abs(np.where(fixed, 0.0, ev_["psi"])).max(initial=0.0), 1e-300)
+        return max(np.abs(pg).sum() / den, feas), grad, free, pg
 
     err = np.inf
     move = 1.0
@@ -507,8 +514,8 @@ def solve(pools: Pools, util: Utility, nu0=None, tol=1e-9, eps=0.1, eps_min=1e-4
                 break
             nu, ev = nu_t, ev_t
             err, grad, free, pg = kkt(nu, ev, err)
-        status = inner_status
         if not sum_groups:
+            status = inner_status
             break
         fin = G(nu, want_trades=True)
         exact = G(nu, 0.0)
@@ -516,7 +523,9 @@ def solve(pools: Pools, util: Utility, nu0=None, tol=1e-9, eps=0.1, eps_min=1e-4
         if verbose:
             print(f"outer={outer} eps={eps_t:.1e} last move={move:.3e} gap={gap_now:.3e}")
         if inner_status == "optimal" and err <= tol and abs(gap_now) <= tol:
+            status = "optimal"          # the only certified exit
             break
+        status = inner_status if inner_status != "optimal" else "max_iter"
         if inner_status != "optimal" and failed_before and eps_t <= eps_min:
             break       # ramp at its narrowest and two failed passes: the residual sits at the fp64 floor (ratio / eps)
         failed_before = inner_status != "optimal"

@@ -277,10 +277,6 @@ def test_python_plumbing_of_batch_entry_points_with_the_host_build(monkeypatch, 
 
 
 # ------------------------------------------------------------------------------------------------- GPU (the product)
-FIRST_RUN = pytest.mark.xfail(strict=False, reason="written after this round's GPU budget was spent: logic covered on CPU by the host "
-                             "build / stand-in tests above, this is the first run on hardware (must not abort the suite under -x)")
-
-
 def _to_api(u):
     class _U:
         def spec(self, n):
@@ -355,7 +351,6 @@ def test_batch_kernel_rejects_what_it_does_not_cover():
 
 
 @pytest.mark.gpu
-@FIRST_RUN
 def test_solve_many_independent_problems_in_one_launch():
     probs = _many_problems() * 40            # 160 problems, four shapes
     rs = cf.solve_many(probs, tol=1e-9)
@@ -372,7 +367,6 @@ def test_solve_many_independent_problems_in_one_launch():
 
 
 @pytest.mark.gpu
-@FIRST_RUN
 def test_batch_kernel_bounded_product_pools_match_oracle():
     hp, specs = _v3_cases()
     rs = cf.solve_batch(hp, [_to_api(u) for u in specs], tol=1e-9)
@@ -393,8 +387,6 @@ def test_batch_kernel_bounded_product_pools_match_oracle():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="warp-per-problem variant (cfmm_set_batch_lanes(32)) was written after this round's GPU "
-                                        "budget was spent: off by default, this is its first run on hardware")
 def test_warp_per_problem_variant_matches_thread_per_problem():
     import torch
     from cfmm_routing_code_b200 import batch as B

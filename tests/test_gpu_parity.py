@@ -64,8 +64,6 @@ def test_blocked_product_eval_matches_oracle(m, n):
     assert any(getattr(b, "blocked", False) for b in st.buckets)
 
 
-@pytest.mark.xfail(strict=False, reason="alternative / runtime tile sizes (cfmm_set_blocked_config(400 + P | 400)) were added after this "
-                                        "round's GPU budget was spent: off by default, first run on hardware")
 @pytest.mark.parametrize("tile_pools", [960, 896, 0])
 def test_blocked_kernels_with_smaller_tiles_match_oracle(tile_pools):
     lib = _lib.load()
@@ -131,11 +129,6 @@ def test_mixed_eval_matches_oracle(eps):
     _check_eval(hp, H.random_prices(s["prices"], 3, 0.03), eps=eps, theta=theta)
 
 
-FIRST_RUN = pytest.mark.xfail(strict=False, reason="written after this round's GPU budget was spent: logic covered on CPU "
-                             "(tests/test_batch.py, tests/test_host_logic.py), first run on hardware (must not abort the suite under -x)")
-
-
-@FIRST_RUN
 def test_bounded_product_bucket_matches_oracle():
     """the bounded-liquidity product (v3 tick range) in the pool-parallel path: trades, psi, arb and the scaled
     Hessian of one evaluation, in range / at the payout cap / out of range, alone and next to every other kind"""
@@ -155,7 +148,6 @@ def test_bounded_product_bucket_matches_oracle():
                                    atol=1e-10 * max(np.abs(Hs).max(), 1e-300))
 
 
-@FIRST_RUN
 def test_random_small_problems_of_every_kind_through_the_pool_parallel_path():
     rng = np.random.default_rng(23)
     for _ in range(5):
@@ -195,7 +187,7 @@ def test_hessian_products_match_oracle():
     np.testing.assert_allclose(st.hvp(torch.as_tensor(v, **F64)).cpu().numpy(), Hs @ v, atol=1e-10 * scale)
 
 
-@pytest.mark.parametrize("method", ["pools", pytest.param("thread", marks=FIRST_RUN), pytest.param("auto", marks=FIRST_RUN)])
+@pytest.mark.parametrize("method", ["pools", "thread", "auto"])
 def test_reference_instances_end_to_end(golden, method):
     """the three scripts' instances through the pool-parallel kernels under the outer loop ('pools') and through the
     one-thread-per-problem solver ('thread', what 'auto' picks at this size)"""

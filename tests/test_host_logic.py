@@ -53,6 +53,19 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
     assert lib.cfmm_batch_solve(ctypes.byref(cp), ctypes.byref(bt), ctypes.byref(prm), None, None) == -1
 
 
+def test_native_solver_work_buffer_covers_the_hcoef_slab_of_every_tile_layout():
+    """cfmm_blocked_solve carves an hcoef slab of the layout's slab stride from the caller's work buffer: n_tiles * P for
+    fixed tiles, ceil4(n_pools) for planned tiles (pools_per_tile == 0) -- a stride of 0 there once aliased hcoef with
+    the psi buffers (8 MB of device writes past a 0.5 MB buffer at 1M pools)."""
+    lib = _lib.load()
+    n = 4096
+    for m, tiles, P in ((1_000_000, 977, 1024), (1_000_000, 1117, 896), (1_000_000, 1480, 0), (1001, 4, 0)):
+        b = _lib.BlockedPairs(m, tiles, P, 0, None, None, None, None, None, None, None, None)
+        stride = tiles * P if P else (m + 3) // 4 * 4
+        need = lib.cfmm_blocked_solve_work_bytes(ctypes.byref(b), n)
+        assert need >= 8 * stride + 8 * (2 * (n + 1) + 15 * n), (m, tiles, P, need)
+
+
 def test_product_path_fails_loudly_without_a_gpu():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
@@ -87,6 +100,46 @@ def test_solver_logic_on_synthetic_mixed_pools_certifies_its_answer():
     hp, s = H.mixed_host_pools(3000, 60, seed=4)
     r = solve_dual(OracleEvaluator(hp), cf.Arbitrage(s["prices"]).spec(60), tol=1e-8)
     assert r.status == "optimal" and abs(r.gap) <= 1e-7 and r.primal_infeas <= 1e-7
+
+
+# ---- CPU twins of the solve-level GPU parity tests (tests/test_gpu_parity.py): same instances, same assertions, the
+# product's outer loop over the CPU stand-in evaluator -- a regression in the outer loop shows up here, without a GPU
+def test_cpu_twin_cfg2_solve_matches_oracle():
+    hp, s = H.cp_host_pools(10_000, 256, seed=0)
+    for ls in ("cg", "dense"):
+        r = solve_dual(OracleEvaluator(hp), cf.Arbitrage(s["prices"]).spec(256), tol=1e-9, linear_solver=ls)
+        ro = O.solve(H.oracle_pools(hp), O.Utility.arbitrage(s["prices"]), tol=1e-10)
+        assert r.status == "optimal" and ro.status == "optimal"
+        assert abs(r.primal_value - ro.value) <= 1e-8 * abs(ro.value)
+        assert abs(r.gap) <= 1e-8 and r.primal_infeas <= 1e-8
+        gross = np.zeros(256); np.add.at(gross, hp.tok_idx, np.concatenate(ro.deltas) + np.concatenate(ro.lambdas))
+        assert np.max(np.abs(r.psi.numpy() - ro.psi) / gross.max()) <= 1e-7
+
+
+def test_cpu_twin_cfg3_small_mixed_solve_matches_oracle():
+    hp, s = H.mixed_host_pools(8000, 150, seed=1)
+    r = solve_dual(OracleEvaluator(hp), cf.Arbitrage(s["prices"]).spec(150), tol=1e-8)
+    ro = O.solve(H.oracle_pools(hp), O.Utility.arbitrage(s["prices"]), tol=1e-9)
+    assert r.status == "optimal"
+    assert abs(r.primal_value - ro.value) <= 1e-6 * abs(ro.value)
+    assert abs(r.gap) <= 1e-6 and r.primal_infeas <= 1e-6
+    # per-token complementarity (arbitrage.py:77): psi >= 0 to 1e-6 of the largest flow
+    assert r.psi.numpy().min() >= -1e-6 * np.abs(ro.psi).max()
+
+
+def test_cpu_twin_cfg4_small_liquidation_matches_oracle():
+    """the case that failed on the B200 in round 1: 'optimal' at tol 1e-8 with one cheap token's equality off by 6.3e-5"""
+    hp, s = H.mixed_host_pools(8000, 150, seed=2)
+    basket = I.synth_basket(150, s["prices"], seed=2)
+    nu0 = s["prices"] / s["prices"][0]
+    r = solve_dual(OracleEvaluator(hp), cf.Liquidate(0, basket).spec(150), nu0=nu0, tol=1e-8)
+    ro = O.solve(H.oracle_pools(hp), O.Utility.liquidate(150, 0, basket), nu0=nu0, tol=1e-9)
+    assert r.status == "optimal"
+    assert abs(r.primal_value - ro.value) <= 1e-6 * abs(ro.value)
+    # liquidation.py:77-80: psi_j + a_j == 0 token by token, to 1e-6 of the basket scale (in fact to ~tol)
+    np.testing.assert_allclose(r.psi.numpy()[1:], -basket[1:], atol=1e-6 * basket.max())
+    np.testing.assert_allclose(ro.psi[1:], -basket[1:], atol=1e-6 * basket.max())
+    assert np.abs(r.psi.numpy()[1:] + basket[1:]).max() <= 1e-7 * basket.max()
 
 
 def test_solver_logic_on_random_small_problems_matches_the_oracle():
