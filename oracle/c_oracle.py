@@ -23,7 +23,43 @@ def load():
         _lib.oracle_hess_pairs.restype = C.c_int
         _lib.oracle_hess_pairs.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int]
         _lib.oracle_num_threads.restype = C.c_int
+        _lib.oracle_solve_pairs.restype = C.c_int
+        _lib.oracle_solve_pairs.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_int32,
+                                            C.POINTER(SolveResult)]
     return _lib
+
+
+class SolveResult(C.Structure):
+    _fields_ = [("dual_value", C.c_double), ("primal_value", C.c_double), ("gap", C.c_double),
+                ("primal_infeas", C.c_double), ("err", C.c_double), ("wall_s", C.c_double), ("iters", C.c_int32),
+                ("evals", C.c_int32), ("hvps", C.c_int32), ("status", C.c_int32)]
+
+
+def solve_pairs(idx, R, gamma, n_tokens, c, a=None, eq=None, pinned=None, nu0=None, tol=1e-8, max_iter=100, cg_max=200):
+    """oracle_solve_pairs: the whole dual solve of a constant-product problem in C (projected Newton-PCG, persistent
+    pthread pool): the CPU arm of bench.py.  Returns (nu, psi, SolveResult)."""
+    lib = load()
+    idx = np.ascontiguousarray(idx, np.int32); R = np.ascontiguousarray(R, np.float64)
+    gamma = np.ascontiguousarray(gamma, np.float64)
+    n = int(n_tokens)
+    c = np.ascontiguousarray(c, np.float64)
+    a = np.zeros(n) if a is None else np.ascontiguousarray(a, np.float64)
+    eq = np.zeros(n, np.uint8) if eq is None else np.ascontiguousarray(eq, np.uint8)
+    pinned = np.zeros(n, np.uint8) if pinned is None else np.ascontiguousarray(pinned, np.uint8)
+    if nu0 is None:
+        pos = c[c > 0]
+        nu = np.where(c > 0, c, np.median(pos) if len(pos) else 1.0).astype(np.float64)
+    else:
+        nu = np.array(nu0, np.float64)
+    psi = np.empty(n)
+    res = SolveResult()
+    rc = lib.oracle_solve_pairs(len(gamma), idx.ctypes.data, R.ctypes.data, gamma.ctypes.data, n, c.ctypes.data,
+                                a.ctypes.data, eq.ctypes.data, pinned.ctypes.data, nu.ctypes.data, psi.ctypes.data,
+                                float(tol), int(max_iter), int(cg_max), C.byref(res))
+    if rc:
+        raise MemoryError("oracle_solve_pairs")
+    return nu, psi, res
 
 
 def num_threads():

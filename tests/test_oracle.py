@@ -151,6 +151,27 @@ def test_c_restatement_matches_numpy_oracle():
     assert CO.num_threads() >= 1
 
 
+def test_c_solve_matches_numpy_oracle_solve():
+    """oracle_solve_pairs (the CPU arm's whole solve: Newton-PCG in C over the persistent pthread pool) vs O.solve"""
+    from oracle import c_oracle as CO
+    hp, s = H.cp_host_pools(10_000, 256, seed=0)
+    idx, R = hp.tok_idx.reshape(-1, 2), hp.reserves.reshape(-1, 2)
+    ro = O.solve(H.oracle_pools(hp), O.Utility.arbitrage(s["prices"]), tol=1e-10)
+    for nt in (1, 3):                   # the pool is rebuilt when the thread count changes
+        CO.set_threads(nt)
+        nu, psi, res = CO.solve_pairs(idx, R, hp.gamma, 256, s["prices"], tol=1e-9)
+        assert res.status == 0 and abs(res.primal_value - ro.value) <= 1e-8 * abs(ro.value)
+        assert abs(res.gap) <= 1e-8 and res.primal_infeas <= 1e-8
+        np.testing.assert_allclose(nu, ro.nu, rtol=1e-6)
+    basket = I.synth_basket(256, s["prices"], seed=2)
+    u = O.Utility.liquidate(256, 0, basket)
+    nu0 = s["prices"] / s["prices"][0]
+    ro = O.solve(H.oracle_pools(hp), u, nu0=nu0, tol=1e-10)
+    nu, psi, res = CO.solve_pairs(idx, R, hp.gamma, 256, u.c, u.a, u.eq, u.pinned, nu0=nu0, tol=1e-9)
+    assert res.status == 0 and abs(res.primal_value - ro.value) <= 1e-7 * abs(ro.value)
+    np.testing.assert_allclose(psi[1:], -basket[1:], atol=1e-7 * basket.max())
+
+
 # ---- property tests (SURVEY section 4, item 4): random pools / prices, invariants of the per-pool solutions -------
 from hypothesis import given, settings, strategies as st
 
