@@ -57,6 +57,11 @@ class PeerLL(C.Structure):
                 ("rank", C.c_int32), ("world", C.c_int32)]
 
 
+class PeerCtx(C.Structure):
+    _fields_ = [("recv_acc_dev", C.c_void_p), ("recv_vec_dev", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32),
+                ("seq_acc", C.c_uint64), ("seq_vec", C.c_uint64)]
+
+
 class CsrPools(C.Structure):
     _fields_ = [("n_tokens", C.c_int32), ("n_pools", C.c_int64), ("nnz", C.c_int64), ("pool_ptr", C.c_void_p),
                 ("tok_idx", C.c_void_p), ("reserves", C.c_void_p), ("weights", C.c_void_p), ("logrw", C.c_void_p),
@@ -129,6 +134,9 @@ def load(build_if_missing: bool = True):
     lib.cfmm_blocked_solve.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp, vp, vp, vp, vp,
                                        C.POINTER(SolveParams), C.POINTER(SolveResult), vp]
     lib.cfmm_blocked_solve.restype = C.c_int
+    lib.cfmm_blocked_solve_peer.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp, vp, vp, vp, vp,
+                                            C.POINTER(SolveParams), C.POINTER(SolveResult), C.POINTER(PeerCtx), vp]
+    lib.cfmm_blocked_solve_peer.restype = C.c_int
     lib.cfmm_batch_solve_work_bytes.argtypes = [C.POINTER(CsrPools), i32, i64]
     lib.cfmm_batch_solve_work_bytes.restype = i64
     lib.cfmm_set_batch_lanes.argtypes = [i32]

@@ -122,8 +122,24 @@ def _small_applicable(hp: HostPools, comm: Comm, verbose, solver_kw) -> bool:
 
 
 def _native_applicable(store: PoolStore, comm: Comm, solver_kw) -> bool:
-    return (comm.dist is None and len(store.buckets) == 1 and getattr(store.buckets[0], "blocked", False)
+    """one blocked constant-product bucket (per rank); pool-sharded runs need the NVLink peer context"""
+    return ((comm.dist is None or getattr(store, "reduces_internally", False))
+            and len(store.buckets) == 1 and getattr(store.buckets[0], "blocked", False)
             and solver_kw.get("linear_solver", "auto") in ("auto", "cg") and not solver_kw.get("verbose"))
+
+
+def _enable_peer(store: PoolStore, comm: Comm) -> None:
+    """world > 1: switch the store to the in-kernel NVLink all-reduce when symmetric memory is available (collective:
+    every rank reaches the same decision because availability is a property of the node)"""
+    if comm.dist is None or getattr(store, "reduces_internally", False) or store.device.type != "cuda":
+        return
+    if comm.dist.get_backend() != "nccl" or store.n_tokens + 1 > 64 * 256:
+        return
+    try:
+        store.enable_peer_allreduce()
+    except Exception as e:                      # no symmetric memory / no peer access: NCCL keeps doing the all-reduce
+        import warnings
+        warnings.warn(f"peer all-reduce unavailable ({type(e).__name__}: {e}); using torch.distributed all_reduce")
 
 
 def _solve_native(store: PoolStore, spec, nu0, tol, max_iter, cg_max=200) -> SolveInfo:
@@ -150,9 +166,13 @@ def _solve_native(store: PoolStore, spec, nu0, tol, max_iter, cg_max=200) -> Sol
     prm = _lib.SolveParams(float(tol), 1e-12 * scale, int(max_iter), int(cg_max))
     res = _lib.SolveResult()
     st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    rc = store.lib.cfmm_blocked_solve(C.byref(b.c_blocked), n, c.data_ptr(), a.data_ptr(), eq.data_ptr(),
-                                      pinned.data_ptr(), nu.data_ptr(), psi.data_ptr(), store._solve_work.data_ptr(),
-                                      C.byref(prm), C.byref(res), st)
+    peer = getattr(store, "_peer", None) if getattr(store, "reduces_internally", False) else None
+    pc = peer.c_struct() if peer is not None else None
+    rc = store.lib.cfmm_blocked_solve_peer(C.byref(b.c_blocked), n, c.data_ptr(), a.data_ptr(), eq.data_ptr(),
+                                           pinned.data_ptr(), nu.data_ptr(), psi.data_ptr(), store._solve_work.data_ptr(),
+                                           C.byref(prm), C.byref(res), C.byref(pc) if pc is not None else None, st)
+    if pc is not None:
+        peer.absorb(pc)                 # the reductions of this solve advanced the shared sequence numbers
     _lib.check(rc, "cfmm_blocked_solve")
     store.evals += res.evals
     store.hvps += res.hvps
@@ -183,6 +203,10 @@ def solve_pools(hp: HostPools, utility, nu0=None, tol: float = 1e-8, max_iter: i
         rank = comm.dist.get_rank() if comm.dist is not None else 0
         world = comm.dist.get_world_size() if comm.dist is not None else 1
         store = PoolStore(hp, device=device, rank=rank, world=world)
+    if store.world > 1:
+        _enable_peer(store, comm)
+    else:
+        comm = Comm(enabled=False)          # an unsharded store under an initialised process group: nothing to reduce
     spec = utility.spec(hp.n_tokens)
     if native and not verbose and _native_applicable(store, comm, solver_kw):
         info = _solve_native(store, spec, nu0, tol, max_iter, solver_kw.get("cg_max", 200))

@@ -201,16 +201,25 @@ int64_t cfmm_blocked_solve_work_bytes(const cfmm_blocked_pairs* b, int32_t n_tok
     bytes += align_up(8 * M);                 // hcoef
     bytes += 2 * align_up(8 * (n + 1));       // [psi | arb] ping-pong
     bytes += 2 * align_up(8 * n);             // y ping-pong
-    bytes += 13 * align_up(8 * n);            // nut, lb, grad, fr, pg, dt, x, r, z, p, minv, diag, spare
+    bytes += 13 * align_up(8 * n);            // nut, lb, grad, fr, pg, dt, x, r, z, p, minv, diag, spare (sharded: local diag)
     bytes += align_up(8 * S_COUNT);
+    bytes += 2 * align_up(8 * (n + 1)) + align_up(8 * n);      // sharded solve: all-reduced [psi | arb] ping-pong, reduced y
     return (int64_t)bytes;
 }
 
 int cfmm_blocked_solve(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* c, const double* a,
                        const uint8_t* eq, const uint8_t* pinned, double* nu, double* psi_out, void* work,
                        const cfmm_solve_params* prm, cfmm_solve_result* res, void* stream) {
+    return cfmm_blocked_solve_peer(b, n_tokens, c, a, eq, pinned, nu, psi_out, work, prm, res, nullptr, stream);
+}
+
+int cfmm_blocked_solve_peer(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* c, const double* a,
+                            const uint8_t* eq, const uint8_t* pinned, double* nu, double* psi_out, void* work,
+                            const cfmm_solve_params* prm, cfmm_solve_result* res, cfmm_peer_ctx* peer, void* stream) {
     if (!b || !c || !a || !eq || !pinned || !nu || !psi_out || !work || !prm || !res) return CFMM_E_NULL;
     if (n_tokens <= 0 || b->n_tiles <= 0) return CFMM_E_SIZE;
+    if (peer && (!peer->recv_acc_dev || !peer->recv_vec_dev)) return CFMM_E_NULL;
+    if (peer && (peer->world < 2 || peer->world > 16 || peer->rank < 0 || peer->rank >= peer->world)) return CFMM_E_SIZE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int n = n_tokens;
     const size_t M = hcoef_stride(b);
@@ -229,8 +238,17 @@ int cfmm_blocked_solve(const cfmm_blocked_pairs* b, int32_t n_tokens, const doub
     V.x = reinterpret_cast<double*>(take(8 * n)); V.r = reinterpret_cast<double*>(take(8 * n));
     V.z = reinterpret_cast<double*>(take(8 * n)); V.p = reinterpret_cast<double*>(take(8 * n));
     V.minv = reinterpret_cast<double*>(take(8 * n)); V.diag = reinterpret_cast<double*>(take(8 * n));
-    take(8 * n);
+    double* diag_loc = reinterpret_cast<double*>(take(8 * n));      // sharded: this rank's partial diagonal
     V.sc = reinterpret_cast<double*>(take(8 * S_COUNT));
+    double* red[2] = {reinterpret_cast<double*>(take(8 * (n + 1))), reinterpret_cast<double*>(take(8 * (n + 1)))};
+    double* yred = reinterpret_cast<double*>(take(8 * n));
+    // sharded: all-reduce `local` (len doubles) into `out` on channel 0 ([psi | arb]) or 1 (n-vectors)
+    auto reduce = [&](int chan, const double* local, int len, double* out) -> int {
+        uint64_t& seq = chan == 0 ? peer->seq_acc : peer->seq_vec;
+        ++seq;
+        return cfmm_allreduce_ll(local, chan == 0 ? peer->recv_acc_dev : peer->recv_vec_dev, peer->rank, peer->world, len,
+                                 (int64_t)(seq % 3) * peer->world * len, len, out, seq, st);
+    };
 
     static thread_local double* hsc = nullptr;          // pinned mirror of the scalar slots
     if (!hsc && cudaHostAlloc(&hsc, 8 * S_COUNT, cudaHostAllocDefault) != cudaSuccess) return CFMM_E_CUDA;
@@ -252,6 +270,10 @@ int cfmm_blocked_solve(const cfmm_blocked_pairs* b, int32_t n_tokens, const doub
         ai ^= 1;
         rc = cfmm_blocked_eval(b, n, x, cur, cur + n, &out, nxt, n + 1, st);
         ++evals;
+        if (peer && !rc) {                       // every rank continues with the sum over the shards
+            rc = reduce(0, cur, n + 1, red[ai]);
+            return red[ai];
+        }
         return cur;
     };
     double* cur_nu = nu;           // the caller's buffer and `nut` swap roles as steps are accepted
@@ -273,8 +295,10 @@ int cfmm_blocked_solve(const cfmm_blocked_pairs* b, int32_t n_tokens, const doub
         const double g0 = hsc[S_G];
         if (err <= prm->tol) { status = 0; break; }
         // ---- Newton direction: Jacobi-PCG on Hs dt = -(nu * grad) over the free set
-        cudaMemsetAsync(V.diag, 0, 8 * n, st);
-        rc = cfmm_blocked_diag(b, n, hcoef, V.diag, st);
+        double* dg = peer ? diag_loc : V.diag;
+        cudaMemsetAsync(dg, 0, 8 * n, st);
+        rc = cfmm_blocked_diag(b, n, hcoef, dg, st);
+        if (!rc && peer) rc = reduce(1, dg, n, V.diag);
         if (rc) return rc;
         k_cg_init<<<1, kVT, 0, st>>>(V);
         const double eta = fmin(0.1, sqrt(err));
@@ -285,6 +309,7 @@ int cfmm_blocked_solve(const cfmm_blocked_pairs* b, int32_t n_tokens, const doub
                 double* ynx = yb[yi ^ 1];
                 yi ^= 1;
                 rc = cfmm_blocked_hvp(b, n, hcoef, V.p, y, ynx, st);
+                if (!rc && peer) { rc = reduce(1, y, n, yred); y = yred; }
                 if (rc) return rc;
                 ++hvps;
                 k_cg_step<<<1, kVT, 0, st>>>(V, y, eta, k == 0);

@@ -111,19 +111,24 @@ class BucketSpec:
     """Which pools of a HostPools form one bucket.  `sel` = global pool indices (None = all pools, in order,
     the fast path for constant-product-only problems: no host-side gathers at all)."""
 
-    def __init__(self, hp: HostPools, kind: int, arity: int, sel: Optional[np.ndarray]):
+    def __init__(self, hp: HostPools, kind: int, arity: int, sel: Optional[np.ndarray], lo: int = 0,
+                 hi: Optional[int] = None):
         self.hp, self.kind, self.arity, self._sel = hp, kind, arity, sel
-        self.m = hp.m if sel is None else int(len(sel))
+        # sel is None: the contiguous block [lo, hi) of the pool list in its own order (a rank's shard, or everything)
+        self.lo, self.hi = int(lo), int(hp.m if hi is None else hi)
+        self._contiguous = sel is None
+        self.m = (self.hi - self.lo) if sel is None else int(len(sel))
         self._off = None
 
     @property
     def identity(self) -> bool:
-        return self._sel is None
+        """pools [lo, hi) in order: the raw host arrays are uploaded as they are and reordered on the GPU"""
+        return self._contiguous
 
     @property
     def sel(self) -> np.ndarray:
         if self._sel is None:
-            self._sel = np.arange(self.hp.m, dtype=np.int64)
+            self._sel = np.arange(self.lo, self.hi, dtype=np.int64)
         return self._sel
 
     @property
@@ -136,10 +141,6 @@ class BucketSpec:
     def subset(self, local_idx: np.ndarray) -> "BucketSpec":
         return BucketSpec(self.hp, self.kind, self.arity, self.sel[local_idx])
 
-    # backwards-compatible dict-style access used by older call sites / tests
-    def __getitem__(self, k):
-        return getattr(self, k)
-
 
 def split_buckets(hp: HostPools, rank: int = 0, world: int = 1) -> List["BucketSpec"]:
     """Group pools by (kind, arity); with world>1 keep this rank's contiguous block of each group."""
@@ -147,20 +148,16 @@ def split_buckets(hp: HostPools, rank: int = 0, world: int = 1) -> List["BucketS
     if m == 0:
         return []
     if getattr(hp, "_uniform_product", False):
-        if world == 1:
-            return [BucketSpec(hp, _lib.KIND_PRODUCT, 2, None)]
         lo, hi = (m * rank) // world, (m * (rank + 1)) // world
-        return [BucketSpec(hp, _lib.KIND_PRODUCT, 2, np.arange(lo, hi, dtype=np.int64))]
+        return [BucketSpec(hp, _lib.KIND_PRODUCT, 2, None, lo, hi)]
     uniform_pairs = int(hp.pool_ptr[-1]) == 2 * m and (hp.pool_ptr[1] - hp.pool_ptr[0]) == 2 and \
         bool(np.all(np.diff(hp.pool_ptr[::max(1, m // 64)]) == 2 * max(1, m // 64))) and \
         bool(np.array_equal(hp.pool_ptr[:3], np.arange(0, 2 * min(m, 2) + 1, 2)[:3]))
     if uniform_pairs:
         uniform_pairs = bool(np.all(np.diff(hp.pool_ptr) == 2))
     if uniform_pairs and not hp.kind.any() and bool(np.all(hp.weights == 0.5)):
-        if world == 1:
-            return [BucketSpec(hp, _lib.KIND_PRODUCT, 2, None)]
         lo, hi = (m * rank) // world, (m * (rank + 1)) // world
-        return [BucketSpec(hp, _lib.KIND_PRODUCT, 2, np.arange(lo, hi, dtype=np.int64))]
+        return [BucketSpec(hp, _lib.KIND_PRODUCT, 2, None, lo, hi)]
     ar = np.diff(hp.pool_ptr)
     first = hp.pool_ptr[:-1]
     is_cp = (hp.kind == KIND_GEOMEAN_HOST) & (ar == 2)
@@ -211,14 +208,14 @@ class DeviceBucket:
         self.stride = max(TILE, -(-self.m // TILE) * TILE)
         f64 = dict(dtype=torch.float64, device=device)
         self.weights = self.logrw = self.theta_bar = None
-        if spec.identity and self.arity == 2:          # uniform pairs, all pools in order: transpose on the GPU
-            m = self.m
+        if spec.identity and self.arity == 2 and int(hp.pool_ptr[-1]) == 2 * hp.m:   # uniform pairs in order: transpose on the GPU
+            m, lo, hi = self.m, spec.lo, spec.hi
             self.reserves = torch.ones((2, self.stride), **f64)
-            self.reserves[:, :m] = torch.from_numpy(hp.reserves).to(device).view(m, 2).t()
+            self.reserves[:, :m] = torch.from_numpy(hp.reserves[2 * lo:2 * hi]).to(device).view(m, 2).t()
             self.tok_idx = torch.zeros((2, self.stride), dtype=torch.int32, device=device)
-            self.tok_idx[:, :m] = torch.from_numpy(hp.tok_idx).to(device).view(m, 2).t()
+            self.tok_idx[:, :m] = torch.from_numpy(hp.tok_idx[2 * lo:2 * hi]).to(device).view(m, 2).t()
             self.gamma = torch.ones(self.stride, **f64)
-            self.gamma[:m] = torch.from_numpy(hp.gamma).to(device)
+            self.gamma[:m] = torch.from_numpy(hp.gamma[lo:hi]).to(device)
             R = W = None
         else:
             R = hp.reserves[spec.off]
@@ -431,9 +428,10 @@ class BlockedBucket:
             n_ctas = 2 * torch.cuda.get_device_properties(device).multi_processor_count
         f64 = dict(dtype=torch.float64, device=device)
         if spec.identity:                       # raw arrays go up as they are; all reordering happens on the GPU
-            R = torch.from_numpy(hp.reserves).to(device, non_blocking=True).view(-1, 2)
-            idx = torch.from_numpy(hp.tok_idx).to(device, non_blocking=True).view(-1, 2).to(torch.int64)
-            gam = torch.from_numpy(hp.gamma).to(device, non_blocking=True)
+            lo, hi = spec.lo, spec.hi            # a rank's shard uploads only its own slice of the (pinned) host arrays
+            R = torch.from_numpy(hp.reserves[2 * lo:2 * hi]).to(device, non_blocking=True).view(-1, 2)
+            idx = torch.from_numpy(hp.tok_idx[2 * lo:2 * hi]).to(device, non_blocking=True).view(-1, 2).to(torch.int64)
+            gam = torch.from_numpy(hp.gamma[lo:hi]).to(device, non_blocking=True)
             if getattr(hp, "_validate_on_device", False):          # same checks as HostPools.validate(), on the GPU
                 chk = torch.stack([R.min(), gam.min(), 1.0 - gam.max(), idx.min().double(),
                                    float(hp.n_tokens - 1) - idx.max().double(),
@@ -500,6 +498,60 @@ class BlockedBucket:
                             self.hcoef.data_ptr() if hess else None, None)
 
 
+class PeerContext:
+    """Symmetric-memory buffers + sequence counters of the NVLink all-reduce kernel (csrc/cfmm_allreduce.cu), one per
+    (process, token count): allocation and rendezvous cost milliseconds, so they are paid once, not per
+    PoolStore / per solve.  All ranks must issue the same sequence of reductions (they do: every rank runs the same
+    outer loop on bit-identical reduced vectors)."""
+
+    def __init__(self, n_tokens: int, device, group):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        n = int(n_tokens)
+        if n + 1 > 64 * 256:
+            raise _lib.CfmmError("peer all-reduce supports n_tokens < 16384; use NCCL (Comm) beyond that")
+        f64 = dict(dtype=torch.float64, device=device)
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.n_tokens = n
+        w = self.world
+        # receive areas: [3 slots][world sources][n cells of {value, sequence flag}] (zero = "nothing received yet")
+        self.sym_acc = symm.empty((3 * w * (n + 1) * 2,), **f64); self.sym_acc.zero_()
+        self.sym_y = symm.empty((3 * w * n * 2,), **f64); self.sym_y.zero_()
+        self.hdl_acc = symm.rendezvous(self.sym_acc, group)
+        self.hdl_y = symm.rendezvous(self.sym_y, group)
+        self.red_acc = torch.zeros(n + 1, **f64)
+        self.red_y = torch.zeros(n, **f64)
+        self.seq = [0, 0]                   # last sequence number used on channel 0 ([psi | arb]) / 1 (n-vectors)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)
+
+    def next_seq(self, chan: int) -> int:
+        self.seq[chan] += 1
+        return self.seq[chan]
+
+    def c_struct(self):
+        """cfmm_peer_ctx for the native solvers (they advance the sequence numbers; read them back with absorb())"""
+        return _lib.PeerCtx(int(self.hdl_acc.buffer_ptrs_dev), int(self.hdl_y.buffer_ptrs_dev), self.rank, self.world,
+                            self.seq[0], self.seq[1])
+
+    def absorb(self, c):
+        self.seq = [int(c.seq_acc), int(c.seq_vec)]
+
+
+_PEER_CONTEXTS: Dict[tuple, "PeerContext"] = {}
+
+
+def peer_context(n_tokens: int, device, group=None) -> "PeerContext":
+    """the process-wide PeerContext for this token count (created on first use; collective)"""
+    import torch.distributed as dist
+    group = group or dist.group.WORLD
+    key = (int(n_tokens), id(group), str(torch.device(device)))
+    if key not in _PEER_CONTEXTS:
+        _PEER_CONTEXTS[key] = PeerContext(n_tokens, torch.device(device), group)
+    return _PEER_CONTEXTS[key]
+
+
 class PoolStore:
     """All pools of one problem (or one rank's shard of them), resident on one GPU."""
 
@@ -508,7 +560,7 @@ class PoolStore:
         if layout not in ("blocked", "plain"):
             raise ValueError("layout must be 'blocked' or 'plain'")
         if validate:
-            if getattr(hp, "_uniform_product", False) and layout == "blocked" and world == 1:
+            if getattr(hp, "_uniform_product", False) and layout == "blocked":
                 hp._validate_on_device = True           # checked after the upload, by reductions on the GPU
             else:
                 hp.validate()
@@ -551,56 +603,24 @@ class PoolStore:
         self.evals = 0
         self.hvps = 0
 
-    # -- multi-GPU: fused peer-memory all-reduce ---------------------------------------------------
-    def enable_peer_allreduce(self, group=None, protocol: str = "ll", fused: bool = False):
-        """Pool-sharded stores (world > 1): finish every evaluate()/hvp() with a fused NVLink all-reduce kernel
-        (PDL-chained behind the pool kernels) instead of returning a partial for NCCL.  protocol 'll': every rank
-        pushes {value, seq} cells into the peers' receive areas (cfmm_allreduce_ll, one NVLink one-way trip);
-        'pull': hand-shake + remote loads of the peers' partial vectors (cfmm_allreduce_oneshot).  The buffers live
-        in torch symmetric memory.  Collective: every rank must call it."""
-        import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm
-        if protocol not in ("ll", "pull"):
-            raise ValueError("protocol must be 'll' or 'pull'")
-        group = group or dist.group.WORLD
-        n = self.n_tokens
-        if n + 1 > 64 * 256:
-            raise _lib.CfmmError("fused peer all-reduce supports n_tokens < 16384; use NCCL (Comm) beyond that")
-        # our hand-shake slots live above word 512 of the signal pad: 4 channels x 64 CTAs x 16 ranks words
-        if symm.get_signal_pad_size() < 65536:
-            symm.set_signal_pad_size(65536)
-        f64 = dict(dtype=torch.float64, device=self.device)
-        self._peer_rank, self._peer_world = dist.get_rank(group), dist.get_world_size(group)
-        w = self._peer_world
-        self._peer_protocol = protocol
-        if protocol == "pull":
-            self._sym_acc = symm.empty((3, n + 1), **f64); self._sym_acc.zero_()
-            self._sym_y = symm.empty((3, n), **f64); self._sym_y.zero_()
-        else:                               # receive areas: [3 slots][world sources][n cells of {value, flag}]
-            self._sym_acc = symm.empty((3 * w * (n + 1) * 2,), **f64); self._sym_acc.zero_()
-            self._sym_y = symm.empty((3 * w * n * 2,), **f64); self._sym_y.zero_()
-        self._hdl_acc = symm.rendezvous(self._sym_acc, group)
-        self._hdl_y = symm.rendezvous(self._sym_y, group)
-        self._red_acc = torch.zeros(n + 1, **f64)
-        self._red_y = torch.zeros(n, **f64)
-        self._seq_acc = self._seq_y = 0
-        # one blocked bucket and the LL protocol: the all-reduce runs INSIDE the pool kernel (last CTA), no extra launch
-        # (measured slower than the separate LL kernel: one CTA polls 9 cells per thread; kept selectable)
-        self._peer_fused = fused and protocol == "ll" and len(self.buckets) == 1 and getattr(self.buckets[0], "blocked", False)
-        self._done_ctr = torch.zeros(2, dtype=torch.int32, device=self.device)
-        torch.cuda.synchronize(self.device)
-        dist.barrier(group)
+    # -- multi-GPU: peer-memory all-reduce -----------------------------------------------------------
+    def enable_peer_allreduce(self, group=None):
+        """Pool-sharded stores (world > 1): finish every evaluate()/hvp()/hess_diag() with the NVLink all-reduce kernel
+        cfmm_allreduce_ll (PDL-chained behind the pool kernels: every rank pushes {value, seq} cells into the peers'
+        receive areas, one NVLink one-way trip) instead of returning a partial for NCCL.  The buffers live in torch
+        symmetric memory and are created ONCE per process and token count (peer_context()); every store of the
+        process shares them.  Collective: every rank must call it, in the same order."""
+        self._peer = peer_context(self.n_tokens, self.device, group)
         self.reduces_internally = True
 
-    def _peer_reduce(self, hdl, local, slot, n, out, seq, channel, st):
-        if self._peer_protocol == "pull":
-            _lib.check(self.lib.cfmm_allreduce_oneshot(int(hdl.buffer_ptrs_dev), int(hdl.signal_pad_ptrs_dev),
-                                                       self._peer_rank, self._peer_world, slot * n, n, out.data_ptr(),
-                                                       seq, channel, st), "cfmm_allreduce_oneshot")
-        else:
-            w = self._peer_world
-            _lib.check(self.lib.cfmm_allreduce_ll(local.data_ptr(), int(hdl.buffer_ptrs_dev), self._peer_rank, w, n,
-                                                  slot * w * n, n, out.data_ptr(), seq, st), "cfmm_allreduce_ll")
+    def _peer_reduce(self, chan, local, n, st):
+        """all-reduce `local` (n doubles, this rank's partial) over the peer context; chan 0 = [psi | arb], 1 = n-vectors"""
+        p = self._peer
+        seq = p.next_seq(chan)
+        hdl, out = (p.hdl_acc, p.red_acc) if chan == 0 else (p.hdl_y, p.red_y)
+        _lib.check(self.lib.cfmm_allreduce_ll(local.data_ptr(), int(hdl.buffer_ptrs_dev), p.rank, p.world, n,
+                                              (seq % 3) * p.world * n, n, out.data_ptr(), seq, st), "cfmm_allreduce_ll")
+        return out
 
     # -- helpers -------------------------------------------------------------------------------
     def _stream(self):
@@ -618,34 +638,17 @@ class PoolStore:
 
     # -- the hot path --------------------------------------------------------------------------
     def evaluate(self, nu: torch.Tensor, eps: float = 0.0, trades: bool = False, hess: bool = False):
-        """psi(nu) (n_tokens) and arb(nu) (1) for this rank's pools, as views into one (n+1) buffer."""
+        """psi(nu) (n_tokens) and arb(nu) (1) for this rank's pools, as views into one (n+1) buffer (all-reduced over
+        the peer context when enable_peer_allreduce() was called)."""
         st = self._stream()
-        peer = getattr(self, "reduces_internally", False)
-        pull = peer and self._peer_protocol == "pull"
-        if pull:                            # 3-slot rotation in symmetric memory (see csrc/cfmm_allreduce.cu)
-            k = self._seq_acc % 3
-            acc, nxt = self._sym_acc[k], self._sym_acc[(k + 1) % 3]
-        else:
-            acc = self._acc2[self._acc_i]
-            nxt = self._acc2[self._acc_i ^ 1]
-            self._acc_i ^= 1
+        acc = self._acc2[self._acc_i]
+        nxt = self._acc2[self._acc_i ^ 1]
+        self._acc_i ^= 1
         if not self._blocked_first:       # otherwise the previous blocked launch already cleared `acc`
             _lib.check(self.lib.cfmm_zero(acc.data_ptr(), acc.numel() * 8, st), "cfmm_zero")
         lognu = torch.log(nu) if self.has_geomean else None
         for b in self.buckets:
             out = b.out_struct(trades, hess) if (trades or hess) else None
-            if peer and self._peer_fused:
-                self._seq_acc += 1
-                w, n1 = self._peer_world, self.n_tokens + 1
-                pl = _lib.PeerLL(int(self._hdl_acc.buffer_ptrs_dev), self._done_ctr.data_ptr(), self._red_acc.data_ptr(),
-                                 (self._seq_acc % 3) * w * n1, n1, self._seq_acc, self._peer_rank, w)
-                rc = self.lib.cfmm_blocked_eval_fused(C.byref(b.c_blocked), self.n_tokens, nu.data_ptr(), acc.data_ptr(),
-                                                      acc.data_ptr() + 8 * self.n_tokens,
-                                                      C.byref(out) if out is not None else None,
-                                                      nxt.data_ptr(), nxt.numel(), C.byref(pl), st)
-                _lib.check(rc, "cfmm_blocked_eval_fused")
-                self.evals += 1
-                return self._red_acc
             if getattr(b, "blocked", False):
                 rc = self.lib.cfmm_blocked_eval(C.byref(b.c_blocked), self.n_tokens, nu.data_ptr(), acc.data_ptr(),
                                                 acc.data_ptr() + 8 * self.n_tokens,
@@ -659,37 +662,18 @@ class PoolStore:
                                         C.byref(out) if out is not None else None, st)
             _lib.check(rc, "cfmm_arb_eval")
         self.evals += 1
-        if peer:
-            self._seq_acc += 1
-            k = (self._seq_acc - 1) % 3 if pull else self._seq_acc % 3
-            self._peer_reduce(self._hdl_acc, acc, k, self.n_tokens + 1, self._red_acc, self._seq_acc, 0, st)
-            return self._red_acc
+        if getattr(self, "reduces_internally", False):
+            return self._peer_reduce(0, acc, self.n_tokens + 1, st)
         return acc
 
     def hvp(self, vt: torch.Tensor) -> torch.Tensor:
         st = self._stream()
-        peer = getattr(self, "reduces_internally", False)
-        pull = peer and self._peer_protocol == "pull"
-        if pull:
-            k = self._seq_y % 3
-            y, ynxt = self._sym_y[k], self._sym_y[(k + 1) % 3]
-        else:
-            y = self._y2[self._y_i]
-            ynxt = self._y2[self._y_i ^ 1]
-            self._y_i ^= 1
+        y = self._y2[self._y_i]
+        ynxt = self._y2[self._y_i ^ 1]
+        self._y_i ^= 1
         if not self._blocked_first:
             _lib.check(self.lib.cfmm_zero(y.data_ptr(), y.numel() * 8, st), "cfmm_zero")
         for b in self.buckets:
-            if peer and self._peer_fused:
-                self._seq_y += 1
-                w, n = self._peer_world, self.n_tokens
-                pl = _lib.PeerLL(int(self._hdl_y.buffer_ptrs_dev), self._done_ctr.data_ptr() + 4, self._red_y.data_ptr(),
-                                 (self._seq_y % 3) * w * n, n, self._seq_y, self._peer_rank, w)
-                _lib.check(self.lib.cfmm_blocked_hvp_fused(C.byref(b.c_blocked), n, b.hcoef.data_ptr(), vt.data_ptr(),
-                                                           y.data_ptr(), ynxt.data_ptr(), C.byref(pl), st),
-                           "cfmm_blocked_hvp_fused")
-                self.hvps += 1
-                return self._red_y
             if getattr(b, "blocked", False):
                 _lib.check(self.lib.cfmm_blocked_hvp(C.byref(b.c_blocked), self.n_tokens, b.hcoef.data_ptr(),
                                                      vt.data_ptr(), y.data_ptr(), ynxt.data_ptr(), st),
@@ -699,11 +683,8 @@ class PoolStore:
                                    b.hmask.data_ptr(), vt.data_ptr(), y.data_ptr(), st)
             _lib.check(rc, "cfmm_hvp")
         self.hvps += 1
-        if peer:
-            self._seq_y += 1
-            k = (self._seq_y - 1) % 3 if pull else self._seq_y % 3
-            self._peer_reduce(self._hdl_y, y, k, self.n_tokens, self._red_y, self._seq_y, 1, st)
-            return self._red_y
+        if getattr(self, "reduces_internally", False):
+            return self._peer_reduce(1, y, self.n_tokens, st)
         return y
 
     def hess_diag(self) -> torch.Tensor:
@@ -716,6 +697,8 @@ class PoolStore:
                 continue
             _lib.check(self.lib.cfmm_hess_diag(C.byref(b.c_bucket), self.n_tokens, b.hcoef.data_ptr(),
                                                b.hmask.data_ptr(), d.data_ptr(), st), "cfmm_hess_diag")
+        if getattr(self, "reduces_internally", False):
+            return self._peer_reduce(1, d, self.n_tokens, st).clone()
         return d
 
     def hess_dense(self) -> torch.Tensor:

@@ -62,9 +62,9 @@ class SolveInfo:
 class Comm:
     """Sum all-reduce over torch.distributed when world_size > 1, else a no-op."""
 
-    def __init__(self):
+    def __init__(self, enabled: bool = True):
         import torch.distributed as dist
-        self.dist = dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
+        self.dist = dist if (enabled and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
         self.calls = 0
 
     def allreduce(self, t: torch.Tensor) -> torch.Tensor:
@@ -170,7 +170,7 @@ def solve_dual(ev, spec: DualSpec, nu0=None, tol: float = 1e-8, eps: float = 0.1
             # ---- Newton direction in log-price coordinates: Hs dt = -(nu*grad) on the free set
             pgfull = nu * grad
             Hs = comm.allreduce(ev.hess_dense()) if linear_solver == "dense" else None
-            diag = None if linear_solver == "dense" else comm.allreduce(ev.hess_diag())
+            diag = None if linear_solver == "dense" else (ev.hess_diag() if internal else comm.allreduce(ev.hess_diag()))
 
             def newton_dir(fr_, x0=None):
                 if linear_solver == "dense":

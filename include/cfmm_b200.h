@@ -186,6 +186,27 @@ int cfmm_blocked_solve(const cfmm_blocked_pairs* b, int32_t n_tokens, const doub
                        const cfmm_solve_params* prm, cfmm_solve_result* res, void* stream);
 
 /*
+ * The same solve with the pools SHARDED over `world` GPUs (one process per GPU): `b` holds this rank's
+ * pools, every rank passes the same c / a / eq / pinned / nu and runs the same loop; each evaluation, Hessian-vector
+ * product and Hessian diagonal is followed by the LL all-reduce (cfmm_allreduce_ll) of its (n_tokens+1)- or
+ * n_tokens-vector over NVLink peer memory, so every rank sees bit-identical reduced vectors, takes identical decisions
+ * and ends with identical nu / psi_out / res.  recv_acc_dev / recv_vec_dev: device arrays of `world` pointers to every
+ * rank's receive areas ([3 slots][world][n_tokens+1] and [3 slots][world][n_tokens] cells of 16 B, zeroed once at
+ * creation; torch symmetric memory: hdl.buffer_ptrs_dev).  seq_acc / seq_vec: last sequence numbers used on the two
+ * channels (in), advanced by the reductions of this call (out) -- equal on all ranks.  peer == NULL: one GPU.
+ */
+typedef struct cfmm_peer_ctx {
+    const void* recv_acc_dev;
+    const void* recv_vec_dev;
+    int32_t rank, world;
+    uint64_t seq_acc, seq_vec;
+} cfmm_peer_ctx;
+
+int cfmm_blocked_solve_peer(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* c, const double* a,
+                            const uint8_t* eq, const uint8_t* pinned, double* nu, double* psi_out, void* work,
+                            const cfmm_solve_params* prm, cfmm_solve_result* res, cfmm_peer_ctx* peer, void* stream);
+
+/*
  * Batches of SMALL problems (the reference's own sizes: 5 pools, 3-5 tokens), one problem per thread, the whole
  * prob.solve() (arbitrage.py:81-82, liquidation.py:84-85, two-asset.py:90-91) of every problem in ONE launch.  Replaces
  * the python loop of two-asset.py:40-100 that builds and solves 50 cvxpy problems in turn.  All problems index the same
