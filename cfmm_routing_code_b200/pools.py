@@ -637,9 +637,9 @@ class PoolStore:
         return n + 16 * self.n_tokens + 8
 
     # -- the hot path --------------------------------------------------------------------------
-    def evaluate(self, nu: torch.Tensor, eps: float = 0.0, trades: bool = False, hess: bool = False):
+    def evaluate(self, nu: torch.Tensor, eps: float = 0.0, trades: bool = False, hess: bool = False, reduce: bool = True):
         """psi(nu) (n_tokens) and arb(nu) (1) for this rank's pools, as views into one (n+1) buffer (all-reduced over
-        the peer context when enable_peer_allreduce() was called)."""
+        the peer context when enable_peer_allreduce() was called, unless reduce=False: this rank's partial)."""
         st = self._stream()
         acc = self._acc2[self._acc_i]
         nxt = self._acc2[self._acc_i ^ 1]
@@ -662,7 +662,7 @@ class PoolStore:
                                         C.byref(out) if out is not None else None, st)
             _lib.check(rc, "cfmm_arb_eval")
         self.evals += 1
-        if getattr(self, "reduces_internally", False):
+        if reduce and getattr(self, "reduces_internally", False):
             return self._peer_reduce(0, acc, self.n_tokens + 1, st)
         return acc
 

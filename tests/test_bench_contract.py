@@ -16,12 +16,23 @@ def test_reference_arm_prints_one_contract_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1
-    assert d["unit"] == "pool-evals/s" and d["higher_is_better"] is True and d["scaling"] == "weak"
+    assert d["unit"] == "pool-evals/s" and d["higher_is_better"] is True and d["scaling"] == "strong"
     assert d["dtype"] == "f64" and d["data"] == "synthetic" and d["vs_baseline"] is None
-    assert "workload" in d["config"] and "1M constant-product pools" in d["config"]["workload"]
+    assert "workload" in d["config"] and "1000000 constant-product pools" in d["config"]["workload"]
     assert d["value"] > 0 and d["ms_per_step"] > 0
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     e = d["e2e"]
     assert e["unit"] == d["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0 and e["value"] > 0
     assert e["status"] == "optimal" and d["time_to_1e-6_gap"]["rel_gap"] <= 1e-6
+    assert "oracle_solve_pairs" in e["what"]            # the CPU arm's solve is the oracle's own C loop, not product code
+
+
+def test_bench_b200_arm_is_syntactically_sound_and_refuses_to_run_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("GPU present")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "20", "--warmup", "5"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode != 0 and "needs a CUDA device" in (out.stderr + out.stdout)
