@@ -51,12 +51,6 @@ class SolveResult(C.Structure):
                 ("hvps", C.c_int32), ("status", C.c_int32)]
 
 
-class PeerLL(C.Structure):
-    _fields_ = [("peer_recv_dev", C.c_void_p), ("done_counter", C.c_void_p), ("reduced", C.c_void_p),
-                ("slot_off_cells", C.c_int64), ("src_stride_cells", C.c_int64), ("seq", C.c_uint64),
-                ("rank", C.c_int32), ("world", C.c_int32)]
-
-
 class PeerCtx(C.Structure):
     _fields_ = [("recv_acc_dev", C.c_void_p), ("recv_vec_dev", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32),
                 ("seq_acc", C.c_uint64), ("seq_vec", C.c_uint64)]
@@ -114,7 +108,7 @@ def load(build_if_missing: bool = True):
     lib.cfmm_hvp.argtypes = [C.POINTER(Bucket), i32, vp, vp, vp, vp, vp]
     lib.cfmm_hess_diag.argtypes = [C.POINTER(Bucket), i32, vp, vp, vp, vp]
     lib.cfmm_hess_dense.argtypes = [C.POINTER(Bucket), i32, vp, vp, vp, vp]
-    lib.cfmm_blocked_layout_info.argtypes = [C.POINTER(i32)] * 5
+    lib.cfmm_blocked_layout_info.argtypes = [C.POINTER(i32)] * 4
     lib.cfmm_blocked_layout_info.restype = C.c_int
     lib.cfmm_set_blocked_config.argtypes = [i32]
     lib.cfmm_set_blocked_config.restype = C.c_int
@@ -122,11 +116,6 @@ def load(build_if_missing: bool = True):
     lib.cfmm_blocked_eval.restype = C.c_int
     lib.cfmm_blocked_hvp.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp, vp, vp]
     lib.cfmm_blocked_hvp.restype = C.c_int
-    lib.cfmm_blocked_eval_fused.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp, C.POINTER(EvalOut), vp, i64,
-                                            C.POINTER(PeerLL), vp]
-    lib.cfmm_blocked_eval_fused.restype = C.c_int
-    lib.cfmm_blocked_hvp_fused.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp, vp, C.POINTER(PeerLL), vp]
-    lib.cfmm_blocked_hvp_fused.restype = C.c_int
     lib.cfmm_blocked_diag.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp]
     lib.cfmm_blocked_diag.restype = C.c_int
     lib.cfmm_blocked_solve_work_bytes.argtypes = [C.POINTER(BlockedPairs), i32]
@@ -137,14 +126,16 @@ def load(build_if_missing: bool = True):
     lib.cfmm_blocked_solve_peer.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp, vp, vp, vp, vp,
                                             C.POINTER(SolveParams), C.POINTER(SolveResult), C.POINTER(PeerCtx), vp]
     lib.cfmm_blocked_solve_peer.restype = C.c_int
+    lib.cfmm_persist_solve_work_bytes.argtypes = [C.POINTER(BlockedPairs), i32]
+    lib.cfmm_persist_solve_work_bytes.restype = i64
+    lib.cfmm_persist_solve.argtypes = lib.cfmm_blocked_solve_peer.argtypes
+    lib.cfmm_persist_solve.restype = C.c_int
     lib.cfmm_batch_solve_work_bytes.argtypes = [C.POINTER(CsrPools), i32, i64]
     lib.cfmm_batch_solve_work_bytes.restype = i64
     lib.cfmm_set_batch_lanes.argtypes = [i32]
     lib.cfmm_set_batch_lanes.restype = C.c_int
     lib.cfmm_batch_solve.argtypes = [C.POINTER(CsrPools), C.POINTER(Batch), C.POINTER(BatchParams), vp, vp]
     lib.cfmm_batch_solve.restype = C.c_int
-    lib.cfmm_allreduce_oneshot.argtypes = [vp, vp, i32, i32, i64, i32, vp, C.c_uint32, i32, vp]
-    lib.cfmm_allreduce_oneshot.restype = C.c_int
     lib.cfmm_allreduce_ll.argtypes = [vp, vp, i32, i32, i32, i64, i64, vp, C.c_uint64, vp]
     lib.cfmm_allreduce_ll.restype = C.c_int
     lib.cfmm_sum_update_multipliers.argtypes = [C.POINTER(Bucket), vp, vp, vp, vp]
@@ -159,8 +150,8 @@ def load(build_if_missing: bool = True):
     lib.cfmm_version.restype = C.c_char_p
     if os.environ.get("CFMM_BATCH_LANES"):          # 1 | 32 threads per problem in cfmm_batch_solve (experiments)
         lib.cfmm_set_batch_lanes(int(os.environ["CFMM_BATCH_LANES"]))
-    if os.environ.get("CFMM_BLOCKED_CFG"):          # kernel-variant override for experiments / A-B tests
-        for c in os.environ["CFMM_BLOCKED_CFG"].split(","):       # e.g. "1296" = tiles of 896 pools, "3,1296"
+    if os.environ.get("CFMM_BLOCKED_CFG"):          # experiment knobs, e.g. "200" = no programmatic dependent launch
+        for c in os.environ["CFMM_BLOCKED_CFG"].split(","):
             lib.cfmm_set_blocked_config(int(c))
     _lib = lib
     return lib

@@ -142,8 +142,10 @@ def _enable_peer(store: PoolStore, comm: Comm) -> None:
         warnings.warn(f"peer all-reduce unavailable ({type(e).__name__}: {e}); using torch.distributed all_reduce")
 
 
-def _solve_native(store: PoolStore, spec, nu0, tol, max_iter, cg_max=200) -> SolveInfo:
-    """cfmm_blocked_solve (csrc/cfmm_solver.cu): the whole outer loop in one C call."""
+def _solve_native(store: PoolStore, spec, nu0, tol, max_iter, cg_max=200, impl="persist") -> SolveInfo:
+    """The whole outer loop in one C call: impl 'persist' = ONE persistent cooperative kernel (csrc/cfmm_persist.cu: the
+    host launches once and reads one result struct), 'hostloop' = C++ host loop over per-pass launches
+    (csrc/cfmm_solver.cu).  Same method, same stopping rule, same results up to summation order."""
     import ctypes as C
     import time
     from .solver import default_nu0
@@ -157,9 +159,13 @@ def _solve_native(store: PoolStore, spec, nu0, tol, max_iter, cg_max=200) -> Sol
     pinned = torch.as_tensor(np.asarray(spec.pinned, np.uint8), device=dev)
     nu = torch.as_tensor(default_nu0(spec) if nu0 is None else np.asarray(nu0, float), **f64).clone()
     psi = torch.empty(n, **f64)
-    nbytes = store.lib.cfmm_blocked_solve_work_bytes(C.byref(b.c_blocked), n)
+    if impl not in ("persist", "hostloop"):
+        raise ValueError("native must be True / 'persist' / 'hostloop' / False")
+    work_bytes = store.lib.cfmm_persist_solve_work_bytes if impl == "persist" else store.lib.cfmm_blocked_solve_work_bytes
+    entry = store.lib.cfmm_persist_solve if impl == "persist" else store.lib.cfmm_blocked_solve_peer
+    nbytes = work_bytes(C.byref(b.c_blocked), n)
     if nbytes <= 0:
-        raise _lib.CfmmError("cfmm_blocked_solve_work_bytes failed")
+        raise _lib.CfmmError("solve work_bytes failed")
     if getattr(store, "_solve_work", None) is None or store._solve_work.numel() < nbytes:
         store._solve_work = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     scale = max(float(np.abs(spec.c).max()), 1.0)
@@ -168,12 +174,12 @@ def _solve_native(store: PoolStore, spec, nu0, tol, max_iter, cg_max=200) -> Sol
     st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     peer = getattr(store, "_peer", None) if getattr(store, "reduces_internally", False) else None
     pc = peer.c_struct() if peer is not None else None
-    rc = store.lib.cfmm_blocked_solve_peer(C.byref(b.c_blocked), n, c.data_ptr(), a.data_ptr(), eq.data_ptr(),
-                                           pinned.data_ptr(), nu.data_ptr(), psi.data_ptr(), store._solve_work.data_ptr(),
-                                           C.byref(prm), C.byref(res), C.byref(pc) if pc is not None else None, st)
+    rc = entry(C.byref(b.c_blocked), n, c.data_ptr(), a.data_ptr(), eq.data_ptr(), pinned.data_ptr(), nu.data_ptr(),
+               psi.data_ptr(), store._solve_work.data_ptr(), C.byref(prm), C.byref(res),
+               C.byref(pc) if pc is not None else None, st)
     if pc is not None:
         peer.absorb(pc)                 # the reductions of this solve advanced the shared sequence numbers
-    _lib.check(rc, "cfmm_blocked_solve")
+    _lib.check(rc, "cfmm_persist_solve" if impl == "persist" else "cfmm_blocked_solve")
     store.evals += res.evals
     store.hvps += res.hvps
     status = {0: "optimal", 1: "max_iter", 2: "stalled"}[res.status]
@@ -184,11 +190,13 @@ def _solve_native(store: PoolStore, spec, nu0, tol, max_iter, cg_max=200) -> Sol
 
 def solve_pools(hp: HostPools, utility, nu0=None, tol: float = 1e-8, max_iter: int = 100, device="cuda",
                 verbose: bool = False, store: Optional[PoolStore] = None, want_trades: bool = True,
-                native: bool = True, method: str = "auto", **solver_kw) -> Result:
+                native=True, method: str = "auto", **solver_kw) -> Result:
     """Same as solve() on CSR host arrays.  Under torch.distributed (world_size > 1) every rank passes the
     full problem and keeps its contiguous shard; psi/value are global, deltas/lambdas are this rank's.
     method: 'pools' = pool-parallel kernels under the outer loop (any size); 'thread' = the whole solve in one GPU
-    thread (<= 64 tokens, arity <= 8); 'auto' picks 'thread' up to SMALL_POOLS pools."""
+    thread (<= 64 tokens, arity <= 8); 'auto' picks 'thread' up to SMALL_POOLS pools.
+    native (constant-product problems): True / 'persist' = the persistent solver kernel, 'hostloop' = the C++ host loop
+    over per-pass launches, False = the python loop (solver.py)."""
     comm = Comm()
     if method not in ("auto", "pools", "thread"):
         raise ValueError("method must be 'auto', 'pools' or 'thread'")
@@ -209,7 +217,8 @@ def solve_pools(hp: HostPools, utility, nu0=None, tol: float = 1e-8, max_iter: i
         comm = Comm(enabled=False)          # an unsharded store under an initialised process group: nothing to reduce
     spec = utility.spec(hp.n_tokens)
     if native and not verbose and _native_applicable(store, comm, solver_kw):
-        info = _solve_native(store, spec, nu0, tol, max_iter, solver_kw.get("cg_max", 200))
+        info = _solve_native(store, spec, nu0, tol, max_iter, solver_kw.get("cg_max", 200),
+                             impl="persist" if native is True else native)
         if want_trades:          # one more pass of the eval kernel to emit Delta / Lambda at the solution
             store.evaluate(info.nu, 0.0, trades=True, hess=False)
     else:

@@ -183,11 +183,8 @@ __global__ void __launch_bounds__(kVT) k_bounds(int n, const double* c, const un
 
 inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
-// slab stride of a blocked layout = what cfmm_blocked.cu's fill_args uses: n_tiles * P for fixed tiles, the pool count
-// rounded up to 4 for planned tiles (pools_per_tile == 0, sizes in the descriptors)
-inline size_t hcoef_stride(const cfmm_blocked_pairs* b) {
-    return b->pools_per_tile ? (size_t)b->n_tiles * (size_t)b->pools_per_tile : (((size_t)b->n_pools + 3) & ~(size_t)3);
-}
+// slab stride of a blocked layout (= BlockedArgs::M in cfmm_blocked.cu)
+inline size_t hcoef_stride(const cfmm_blocked_pairs* b) { return (size_t)b->n_tiles * (size_t)b->pools_per_tile; }
 
 }  // namespace
 

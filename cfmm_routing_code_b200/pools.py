@@ -190,7 +190,7 @@ def split_buckets(hp: HostPools, rank: int = 0, world: int = 1) -> List["BucketS
     return out
 
 
-TILE = 1024     # pools per TMA tile (csrc kTile): slot stride is padded to a multiple of it
+TILE = 1024     # pools per TMA tile of the PLAIN buckets (csrc/cfmm_kernels.cu kTile): slot stride is padded to a multiple of it
 
 
 def _padded(arr2d: np.ndarray, stride: int, fill) -> np.ndarray:
@@ -268,56 +268,21 @@ class DeviceBucket:
 
 
 def blocked_layout_info(lib):
-    v = [C.c_int32() for _ in range(5)]
+    v = [C.c_int32() for _ in range(4)]
     _lib.check(lib.cfmm_blocked_layout_info(*[C.byref(x) for x in v]), "cfmm_blocked_layout_info")
-    return tuple(int(x.value) for x in v)      # pools_per_tile, rows_stride, tok_stride, row_cap, ent_stride
+    return tuple(int(x.value) for x in v)      # pools_per_tile, rows_stride, tok_stride, row_cap
 
 
-def plan_tiles(m: int, n_ctas: int, cap: int = 1024, first: int = 256, lo: int = 256) -> np.ndarray:
-    """Tile sizes (in order, sum = m) for the descriptor-sized blocked kernels (cfmm_set_blocked_config(400)).
-
-    The kernels give CTA b the tiles [T b / G, T (b+1) / G) of a launch (G = min(T, n_ctas) CTAs) and their run time is
-    ramp + the longest chain of tiles.  Tiles of `cap` pools leave a ragged last round (1M pools on 296 CTAs: 977 tiles,
-    89 CTAs walk 4096 pools, the others 3072).  Instead every CTA gets the same number of pools (+-4), cut into the same
-    number k of tiles, the FIRST one small so that compute starts before the bulk of the CTA's data has landed:
-    1M pools -> 296 x (256 + 4 x ~781).  Every size but the last is a multiple of 4 (16-byte aligned bulk copies)."""
-    if m <= 0:
-        return np.zeros(0, np.int64)
-    if m <= n_ctas * lo:                                    # fewer tiles than CTAs: one small tile each
-        t = np.full(-(-m // lo), lo, np.int64)
-        t[-1] = m - lo * (len(t) - 1)
-        return t
-    bounds = (np.arange(n_ctas + 1, dtype=np.int64) * m // n_ctas) // 4 * 4     # pools of CTA b: [bounds[b], bounds[b+1])
-    bounds[-1] = m
-    per = int(np.diff(bounds).max())
-    if per <= cap:                                          # a single round: one tile per CTA
-        return np.diff(bounds)
-    k = 1 + -(-(per - first) // (cap - 8))                  # tiles per CTA (8 pools of slack for the rounding below)
-    sizes = np.empty((n_ctas, k), np.int64)
-    rest = np.diff(bounds) - first
-    base = rest // (k - 1) // 4 * 4
-    extra = rest - base * (k - 1)                           # < 4 (k - 1): handed out 4 at a time, the odd rest to the last tile
-    sizes[:, 0] = first
-    sizes[:, 1:] = base[:, None] + 4 * (np.arange(k - 1)[None, :] < (extra // 4)[:, None])
-    sizes[:, -1] += extra % 4
-    assert sizes.min() > 0 and sizes.max() <= cap and int(sizes.sum()) == m
-    return sizes.reshape(-1)
-
-
-def build_blocked_pairs(idx: torch.Tensor, n_tokens: int, P: int, rows_stride: int, tok_stride: int, row_cap: int,
-                        ent_stride: int, n_ctas: int = 0):
-    """Layout builder for cfmm_blocked_pairs (see csrc/cfmm_blocked.cu).  idx: (2, m) int64 token ids on the
+def build_blocked_pairs(idx: torch.Tensor, n_tokens: int, P: int, rows_stride: int, tok_stride: int, row_cap: int):
+    """Layout builder for cfmm_blocked_pairs (see csrc/cfmm_blocked.cuh).  idx: (2, m) int64 token ids on the
     device.  Pools are sorted by (token block of slot 0, token block of slot 1) and cut into tiles of P; each
     tile gets its distinct-token list, 16-bit local ids, and a CSR of rows (token, <= row_cap entries).
     Returns (order, residual, tables): `order` = bucket-local pool index at each blocked position, `residual` =
-    pools left out because their tile would touch more than tok_stride tokens (they go to a plain bucket).
-    P == 0: planned tiles (plan_tiles(m, n_ctas)): any size <= tok_stride, (size, first pool) in desc[:, 2:4]."""
+    pools left out because their tile would touch more than tok_stride tokens (they go to a plain bucket)."""
     dev = idx.device
     m = idx.shape[1]
     i64 = dict(dtype=torch.int64, device=dev)
-    planned = P == 0
-    cap_pools = tok_stride if planned else P            # most pools a tile can hold
-    nb = max(1, int(round((m / cap_pools) ** 0.5)))
+    nb = max(1, int(round((m / P) ** 0.5)))
     a, b = idx[0], idx[1]
     # primary: (token block of slot 0, token block of slot 1); secondary: slot-0 token, so that the lanes of a warp
     # read the same nu_local entry (shared-memory broadcast) and scatter slot-0 flows to consecutive positions
@@ -329,22 +294,10 @@ def build_blocked_pairs(idx: torch.Tensor, n_tokens: int, P: int, rows_stride: i
         if mm == 0:
             break
         pos = torch.arange(mm, **i64)
-        if planned:
-            plan = plan_tiles(mm, n_ctas, cap=cap_pools)
-            if np.any(plan[:-1] % 4) or plan.max() > cap_pools or int(plan.sum()) != mm:
-                raise _lib.CfmmError("blocked layout: bad tile plan (sizes must be multiples of 4, <= the stage capacity)")
-            sizes = torch.as_tensor(plan, **i64)
-            ntiles = int(sizes.numel())
-            starts = torch.cumsum(sizes, 0) - sizes
-            tile = torch.bucketize(pos, starts[1:].contiguous(), right=True)
-            l = pos - starts[tile]
-        else:
-            ntiles = -(-mm // P)
-            tile = pos // P
-            l = pos - tile * P
+        ntiles = -(-mm // P)
+        tile = pos // P
         he_tok = torch.cat([a[order], b[order]])
         he_tile = torch.cat([tile, tile])
-        he_code = torch.cat([2 * l, 2 * l + 1])
         ck, perm = torch.sort(he_tile * n_tokens + he_tok, stable=True)
         uniq, inv, counts = torch.unique_consecutive(ck, return_inverse=True, return_counts=True)
         u_tile = uniq // n_tokens
@@ -366,7 +319,7 @@ def build_blocked_pairs(idx: torch.Tensor, n_tokens: int, P: int, rows_stride: i
     ltok_u = torch.arange(U, **i64) - tok_off[u_tile]
     he_ltok = torch.empty(2 * mm, **i64)
     he_ltok[perm] = ltok_u[inv]
-    M = -(-mm // 4) * 4 if planned else ntiles * P
+    M = ntiles * P
     lid = torch.zeros(M, dtype=torch.int32, device=dev)
     lid[:mm] = (he_ltok[:mm] | (he_ltok[mm:] << 16)).to(torch.int32)
     tok = torch.zeros((ntiles, tok_stride), dtype=torch.int32, device=dev)
@@ -397,18 +350,15 @@ def build_blocked_pairs(idx: torch.Tensor, n_tokens: int, P: int, rows_stride: i
     he_pos[perm] = row_start[he_row] + he_o % row_cap                           # back to (pool, slot) order
     pos = torch.zeros(M, dtype=torch.int32, device=dev)
     # padding pools (last tile) write their zero flows to slots past the real entries of that tile
-    pad_base = 0 if planned else 2 * (mm - (ntiles - 1) * P)
-    if M > mm and not planned:            # (planned tiles: lanes beyond a tile's pool count never run)
+    pad_base = 2 * (mm - (ntiles - 1) * P)
+    if M > mm:
         padl = torch.arange(M - mm, **i64)
         pos[mm:] = ((pad_base + 2 * padl) | ((pad_base + 2 * padl + 1) << 16)).to(torch.int32)
     pos[:mm] = (he_pos[:mm] | (he_pos[mm:] << 16)).to(torch.int32)
     rows = torch.zeros((ntiles, rows_stride), dtype=torch.int32, device=dev)
     word = row_start | (row_len << 16) | (row_ltok << 22)          # start:16 | len:6 | ltok:10 (may set bit 31)
     rows[row_tile, r_local] = torch.where(word >= 2 ** 31, word - 2 ** 32, word).to(torch.int32)
-    if planned:
-        desc = torch.stack([ntok, nrow, sizes, starts], 1).to(torch.int32).contiguous()
-    else:
-        desc = torch.stack([ntok, nrow, torch.zeros_like(ntok), torch.zeros_like(ntok)], 1).to(torch.int32).contiguous()
+    desc = torch.stack([ntok, nrow, torch.zeros_like(ntok), torch.zeros_like(ntok)], 1).to(torch.int32).contiguous()
     tables = dict(n_tiles=ntiles, M=M, lid=lid, tok=tok, pos=pos, rows=rows, desc=desc,
                   rows_per_pool=n_rows / mm, tok_per_tile=float(ntok.double().mean()))
     return order, residual, tables
@@ -422,10 +372,7 @@ class BlockedBucket:
 
     def __init__(self, hp: HostPools, spec, device, lib):
         self.spec = spec
-        P, rows_stride, tok_stride, row_cap, ent_stride = blocked_layout_info(lib)
-        n_ctas = 0
-        if P == 0:                              # planned tiles (cfmm_set_blocked_config(400)): sizes in the descriptors
-            n_ctas = 2 * torch.cuda.get_device_properties(device).multi_processor_count
+        P, rows_stride, tok_stride, row_cap = blocked_layout_info(lib)
         f64 = dict(dtype=torch.float64, device=device)
         if spec.identity:                       # raw arrays go up as they are; all reordering happens on the GPU
             lo, hi = spec.lo, spec.hi            # a rank's shard uploads only its own slice of the (pinned) host arrays
@@ -442,8 +389,7 @@ class BlockedBucket:
             R = torch.as_tensor(np.ascontiguousarray(hp.reserves[spec.off].T), **f64)
             idx = torch.as_tensor(np.ascontiguousarray(hp.tok_idx[spec.off].T).astype(np.int64), device=device)
             gam = torch.as_tensor(np.ascontiguousarray(hp.gamma[spec.sel]), **f64)
-        order, residual, t = build_blocked_pairs(idx.t(), hp.n_tokens, P, rows_stride, tok_stride, row_cap, ent_stride,
-                                                 n_ctas=n_ctas)
+        order, residual, t = build_blocked_pairs(idx.t(), hp.n_tokens, P, rows_stride, tok_stride, row_cap)
         self.order = order                               # blocked position -> bucket-local pool index (device)
         self.residual = residual.cpu().numpy() if residual.numel() else np.zeros(0, np.int64)
         self.m = int(order.numel())

@@ -112,18 +112,13 @@ typedef struct cfmm_blocked_pairs {
                                  pos(slot 0) | pos(slot 1) << 16, each < 2P                              */
     const uint32_t* rows;     /* [n_tiles][rows_stride] start :16 | length 1..32 :6 | local token :10, longest first */
     const int32_t* tok;       /* [n_tiles][tok_stride] local token id -> global token id                 */
-    const int32_t* desc;      /* [n_tiles][4] (ntok, nrow, 0, 0); planned tiles: (ntok, nrow, pools, first pool) */
+    const int32_t* desc;      /* [n_tiles][4] (ntok, nrow, 0, 0)                                          */
 } cfmm_blocked_pairs;
 
-int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int32_t* tok_stride, int32_t* row_cap,
-                             int32_t* ent_stride);
-/* tuning: -1 = default (evaluation: TMA-staged slabs; Hessian products / diagonal: register-fed variant),
- * 0 = TMA-staged for everything, 3 = register-fed for everything; 200/201 = programmatic dependent launch off/on;
- * 300+c = row cap c (8..32) for layouts built afterwards; 400+P = pools per tile P (1024 default | 960 | 896) of
- * layouts built afterwards (load balance: a launch's critical path is ceil(n_tiles / (2 SMs)) tiles); 400 = planned
- * tiles: cfmm_blocked_layout_info then reports pools_per_tile 0 and the builder cuts tiles of any size <= 1024
- * (offsets multiples of 4), writing (pools, first pool) into desc[2], desc[3] of every tile; such a layout is passed
- * with cfmm_blocked_pairs.pools_per_tile = 0, slabs of ceil4(n_pools) entries, table strides of the 1024 layout. */
+int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int32_t* tok_stride, int32_t* row_cap);
+/* tuning knobs for experiments: 200/201 = programmatic dependent launch off/on; 300+c = row cap c (8..32) of layouts
+ * built afterwards.  (The tile size is a compile-time constant of the library, 896 pools: the fastest of 1024 / 960 /
+ * 896 / per-tile planned sizes measured on B200, profiles/r2a_tile_variants.txt.) */
 int cfmm_set_blocked_config(int32_t cfg);
 
 /* Same contract as cfmm_arb_eval for a blocked constant-product bucket: psi/arb ACCUMULATE (one red.add per row
@@ -136,29 +131,6 @@ int cfmm_blocked_eval(const cfmm_blocked_pairs* b, int32_t n_tokens, const doubl
 int cfmm_blocked_hvp(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* hcoef, const double* vt, double* y,
                      double* zero_next, void* stream);
 int cfmm_blocked_diag(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* hcoef, double* diag, void* stream);
-
-/*
- * Pool-sharded (multi-GPU) forms: ONE kernel evaluates this rank's pools AND all-reduces the result over NVLink peer
- * memory (LL protocol, see cfmm_allreduce_ll): the CTA that finishes last pushes the finished vector into the peers'
- * receive areas as 16-byte {value, seq} cells and sums what the peers pushed, in rank order, into peer->reduced
- * ([psi | arb], n_tokens + 1 doubles, for eval -- arb must be psi + n_tokens; n_tokens doubles for hvp).  Because the
- * collective is inside the launch, consecutive launches stay chained by programmatic dependent launch.
- */
-typedef struct cfmm_peer_ll {
-    const void* peer_recv_dev;   /* device array of `world` pointers: every rank's receive area [3][world][stride] cells */
-    uint32_t* done_counter;      /* device, zero-initialised, private to this rank                                      */
-    double* reduced;             /* device, all-reduced output                                                          */
-    int64_t slot_off_cells;      /* (seq % 3) * world * src_stride_cells                                                */
-    int64_t src_stride_cells;
-    uint64_t seq;                /* >= 1, strictly increasing per call, equal on all ranks                              */
-    int32_t rank, world;
-} cfmm_peer_ll;
-
-int cfmm_blocked_eval_fused(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* nu, double* psi, double* arb,
-                            const cfmm_eval_out* out, double* zero_next, int64_t n_zero, const cfmm_peer_ll* peer,
-                            void* stream);
-int cfmm_blocked_hvp_fused(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* hcoef, const double* vt, double* y,
-                           double* zero_next, const cfmm_peer_ll* peer, void* stream);
 
 /*
  * Native outer loop (csrc/cfmm_solver.cu) for problems whose pools are ONE blocked constant-product bucket: the
@@ -205,6 +177,19 @@ typedef struct cfmm_peer_ctx {
 int cfmm_blocked_solve_peer(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* c, const double* a,
                             const uint8_t* eq, const uint8_t* pinned, double* nu, double* psi_out, void* work,
                             const cfmm_solve_params* prm, cfmm_solve_result* res, cfmm_peer_ctx* peer, void* stream);
+
+/*
+ * The same solve (one GPU or sharded, same arguments and results) as ONE persistent cooperative kernel
+ * (csrc/cfmm_persist.cu): every CTA keeps its chunk of pool tiles for the whole solve and runs all evaluation /
+ * Hessian-product / diagonal passes on it; CTA 0 does the n_token-sized vector algebra between passes and broadcasts
+ * the next command; sharded runs all-reduce inside the kernel (LL pushes over NVLink peer memory by CTA 0).  The host
+ * launches once and reads one result struct -- no host round trip per Newton iteration.  status 3 / CFMM_E_STATE: a
+ * peer or CTA never showed up within the spin limit (~3 s) and the kernel gave up.  work: cfmm_persist_solve_work_bytes().
+ */
+int64_t cfmm_persist_solve_work_bytes(const cfmm_blocked_pairs* b, int32_t n_tokens);
+int cfmm_persist_solve(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* c, const double* a,
+                       const uint8_t* eq, const uint8_t* pinned, double* nu, double* psi_out, void* work,
+                       const cfmm_solve_params* prm, cfmm_solve_result* res, cfmm_peer_ctx* peer, void* stream);
 
 /*
  * Batches of SMALL problems (the reference's own sizes: 5 pools, 3-5 tokens), one problem per thread, the whole
@@ -257,18 +242,9 @@ int cfmm_batch_solve(const cfmm_csr_pools* pools, const cfmm_batch* batch, const
                      void* stream);
 
 /*
- * One-shot all-reduce (sum) of out[0..n) = sum_r peer_buf[r][offset .. offset+n) over NVLink peer memory: the ONE
- * collective of a pool-sharded dual evaluation, fused into the launch chain (PDL) right behind the
- * evaluation kernels.  peer_bufs_dev / peer_pads_dev: DEVICE arrays of `world` pointers to every rank's partial
- * buffer / signal pad (torch symmetric memory: hdl.buffer_ptrs_dev, hdl.signal_pad_ptrs_dev).  seq: strictly
- * increasing per call and equal on all ranks; channel 0..3 separates concurrent uses (psi, y).  Callers rotate the
- * partial buffers over 3 slots.  Same bits on every rank (fixed rank order).
- */
-int cfmm_allreduce_oneshot(const void* peer_bufs_dev, const void* peer_pads_dev, int32_t rank, int32_t world,
-                           int64_t offset_elems, int32_t n, double* out, uint32_t seq, int32_t channel, void* stream);
-
-/*
- * Low-latency ("LL") variant of the same all-reduce: every rank PUSHES its n doubles into a receive area of every
+ * All-reduce (sum) of n doubles over NVLink peer memory, the ONE collective of a pool-sharded dual evaluation (SURVEY
+ * 8e), chained into the launch sequence (programmatic dependent launch) right behind the evaluation kernels.
+ * Low-latency ("LL") protocol: every rank PUSHES its n doubles into a receive area of every
  * peer as 16-byte {value, seq} cells (flag travels with the data: one NVLink one-way trip, no hand-shake) and sums what
  * it received, in rank order.  peer_recv_dev: device array of `world` pointers to every rank's receive area
  * [3 slots][world sources][src_stride cells of 16 B]; slot_off_cells = (seq % 3) * world * src_stride.  seq >= 1,

@@ -16,10 +16,8 @@ ninst = 8
 stores = []
 LAYOUT = os.environ.get("LAYOUT", "blocked")
 from cfmm_routing_code_b200 import _lib as _L
-_L.load().cfmm_set_blocked_config(int(os.environ.get("BLOCKED_CFG", "-1")))
 _L.load().cfmm_set_blocked_config(200 + int(os.environ.get("PDL", "1")))
 _L.load().cfmm_set_blocked_config(300 + int(os.environ.get("ROWCAP", "32")))
-_L.load().cfmm_set_blocked_config(400 + int(os.environ.get("TILE_POOLS", "1024")))      # 1024 | 960 | 896 | 0 = planned tiles (equal work per CTA, small first tile)
 for k in range(ninst):
     s = I.synth_const_product(m, n, seed=3 + k)
     hp = cf.HostPools.from_pairs(n, s["idx"], s["reserves"], s["gamma"])

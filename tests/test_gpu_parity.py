@@ -56,7 +56,7 @@ def test_product_eval_matches_oracle(mode):
     _check_eval(hp, H.random_prices(s["prices"], 1), scatter_mode=mode, layout="plain")
 
 
-@pytest.mark.parametrize("m,n", [(20_000, 97), (1500, 700), (1024, 8), (1025, 3000), (70_000, 4096)])
+@pytest.mark.parametrize("m,n", [(20_000, 97), (1500, 700), (896, 8), (897, 3000), (70_000, 4096)])
 def test_blocked_product_eval_matches_oracle(m, n):
     """token-blocked layout (csrc/cfmm_blocked.cu): ragged last tile, few and many tokens per tile"""
     hp, s = H.cp_host_pools(m, n, seed=13)
@@ -64,22 +64,16 @@ def test_blocked_product_eval_matches_oracle(m, n):
     assert any(getattr(b, "blocked", False) for b in st.buckets)
 
 
-@pytest.mark.parametrize("tile_pools", [960, 896, 0])
-def test_blocked_kernels_with_smaller_tiles_match_oracle(tile_pools):
-    lib = _lib.load()
-    assert lib.cfmm_set_blocked_config(400 + tile_pools) == 0
-    try:
-        for m, n in ((20_000, 97), (70_000, 4096), (400_000, 512)):       # the last: several tiles per CTA
-            hp, s = H.cp_host_pools(m, n, seed=m % 97)
-            st, ref = _check_eval(hp, H.random_prices(s["prices"], 1))
-            assert st.buckets[0].c_blocked.pools_per_tile == tile_pools      # 0 = planned tiles, sizes in the descriptors
-            v = np.random.default_rng(2).standard_normal(n)
-            Hs = ref["hess_scaled"]
-            np.testing.assert_allclose(st.hvp(torch.as_tensor(v, **F64)).cpu().numpy(), Hs @ v,
-                                       atol=1e-10 * np.abs(Hs).max())
-            np.testing.assert_allclose(st.hess_diag().cpu().numpy(), np.diag(Hs), atol=1e-11 * np.abs(Hs).max())
-    finally:
-        lib.cfmm_set_blocked_config(400 + 1024)
+def test_blocked_hvp_and_diag_match_oracle_over_several_tiles_per_cta():
+    for m, n in ((20_000, 97), (70_000, 4096), (400_000, 512)):       # the last: several tiles per CTA
+        hp, s = H.cp_host_pools(m, n, seed=m % 97)
+        st, ref = _check_eval(hp, H.random_prices(s["prices"], 1))
+        assert st.buckets[0].c_blocked.pools_per_tile == 896
+        v = np.random.default_rng(2).standard_normal(n)
+        Hs = ref["hess_scaled"]
+        np.testing.assert_allclose(st.hvp(torch.as_tensor(v, **F64)).cpu().numpy(), Hs @ v,
+                                   atol=1e-10 * np.abs(Hs).max())
+        np.testing.assert_allclose(st.hess_diag().cpu().numpy(), np.diag(Hs), atol=1e-11 * np.abs(Hs).max())
 
 
 def test_blocked_layout_falls_back_when_tiles_touch_too_many_tokens():
@@ -265,15 +259,17 @@ def test_cfg2_solve_matches_oracle(linear_solver):
     assert np.max(np.abs(r.psi - ro.psi) / gross.max()) <= 1e-7
 
 
-def test_native_solver_matches_python_solver_and_oracle():
-    """cfmm_blocked_solve (C++ host loop) vs solver.py on the same store, cfg2 size, arbitrage and liquidation"""
+@pytest.mark.parametrize("impl", ["persist", "hostloop"])
+def test_native_solver_matches_python_solver_and_oracle(impl):
+    """the persistent solver kernel (cfmm_persist_solve: one launch per solve) and the C++ host loop (cfmm_blocked_solve)
+    vs solver.py on the same store, cfg2 size, arbitrage and liquidation"""
     hp, s = H.cp_host_pools(10_000, 256, seed=0)
     st = cf.PoolStore(hp)
-    r_nat = cf.solve_pools(hp, cf.Arbitrage(s["prices"]), tol=1e-9, store=st, native=True)
+    r_nat = cf.solve_pools(hp, cf.Arbitrage(s["prices"]), tol=1e-9, store=st, native=impl)
     r_py = cf.solve_pools(hp, cf.Arbitrage(s["prices"]), tol=1e-9, store=st, native=False)
     ro = O.solve(H.oracle_pools(hp), O.Utility.arbitrage(s["prices"]), tol=1e-10)
     assert r_nat.status == "optimal" and r_py.status == "optimal"
-    assert r_nat.info.history == [] and len(r_py.info.history) > 0          # really two different host loops
+    assert r_nat.info.history == [] and len(r_py.info.history) > 0          # really two different loops
     for r in (r_nat, r_py):
         assert abs(r.value - ro.value) <= 1e-8 * abs(ro.value)
         assert abs(r.gap) <= 1e-8 and r.primal_infeas <= 1e-8
@@ -282,10 +278,26 @@ def test_native_solver_matches_python_solver_and_oracle():
     np.testing.assert_allclose(np.concatenate(r_nat.deltas), d_ref, atol=1e-6 * np.abs(d_ref).max())
     basket = I.synth_basket(256, s["prices"], seed=2)
     nu0 = s["prices"] / s["prices"][0]
-    r_nat = cf.solve_pools(hp, cf.Liquidate(0, basket), nu0=nu0, tol=1e-9, store=st)
+    r_nat = cf.solve_pools(hp, cf.Liquidate(0, basket), nu0=nu0, tol=1e-9, store=st, native=impl)
     ro = O.solve(H.oracle_pools(hp), O.Utility.liquidate(256, 0, basket), nu0=nu0, tol=1e-10)
     assert r_nat.status == "optimal" and abs(r_nat.value - ro.value) <= 1e-7 * abs(ro.value)
     np.testing.assert_allclose(r_nat.psi[1:], -basket[1:], atol=1e-7 * basket.max())
+
+
+def test_persistent_and_hostloop_solvers_take_the_same_path():
+    """same method, same constants: iteration / evaluation / HVP counts of the two native loops agree on a problem with
+    several tiles per CTA (400k pools) and on tiny ones (a single tile; fewer tiles than CTAs), from several starts"""
+    for m, n, seed in ((400_000, 2048, 5), (700, 12, 6), (30_000, 700, 7)):
+        hp, s = H.cp_host_pools(m, n, seed=seed)
+        st = cf.PoolStore(hp)
+        for util, nu0 in ((cf.Arbitrage(s["prices"]), None),
+                          (cf.Swap(0, 1, float(hp.reserves[0]) * 0.5), s["prices"] / s["prices"][1])):
+            ra = cf.solve_pools(hp, util, nu0=nu0, tol=1e-8, store=st, native="persist", want_trades=False)
+            rb = cf.solve_pools(hp, util, nu0=nu0, tol=1e-8, store=st, native="hostloop", want_trades=False)
+            assert ra.status == rb.status == "optimal", (m, ra.status, rb.status)
+            assert abs(ra.value - rb.value) <= 1e-9 * max(abs(rb.value), 1e-300) + 1e-12 * abs(rb.dual_value)
+            assert abs(ra.iters - rb.iters) <= 1 and abs(ra.evals - rb.evals) <= 2, (ra.iters, rb.iters, ra.evals, rb.evals)
+            np.testing.assert_allclose(ra.nu, rb.nu, rtol=1e-6)
 
 
 def test_cfg3_small_mixed_solve_matches_oracle():

@@ -53,17 +53,14 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
     assert lib.cfmm_batch_solve(ctypes.byref(cp), ctypes.byref(bt), ctypes.byref(prm), None, None) == -1
 
 
-def test_native_solver_work_buffer_covers_the_hcoef_slab_of_every_tile_layout():
-    """cfmm_blocked_solve carves an hcoef slab of the layout's slab stride from the caller's work buffer: n_tiles * P for
-    fixed tiles, ceil4(n_pools) for planned tiles (pools_per_tile == 0) -- a stride of 0 there once aliased hcoef with
-    the psi buffers (8 MB of device writes past a 0.5 MB buffer at 1M pools)."""
+def test_native_solver_work_buffer_covers_the_hcoef_slab():
+    """cfmm_blocked_solve carves an hcoef slab of the layout's slab stride (n_tiles * P) from the caller's work buffer"""
     lib = _lib.load()
     n = 4096
-    for m, tiles, P in ((1_000_000, 977, 1024), (1_000_000, 1117, 896), (1_000_000, 1480, 0), (1001, 4, 0)):
-        b = _lib.BlockedPairs(m, tiles, P, 0, None, None, None, None, None, None, None, None)
-        stride = tiles * P if P else (m + 3) // 4 * 4
+    for m, tiles in ((1_000_000, 1117), (1001, 2)):
+        b = _lib.BlockedPairs(m, tiles, 896, 0, None, None, None, None, None, None, None, None)
         need = lib.cfmm_blocked_solve_work_bytes(ctypes.byref(b), n)
-        assert need >= 8 * stride + 8 * (2 * (n + 1) + 15 * n), (m, tiles, P, need)
+        assert need >= 8 * tiles * 896 + 8 * (2 * (n + 1) + 15 * n), (m, tiles, need)
 
 
 def test_product_path_fails_loudly_without_a_gpu():
@@ -215,63 +212,30 @@ def test_bounded_product_pools_get_their_own_bucket():
         cf.HostPools.from_lists(2, [[0, 1]], [[0.0, 1.0]], [0.99], ["bounded_product"], [[0.0, 1.0]]).validate()
 
 
-def test_tile_plan_gives_every_cta_the_same_work():
-    """planned tiles (cfmm_set_blocked_config(400)): same pool count (+-4) and same tile count for every CTA, small first
-    tile, 16-byte aligned offsets; the kernels' tile -> CTA map is [T b / G, T (b + 1) / G)"""
-    G = 296
-    t = PL.plan_tiles(1_000_000, G)
-    assert t.sum() == 1_000_000 and len(t) == G * 5 and t.max() <= 1024 and t.min() >= 256
-    per_cta = t.reshape(G, 5)
-    assert np.all(per_cta[:, 0] == 256) and per_cta.sum(1).max() - per_cta.sum(1).min() <= 4
-    assert np.all((np.cumsum(t) - t) % 4 == 0)
-    for m in (1, 3, 255, 257, 10_000, 75_776, 75_780, 303_104, 303_108, 2_000_000, 12_345_679):
-        t = PL.plan_tiles(m, G)
-        T = len(t)
-        assert t.sum() == m and t.min() > 0 and t.max() <= 1024 and np.all((np.cumsum(t) - t) % 4 == 0)
-        g = min(T, G)
-        chains = [t[T * b // g: T * (b + 1) // g].sum() for b in range(g)]
-        assert max(chains) <= -(-m // g) + 1024 and (T <= G or max(chains) - min(chains) <= 8), (m, max(chains), min(chains))
-
-
-@pytest.mark.parametrize("tile_pools", [1024, 960, 896, 0])
-def test_blocked_layout_builder_tables_reproduce_the_scatter(tile_pools):
-    """build_blocked_pairs on CPU tensors: emulate the kernel's row sums and compare with index_add; for every tile
-    size the kernels are instantiated for (cfmm_set_blocked_config(400 + P)) and for planned tiles (400)."""
+def test_blocked_layout_builder_tables_reproduce_the_scatter():
+    """build_blocked_pairs on CPU tensors: emulate the kernel's row sums (cfmm_blocked.cuh: pool phase scatters the flows
+    into row order, one thread sums each row) and compare with index_add"""
     lib = _lib.load()
-    assert lib.cfmm_set_blocked_config(400 + 1000) == -2               # not an instantiated tile size
-    assert lib.cfmm_set_blocked_config(400 + tile_pools) == 0
-    try:
-        P, rs, ts, cap, es = PL.blocked_layout_info(lib)
-    finally:
-        lib.cfmm_set_blocked_config(400 + 1024)
-    planned = tile_pools == 0
-    if planned:                                                         # tables keep the strides of the 1024 layout
-        assert P == 0 and rs == 1024 + 256 + 8 and ts == 1024
-    else:
-        assert P == tile_pools and rs == P + P // 4 + 8 and ts == P
-    for m, n, G in ((5000, 300, 8), (700, 3, 296), (40_000, 2000, 16), (9_000, 50, 2)):
+    assert lib.cfmm_set_blocked_config(400 + 1024) == -2               # tile size is a compile-time constant now
+    P, rs, ts, cap = PL.blocked_layout_info(lib)
+    assert P == 896 and rs == P + P // 4 + 8 and ts == P and cap == 32
+    for m, n in ((5000, 300), (700, 3), (40_000, 2000), (9_000, 50)):
         s = I.synth_const_product(m, n, 0)
         idx = torch.as_tensor(s["idx"].T.astype(np.int64).copy())
-        order, res, t = PL.build_blocked_pairs(idx, n, P, rs, ts, cap, es, n_ctas=G)
+        order, res, t = PL.build_blocked_pairs(idx, n, P, rs, ts, cap)
         assert len(order) + len(res) == m and t is not None
         M, T = t["M"], t["n_tiles"]
         desc = t["desc"].to(torch.int64)
-        if planned:
-            sizes, starts = desc[:, 2], desc[:, 3]
-            assert M == -(-len(order) // 4) * 4 and int(sizes.sum()) == len(order) and int(sizes.max()) <= 1024
-            assert bool((starts == torch.cumsum(sizes, 0) - sizes).all()) and bool((starts % 4 == 0).all())
-            assert T <= G or T % G == 0                                  # a whole number of tiles per CTA
-        else:
-            assert M == T * P
-            starts = torch.arange(T) * P
+        assert M == T * P
         q = torch.arange(len(order))
-        tl = torch.bucketize(q, starts[1:].contiguous(), right=True)
-        l = q - starts[tl]
+        tl = q // P
         f = torch.randn(len(order), 2, dtype=torch.float64)            # flows of (pool, slot), blocked order
         pos = t["pos"].to(torch.int64)[:len(order)] & 0xffffffff
-        g = torch.zeros(T, 2 * 1024, dtype=torch.float64)               # the pool phase scatters into row order
+        g = torch.zeros(T, 2 * P, dtype=torch.float64)                  # the pool phase scatters into row order
         g[tl, pos & 0xffff] = f[:, 0]
         g[tl, pos >> 16] = f[:, 1]
+        padpos = t["pos"].to(torch.int64)[len(order):] & 0xffffffff     # padding pools of the last tile: slots past the real flows
+        assert bool(((padpos & 0xffff) < 2 * P).all() and ((padpos >> 16) < 2 * P).all())
         rows = t["rows"].to(torch.int64) & 0xffffffff
         out = torch.zeros(n, dtype=torch.float64)
         for tile in range(T):
@@ -280,8 +244,7 @@ def test_blocked_layout_builder_tables_reproduce_the_scatter(tile_pools):
             w = rows[tile, :nrow]
             st, ln, lt = w & 0xffff, (w >> 16) & 0x3f, w >> 22
             assert bool((ln[:-1] >= ln[1:]).all()) and int(ln.max()) <= cap     # longest rows first
-            cnt = int(sizes[tile]) if planned else P
-            assert int((st + ln).max()) <= 2 * cnt                      # rows stay inside the tile's 2 cnt flow slots
+            assert int((st + ln).max()) <= 2 * P                        # rows stay inside the tile's 2 P flow slots
             for r in range(nrow):
                 out[t["tok"][tile, lt[r]]] += g[tile, st[r]:st[r] + ln[r]].sum()
         a, b = idx[0][order], idx[1][order]

@@ -69,10 +69,11 @@ def _rank_main(rank, world, port, q):
         util = cf.Arbitrage(s["prices"])
         r_api = cf.solve_pools(hp, util, tol=1e-8, want_trades=False, device=dev)
         r_api2 = cf.solve_pools(hp, util, tol=1e-8, want_trades=False, device=dev)       # second call: cached peer context
+        r_host = cf.solve_pools(hp, util, tol=1e-8, want_trades=False, device=dev, native="hostloop")   # C++ loop + LL kernels
         r_nccl = cf.solve_pools(hp, util, tol=1e-8, want_trades=False, store=st_nccl, native=False)
         r_one = cf.solve_pools(hp, util, tol=1e-8, want_trades=False, store=full)
         out.update(api=(r_api.status, r_api.value, r_api.evals, r_api.hvps, r_api.wall_s, r_api.info.history == []),
-                   api2=(r_api2.status, r_api2.value, r_api2.wall_s), nccl=(r_nccl.status, r_nccl.value, r_nccl.wall_s),
+                   api2=(r_api2.status, r_api2.value, r_api2.wall_s), host=(r_host.status, r_host.value, r_host.wall_s), nccl=(r_nccl.status, r_nccl.value, r_nccl.wall_s),
                    one=(r_one.status, r_one.value, r_one.wall_s))
         g = [torch.zeros(n, dtype=torch.float64, device=dev) for _ in range(world)]
         dist.all_gather(g, torch.as_tensor(r_api.nu, device=dev))
@@ -117,9 +118,10 @@ def test_pool_sharded_kernels_and_solves_match_single_gpu(world):
         st, val, evals, hvps, wall, native = o["api"]
         assert st == "optimal" and native, o["api"]                     # the C++ loop ran (no python history), on shards
         assert o["api2"][0] == "optimal" and abs(o["api2"][1] - val) <= 1e-12 * abs(val)
+        assert o["host"][0] == "optimal" and abs(o["host"][1] - val) <= 1e-9 * abs(val)
         assert o["nccl"][0] == "optimal" and abs(o["nccl"][1] - val) <= 1e-8 * abs(val)
         assert o["one"][0] == "optimal" and abs(o["one"][1] - val) <= 1e-8 * abs(val)
         assert o["nu_bit_identical"] and o["psi_vs_one"] <= 1e-6
         assert o["liq"][0] == "optimal" and abs(o["liq"][1] - o["liq"][2]) <= 1e-7 * abs(o["liq"][2]) and o["liq"][3] <= 1e-7
-    print("\nmulti-GPU timings (rank 0): api", outs[0]["api"], "api2", outs[0]["api2"], "nccl/python", outs[0]["nccl"],
+    print("\nmulti-GPU timings (rank 0): api", outs[0]["api"], "api2", outs[0]["api2"], "hostloop", outs[0]["host"], "nccl/python", outs[0]["nccl"],
           "one GPU", outs[0]["one"])
