@@ -24,9 +24,9 @@ k_blocked(const BlockedArgs A) {
     __syncthreads();
     const long long t_beg = (A.n_tiles * (long long)blockIdx.x) / gridDim.x;
     const long long t_end = (A.n_tiles * (long long)(blockIdx.x + 1)) / gridDim.x;
-    double acc = 0.0;
+    double acc = 0.0, acc2 = 0.0;
     unsigned phase = 0;
-    blocked_pass<P, THREADS, STAGES, MODE, TRADES, HESS, false, true>(A, smem_raw, full, phase, t_beg, t_end, acc);
+    blocked_pass<P, THREADS, STAGES, MODE, TRADES, HESS, false, true>(A, smem_raw, full, phase, t_beg, t_end, acc, acc2);
     if (MODE == 0) cta_accumulate<THREADS>(acc, part, A.arb);
 }
 
@@ -292,7 +292,8 @@ int fill_blocked_args(const cfmm_blocked_pairs* b, BlockedArgs& A) {
     A.desc = reinterpret_cast<const int4*>(b->desc);
     A.zero_next = nullptr; A.n_zero = 0;
     A.slab[0] = A.slab[1] = A.slab[2] = nullptr;
-    A.vec = nullptr; A.out = nullptr; A.arb = nullptr; A.delta = A.lambda = A.hcoef = nullptr;
+    A.vec = nullptr; A.vec2 = nullptr; A.beta = 0.0;
+    A.out = nullptr; A.arb = nullptr; A.delta = A.lambda = A.hcoef = nullptr;
     return CFMM_OK;
 }
 

@@ -56,6 +56,8 @@ struct BlockedArgs {
     const int32_t* tok;           // [n_tiles][kTokMax]
     const int4* desc;             // [n_tiles] (ntok, nrow, 0, 0)
     const double* vec;            // nu (eval) or vt (hvp); unused for diag
+    const double* vec2;           // hvp inside the persistent solver: the direction is vec2 + beta * vec (PCG's p = z + beta p, formed on the fly)
+    double beta;
     double* out;                  // psi / y / diag (+= via one red.add per row)
     double* zero_next;            // optional: buffer of n_zero doubles this launch clears for the NEXT call
     int n_zero;
@@ -131,6 +133,12 @@ __device__ __forceinline__ int row_tok(uint32_t r) { return (int)(r >> 22); }
 // inside the persistent solver, where the vector is rewritten between passes of the same launch
 template <bool COHERENT>
 __device__ __forceinline__ double load_vec(const double* p) { return COHERENT ? __ldcg(p) : __ldg(p); }
+// MODE 1 inside the persistent solver (COHERENT): the gathered entry is vec2[t] + beta * vec[t]
+template <int MODE, bool COHERENT>
+__device__ __forceinline__ double gather_vec(const BlockedArgs& A, int t) {
+    if (MODE == 1 && COHERENT) return fma(A.beta, __ldcg(A.vec + t), __ldcg(A.vec2 + t));
+    return load_vec<COHERENT>(A.vec + t);
+}
 
 // Shared memory of one CTA of the TMA-staged pass: STAGES ring stages, nu_local [P], flows in row order [2P]
 template <int P, int STAGES>
@@ -141,10 +149,11 @@ constexpr size_t pass_smem_bytes(int nf) {
 // One pass over this CTA's chunk of tiles [t_beg, t_end): MODE 0 evaluation (psi += flows, acc += nu'flows),
 // 1 Hessian-vector product (y += Hs vt), 2 Hessian diagonal.  `full` = STAGES initialised mbarriers, `phase` = their
 // current parities as a bit mask (carried across passes by the persistent kernel; 0 in a fresh launch).
+// acc: eval: sum of nu'flows (= arb); persistent hvp: p'Hp, with acc2 = p'diag(H)p.
 // PDL: the standalone kernels wait for the previous grid only after their first tiles are in flight.
 template <int P, int THREADS, int STAGES, int MODE, bool TRADES, bool HESS, bool COHERENT, bool PDL>
 __device__ __forceinline__ void blocked_pass(const BlockedArgs& A, unsigned char* smem_raw, uint64_t* full, unsigned& phase,
-                                             long long t_beg, long long t_end, double& acc) {
+                                             long long t_beg, long long t_end, double& acc, double& acc2) {
     constexpr int NF = (MODE == 0) ? 3 : 1;
     using St = Stage<P, NF>;
     St* stages = reinterpret_cast<St*>(smem_raw);
@@ -176,7 +185,7 @@ __device__ __forceinline__ void blocked_pass(const BlockedArgs& A, unsigned char
         mbar_wait(&full[0], phase & 1u);
         if (MODE != 2) {
             const int ntok = stages[0].desc.x;
-            for (int t = tid; t < ntok; t += THREADS) nul[t] = load_vec<COHERENT>(A.vec + stages[0].tok[t]);
+            for (int t = tid; t < ntok; t += THREADS) nul[t] = gather_vec<MODE, COHERENT>(A, stages[0].tok[t]);
         }
     }
     __syncthreads();
@@ -203,8 +212,13 @@ __device__ __forceinline__ void blocked_pass(const BlockedArgs& A, unsigned char
                     EvalOp::apply<TRADES, HESS>(A, tile * P + l, S.a[0][l], S.a[NF > 1 ? 1 : 0][l], S.a[NF > 2 ? 2 : 0][l],
                                                 nul[li & 0xffffu], nul[li >> 16], f0[u], f1[u], acc);
                 } else if (MODE == 1) {
-                    f0[u] = S.a[0][l] * (nul[li & 0xffffu] - nul[li >> 16]);
+                    const double pa = nul[li & 0xffffu], pb = nul[li >> 16], h = S.a[0][l];
+                    f0[u] = h * (pa - pb);
                     f1[u] = -f0[u];
+                    if (COHERENT) {                    // the persistent solver's PCG: p'Hp and p'diag(H)p come with the pass
+                        acc = fma(f0[u], pa - pb, acc);
+                        acc2 = fma(h, fma(pa, pa, pb * pb), acc2);
+                    }
                 } else {
                     f0[u] = S.a[0][l];
                     f1[u] = f0[u];
@@ -229,7 +243,7 @@ __device__ __forceinline__ void blocked_pass(const BlockedArgs& A, unsigned char
 #pragma unroll
                 for (int k = 0; k < NPRE; ++k) {
                     const int t = tid + k * THREADS;
-                    pre[k] = (t < ntok_n) ? load_vec<COHERENT>(A.vec + stages[nstage].tok[t]) : 0.0;
+                    pre[k] = (t < ntok_n) ? gather_vec<MODE, COHERENT>(A, stages[nstage].tok[t]) : 0.0;
                 }
             }
         }

@@ -463,7 +463,7 @@ class PeerContext:
         w = self.world
         # receive areas: [3 slots][world sources][n cells of {value, sequence flag}] (zero = "nothing received yet")
         self.sym_acc = symm.empty((3 * w * (n + 1) * 2,), **f64); self.sym_acc.zero_()
-        self.sym_y = symm.empty((3 * w * n * 2,), **f64); self.sym_y.zero_()
+        self.sym_y = symm.empty((3 * w * (n + 2) * 2,), **f64); self.sym_y.zero_()      # n-vectors (+2: the persistent solver appends p'Hp, p'Dp)
         self.hdl_acc = symm.rendezvous(self.sym_acc, group)
         self.hdl_y = symm.rendezvous(self.sym_y, group)
         self.red_acc = torch.zeros(n + 1, **f64)

@@ -187,6 +187,8 @@ int cfmm_blocked_solve_peer(const cfmm_blocked_pairs* b, int32_t n_tokens, const
  * peer or CTA never showed up within the spin limit (~3 s) and the kernel gave up.  work: cfmm_persist_solve_work_bytes().
  */
 int64_t cfmm_persist_solve_work_bytes(const cfmm_blocked_pairs* b, int32_t n_tokens);
+int cfmm_set_persist_mode(int32_t mode);        /* experiments: 0 = distributed vector algebra (default), 1 = CTA 0 does it */
+int cfmm_persist_last_profile(int64_t* out8);   /* development aid: CTA 0's cycle totals of the last persistent solve */
 int cfmm_persist_solve(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* c, const double* a,
                        const uint8_t* eq, const uint8_t* pinned, double* nu, double* psi_out, void* work,
                        const cfmm_solve_params* prm, cfmm_solve_result* res, cfmm_peer_ctx* peer, void* stream);
