@@ -129,14 +129,15 @@ __device__ __forceinline__ int row_start(uint32_t r) { return (int)(r & 0xffffu)
 __device__ __forceinline__ int row_len(uint32_t r) { return (int)((r >> 16) & 0x3fu); }
 __device__ __forceinline__ int row_tok(uint32_t r) { return (int)(r >> 22); }
 
-// gather of the price / direction vector: through the read-only path in a kernel of its own, through L2 (ld.global.cg)
-// inside the persistent solver, where the vector is rewritten between passes of the same launch
+// gather of the price / direction vector: through the read-only path (ld.global.nc) in a kernel of its own; inside the
+// persistent solver the vector is rewritten between passes of the same launch, so it is a plain (coherent) load there --
+// the grid barrier between the writer and this pass (fence + atomic / ld.acquire) makes the new values visible
 template <bool COHERENT>
-__device__ __forceinline__ double load_vec(const double* p) { return COHERENT ? __ldcg(p) : __ldg(p); }
+__device__ __forceinline__ double load_vec(const double* p) { return COHERENT ? *p : __ldg(p); }
 // MODE 1 inside the persistent solver (COHERENT): the gathered entry is vec2[t] + beta * vec[t]
 template <int MODE, bool COHERENT>
 __device__ __forceinline__ double gather_vec(const BlockedArgs& A, int t) {
-    if (MODE == 1 && COHERENT) return fma(A.beta, __ldcg(A.vec + t), __ldcg(A.vec2 + t));
+    if (MODE == 1 && COHERENT) return fma(A.beta, A.vec[t], A.vec2[t]);
     return load_vec<COHERENT>(A.vec + t);
 }
 

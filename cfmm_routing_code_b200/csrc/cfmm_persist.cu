@@ -588,6 +588,12 @@ k_solve_persist(const __grid_constant__ PersistArgs S) {
 // A sharded solve all-reduces inside the slice phase: each lane pushes ITS token to the peers and sums what they pushed
 // (rank order) -- the exchange is spread over all CTAs instead of serialised in one.
 // =====================================================================================================================
+// Loads of data another CTA wrote before the last grid barrier: PLAIN loads.  The barrier is fence + bar.sync + atomic on
+// the writer's side and ld.acquire.gpu + bar.sync on the reader's, which orders weak accesses across it (and the acquire
+// refreshes this SM's L1); ld.global.cg would also be correct but B200 issues those ~100 ns apart per thread (measured:
+// 72 of them = 8 us), while plain loads pipeline.
+__device__ __forceinline__ double ldw(const double* p) { return *p; }
+
 constexpr int kSliceMax = 256;                   // slices (>= 1): min(256, ceil(n / 16))
 constexpr int kQ = 10;                           // partial quantities per phase
 
@@ -706,7 +712,7 @@ k_solve_dist(const __grid_constant__ DistArgs D) {
         if (phase == PH_HVP) {                       // p'Hp and p'diag(H)p first: alpha feeds the element-wise update
             if (tid == 0) {
                 const double* yb = D.y2[ds.yb];
-                double pHp = __ldcg(yb + n), pdp = __ldcg(yb + n + 1);
+                double pHp = ldw(yb + n), pdp = ldw(yb + n + 1);
                 if (multi) {                         // one thread of the grid pushes them, every CTA sums what the peers pushed
                     const long long slot = (long long)(seq % 3) * S.world * (n + 2);
                     const bool owner = blockIdx.x == (nsl - 1) % G;
@@ -728,11 +734,11 @@ k_solve_dist(const __grid_constant__ DistArgs D) {
             for (int k = 0; k < kQ; ++k) q[k] = 0.0;
             for (int j = lo + lane; j < hi; j += 32) {
                 if (phase == PH_KKT) {
-                    double pj = __ldcg(S.acc[set] + j);
-                    const double nj = __ldcg(S.nu[set] + j), aj = S.a[j], cj = S.c[j], lbj = __ldcg(S.lb + j);
+                    double pj = ldw(S.acc[set] + j);
+                    const double nj = ldw(S.nu[set] + j), aj = S.a[j], cj = S.c[j], lbj = ldw(S.lb + j);
                     const unsigned char ej = S.eq[j], fj = S.fixed[j];
                     const bool wl = set != cur;      // trial point: also grad_cur . (nu_trial - nu_cur)
-                    const double np = wl ? __ldcg(S.nu[cur] + j) : 0.0, gp = wl ? __ldcg(S.grad[cur] + j) : 0.0;
+                    const double np = wl ? ldw(S.nu[cur] + j) : 0.0, gp = wl ? ldw(S.grad[cur] + j) : 0.0;
                     if (multi) {
                         int ab = 0;
                         pj = ll_exchange(pj, S.recv_acc, (long long)(seq % 3) * S.world * (n + 1), n + 1, j, S.rank, S.world, seq, true, S.ctl, &ab);
@@ -749,8 +755,8 @@ k_solve_dist(const __grid_constant__ DistArgs D) {
                     q[6] = fmax(q[6], fabs(g) * f);
                     q[7] = fmax(q[7], fmax(fabs(aj), fj ? 0.0 : fabs(pj)));
                 } else if (phase == PH_DIAG) {
-                    double d = __ldcg(S.diag + j);
-                    const double f = __ldcg(S.fr[cur] + j), g = __ldcg(S.pg[cur] + j);
+                    double d = ldw(S.diag + j);
+                    const double f = ldw(S.fr[cur] + j), g = ldw(S.pg[cur] + j);
                     if (multi) {
                         int ab = 0;
                         d = ll_exchange(d, S.recv_vec, (long long)(seq % 3) * S.world * (n + 2), n + 2, j, S.rank, S.world, seq, true, S.ctl, &ab);
@@ -761,9 +767,9 @@ k_solve_dist(const __grid_constant__ DistArgs D) {
                     q[0] += r * z;
                     q[6] = fmax(q[6], fabs(g));
                 } else if (phase == PH_HVP) {
-                    double yv = __ldcg(D.y2[ds.yb] + j);
-                    const double pp = __ldcg(S.p + j), zz = __ldcg(S.z + j), xx = __ldcg(S.x + j), rr = __ldcg(S.r + j),
-                                 mm = __ldcg(S.minv + j), g = __ldcg(S.pg[cur] + j);
+                    double yv = ldw(D.y2[ds.yb] + j);
+                    const double pp = ldw(S.p + j), zz = ldw(S.z + j), xx = ldw(S.x + j), rr = ldw(S.r + j),
+                                 mm = ldw(S.minv + j), g = ldw(S.pg[cur] + j);
                     if (multi) {
                         int ab = 0;
                         yv = ll_exchange(yv, S.recv_vec, (long long)(seq % 3) * S.world * (n + 2), n + 2, j, S.rank, S.world, seq, true, S.ctl, &ab);
@@ -782,10 +788,10 @@ k_solve_dist(const __grid_constant__ DistArgs D) {
                     q[1] += g * xn;                  // pg . x: is x a descent direction (needed when PCG stops here)
                     D.y2[ds.yb ^ 1][j] = 0.0;
                 } else {                             // PH_STEP: direction (first step of a search) + trial point
-                    const double g = __ldcg(S.pg[cur] + j), xx = __ldcg(S.x + j), v = __ldcg(S.nu[cur] + j), l = __ldcg(S.lb + j);
+                    const double g = ldw(S.pg[cur] + j), xx = ldw(S.x + j), v = ldw(S.nu[cur] + j), l = ldw(S.lb + j);
                     double d;
                     if (ds.first_step) { d = ds.dir_ok ? xx : -g * ds.imx; S.dt[j] = d; }
-                    else d = __ldcg(S.dt + j);
+                    else d = ldw(S.dt + j);
                     const double e = fmin(fmax(ds.alpha * d, -20.0), 20.0);
                     S.nu[cur ^ 1][j] = S.fixed[j] ? S.c[j] : fmax(v * exp(e), l);
                     S.acc[cur ^ 1][j] = 0.0;
@@ -793,7 +799,7 @@ k_solve_dist(const __grid_constant__ DistArgs D) {
             }
             if (s0 == nsl - 1 && lane == 0) {        // the extras behind the vectors
                 if (phase == PH_KKT) {
-                    double arb = __ldcg(S.acc[set] + n);
+                    double arb = ldw(S.acc[set] + n);
                     if (multi) {
                         int ab = 0;
                         arb = ll_exchange(arb, S.recv_acc, (long long)(seq % 3) * S.world * (n + 1), n + 1, n, S.rank, S.world, seq, true, S.ctl, &ab);
@@ -817,17 +823,16 @@ k_solve_dist(const __grid_constant__ DistArgs D) {
         grid_barrier(S.ctl, &ds);
         const long long tp4 = clock64();
         // ---- decide phase: slice partials -> totals (slice order: same bits in every CTA and on every rank)
-        if (warp == 0 && phase != PH_STEP) {
-#pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                double t = 0.0;
-                for (int s = lane; s < nsl; s += 32) {
-                    const double v = __ldcg(P0 + k * kSliceMax + s);
-                    t = (k == 6 || k == 7) ? fmax(t, v) : t + v;
-                }
-                t = (k == 6 || k == 7) ? warp_max(t) : warp_sum(t);
-                if (lane == 0) tot[k] = t;
+        if (warp < 9 && phase != PH_STEP) {          // warp k totals quantity k: all loads of the phase in flight at once
+            const int k = warp;
+            const bool is_max = k == 6 || k == 7;
+            double t = 0.0;
+            for (int s = lane; s < nsl; s += 32) {
+                const double v = ldw(P0 + k * kSliceMax + s);
+                t = is_max ? fmax(t, v) : t + v;
             }
+            t = is_max ? warp_max(t) : warp_sum(t);
+            if (lane == 0) tot[k] = t;
         }
         __syncthreads();
         if (tid == 0) {
@@ -907,8 +912,8 @@ k_solve_dist(const __grid_constant__ DistArgs D) {
         for (int s0 = blockIdx.x + warp * G; s0 < nsl; s0 += (PT / 32) * G) {
             const int lo = (int)((long long)n * s0 / nsl), hi = (int)((long long)n * (s0 + 1) / nsl);
             for (int j = lo + lane; j < hi; j += 32) {
-                S.psi_out[j] = __ldcg(D.accr[cur] + j);
-                if (cur != 0) S.nu_out[j] = __ldcg(S.nu[cur] + j);
+                S.psi_out[j] = ldw(D.accr[cur] + j);
+                if (cur != 0) S.nu_out[j] = ldw(S.nu[cur] + j);
             }
         }
         if (blockIdx.x == 0 && tid == 0) {

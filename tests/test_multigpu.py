@@ -69,6 +69,10 @@ def _rank_main(rank, world, port, q):
         util = cf.Arbitrage(s["prices"])
         r_api = cf.solve_pools(hp, util, tol=1e-8, want_trades=False, device=dev)
         r_api2 = cf.solve_pools(hp, util, tol=1e-8, want_trades=False, device=dev)       # second call: cached peer context
+        import ctypes
+        prof = (ctypes.c_int64 * 16)()
+        st_peer.lib.cfmm_persist_last_profile(prof)
+        out["prof_us"] = [round(x / 1965.0) for x in prof][:8]
         r_host = cf.solve_pools(hp, util, tol=1e-8, want_trades=False, device=dev, native="hostloop")   # C++ loop + LL kernels
         r_nccl = cf.solve_pools(hp, util, tol=1e-8, want_trades=False, store=st_nccl, native=False)
         r_one = cf.solve_pools(hp, util, tol=1e-8, want_trades=False, store=full)
@@ -123,5 +127,6 @@ def test_pool_sharded_kernels_and_solves_match_single_gpu(world):
         assert o["one"][0] == "optimal" and abs(o["one"][1] - val) <= 1e-8 * abs(val)
         assert o["nu_bit_identical"] and o["psi_vs_one"] <= 1e-6
         assert o["liq"][0] == "optimal" and abs(o["liq"][1] - o["liq"][2]) <= 1e-7 * abs(o["liq"][2]) and o["liq"][3] <= 1e-7
-    print("\nmulti-GPU timings (rank 0): api", outs[0]["api"], "api2", outs[0]["api2"], "hostloop", outs[0]["host"], "nccl/python", outs[0]["nccl"],
+    print("\npersistent solver profile of rank 0 (us: pass eval/hvp/diag, barrier A, slice phase, barrier B, decide):", outs[0].get("prof_us"))
+    print("multi-GPU timings (rank 0): api", outs[0]["api"], "api2", outs[0]["api2"], "hostloop", outs[0]["host"], "nccl/python", outs[0]["nccl"],
           "one GPU", outs[0]["one"])
