@@ -181,13 +181,14 @@ int cfmm_blocked_solve_peer(const cfmm_blocked_pairs* b, int32_t n_tokens, const
 /*
  * The same solve (one GPU or sharded, same arguments and results) as ONE persistent cooperative kernel
  * (csrc/cfmm_persist.cu): every CTA keeps its chunk of pool tiles for the whole solve and runs all evaluation /
- * Hessian-product / diagonal passes on it; CTA 0 does the n_token-sized vector algebra between passes and broadcasts
- * the next command; sharded runs all-reduce inside the kernel (LL pushes over NVLink peer memory by CTA 0).  The host
- * launches once and reads one result struct -- no host round trip per Newton iteration.  status 3 / CFMM_E_STATE: a
- * peer or CTA never showed up within the spin limit (~3 s) and the kernel gave up.  work: cfmm_persist_solve_work_bytes().
+ * Hessian-product / diagonal passes on it; every CTA also owns slices of the n_tokens-long vectors and updates them
+ * between passes (two grid barriers per pass), and all CTAs run the same scalar state machine on the same reduced
+ * sums, so they agree on the next pass without a broadcast; sharded runs all-reduce inside the slice update (LL pushes
+ * over NVLink peer memory, every lane its own token).  The host launches once and reads one result struct -- no host
+ * round trip per Newton iteration.  status 3 / CFMM_E_STATE: a peer or CTA never showed up within the spin limit (~3 s)
+ * and the kernel gave up.  work: cfmm_persist_solve_work_bytes().
  */
 int64_t cfmm_persist_solve_work_bytes(const cfmm_blocked_pairs* b, int32_t n_tokens);
-int cfmm_set_persist_mode(int32_t mode);        /* experiments: 0 = distributed vector algebra (default), 1 = CTA 0 does it */
 int cfmm_persist_last_profile(int64_t* out8);   /* development aid: CTA 0's cycle totals of the last persistent solve */
 int cfmm_persist_solve(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* c, const double* a,
                        const uint8_t* eq, const uint8_t* pinned, double* nu, double* psi_out, void* work,

@@ -14,8 +14,7 @@ for rep in range(3):
     t0 = time.perf_counter(); st = cf.PoolStore(hp, validate=False); torch.cuda.synchronize(); tb = time.perf_counter() - t0
 print(f"PoolStore build (upload + layout) {1e3*tb:.2f} ms")
 import ctypes
-for impl, mode in (("persist", 0), ("persist", 1), ("hostloop", 0)):
-    st.lib.cfmm_set_persist_mode(mode)
+for impl, mode in (("persist", 0), ("hostloop", 0)):
     for tol in (1e-6, 1e-9):
         ws = []
         for rep in range(5):
@@ -35,7 +34,6 @@ for impl, mode in (("persist", 0), ("persist", 1), ("hostloop", 0)):
             else:
                 print(f"   CTA0 profile (us): pass eval {us[0]:.0f} hvp {us[1]:.0f} diag {us[2]:.0f} | wait-grid {us[3]:.0f} | "
                       f"algebra after eval {us[4]:.0f} hvp {us[5]:.0f} diag {us[6]:.0f}")
-st.lib.cfmm_set_persist_mode(0)
 ws = []
 for rep in range(5):
     torch.cuda.synchronize(); t0 = time.perf_counter()
