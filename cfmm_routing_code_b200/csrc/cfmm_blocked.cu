@@ -87,7 +87,7 @@ __device__ __forceinline__ void prefetch_pools_l2(const BlockedArgs& A, long lon
 }
 
 template <int P, int THREADS, int STAGES, int MODE, bool TRADES, bool HESS>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, kCtasPerSm)
 k_blocked_regs(const BlockedArgs A) {
     constexpr int NF = (MODE == 0) ? 3 : 1;
     constexpr int NPOOL = P / THREADS;
@@ -265,7 +265,7 @@ int launch_regs(const BlockedArgs& A, cudaStream_t st) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         attr = true;
     }
-    const long long cap = 2LL * num_sms();
+    const long long cap = (long long)kCtasPerSm * num_sms();
     const int grid = (int)(A.n_tiles < cap ? A.n_tiles : cap);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T); cfg.dynamicSmemBytes = sm; cfg.stream = st;

@@ -20,11 +20,18 @@
 
 namespace cfmm {
 
-constexpr int kTileP = 896;          // pools per tile: 1M pools = 1117 tiles over 296 resident CTAs -> 4 x 896 on the critical
+#ifndef CFMM_TILE_P
+#define CFMM_TILE_P 896              // (build-time knobs for tile-size experiments: -DCFMM_TILE_P=... -DCFMM_CTAS_PER_SM=...)
+#endif
+#ifndef CFMM_CTAS_PER_SM
+#define CFMM_CTAS_PER_SM 2
+#endif
+constexpr int kTileP = CFMM_TILE_P;  // pools per tile: 1M pools = 1117 tiles over 296 resident CTAs -> 4 x 896 on the critical
                                      // path (1024: 977 tiles -> 4 x 1024); measured fastest of 1024 / 960 / 896 / planned (profiles/r2a_*)
 constexpr int kTileT = kTileP / 2;   // threads per CTA: two pools per thread
 constexpr int kTileStages = 2;       // TMA ring depth
-constexpr int kCtasPerSm = 2;
+constexpr int kCtasPerSm = CFMM_CTAS_PER_SM;
+static_assert(kTileP % 64 == 0 && kTileP <= 1024, "tile size: whole warps of two-pool threads, 10-bit local token ids");
 
 template <int P>
 struct BlockedCfg {
