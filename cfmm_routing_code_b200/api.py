@@ -78,7 +78,7 @@ class Result:
     iters: int
     evals: int
     hvps: int
-    status: str                   # 'optimal' | 'max_iter' | 'stalled'   (cf. prob.status)
+    status: str                   # 'optimal' | 'max_iter' | 'stalled' | 'infeasible' (suspected)   (cf. prob.status)
     wall_s: float
     info: Optional[SolveInfo] = None
 
@@ -110,6 +110,27 @@ def _check_structurally_feasible(hp: HostPools, spec) -> None:
         if len(bad):
             raise ValueError(f"infeasible problem: token(s) {bad.tolist()} must be traded (non-zero endowment / demand) "
                              "but appear in no pool")
+
+
+def infeasible_suspected(spec, nu, psi, status: str) -> bool:
+    """cvxpy would set prob.status = 'infeasible' (arbitrage.py:82 never looks) when no trade meets the constraints on
+    psi.  The dual method cannot prove that, but it shows an unmistakable pattern: the solve ends uncertified AND the price
+    of a token whose constraint is still badly violated has run away -- to the floor (a token that must be sold but
+    nobody can take: liquidation.py:77-80 with an unroutable basket entry) or to the sky (a token that must be received
+    in a quantity the pools cannot deliver).  Returns True for that pattern only."""
+    if status == "optimal":
+        return False
+    nu = np.asarray(nu, float); psi = np.asarray(psi, float)
+    a = np.asarray(spec.a, float); eq = np.asarray(spec.eq, bool); pinned = np.asarray(spec.pinned, bool)
+    s = psi + a
+    viol = np.where(pinned, 0.0, np.where(eq, np.abs(s), np.maximum(-s, 0.0)))
+    scale = max(float(np.abs(a).max(initial=0.0)), float(np.abs(np.where(pinned, 0.0, psi)).max(initial=0.0)), 1e-300)
+    bad = viol > 1e-3 * scale
+    if not bad.any() or not np.all(np.isfinite(nu)):
+        return bool(bad.any())
+    ok = ~bad & (nu > 0)
+    ref = float(np.median(nu[ok])) if ok.any() else float(np.max(np.abs(np.asarray(spec.c, float)), initial=1.0))
+    return bool(np.any(bad & ((nu <= 1e-8 * ref) | (nu >= 1e8 * ref))))
 
 
 SMALL_POOLS = 256        # up to here one GPU thread walks all pools of a problem faster than a launch per evaluation
@@ -231,10 +252,12 @@ def solve_pools(hp: HostPools, utility, nu0=None, tol: float = 1e-8, max_iter: i
         ptr = hp.pool_ptr
         deltas = [d[ptr[i]:ptr[i + 1]] for i in range(hp.m)] if hp.m <= 100_000 else [d]
         lambdas = [l[ptr[i]:ptr[i + 1]] for i in range(hp.m)] if hp.m <= 100_000 else [l]
-    return Result(value=info.primal_value, psi=info.psi.cpu().numpy(), deltas=deltas, lambdas=lambdas,
-                  nu=info.nu.cpu().numpy(), dual_value=info.dual_value, gap=info.gap,
+    psi_h, nu_h = info.psi.cpu().numpy(), info.nu.cpu().numpy()
+    status = "infeasible" if infeasible_suspected(spec, nu_h, psi_h, info.status) else info.status
+    return Result(value=info.primal_value, psi=psi_h, deltas=deltas, lambdas=lambdas,
+                  nu=nu_h, dual_value=info.dual_value, gap=info.gap,
                   primal_infeas=info.primal_infeas, iters=info.iters, evals=info.evals, hvps=info.hvps,
-                  status=info.status, wall_s=info.wall_s, info=info)
+                  status=status, wall_s=info.wall_s, info=info)
 
 
 def solve_sweep(local_indices, reserves, fees, kinds, weights, utilities, n_tokens: Optional[int] = None,

@@ -64,6 +64,10 @@ class CsrStore:
         return self._work
 
 
+SMALL_BATCH = 512            # up to this many problems a warp per problem beats a thread per problem
+LANES_SMALL_BATCH = 32
+
+
 @torch.no_grad()
 def solve_batch_device(store: CsrStore, c: torch.Tensor, a: torch.Tensor, flags: torch.Tensor, nu: torch.Tensor,
                        tol: float = 1e-8, want_trades: bool = True, pool_range: Optional[torch.Tensor] = None,
@@ -84,8 +88,12 @@ def solve_batch_device(store: CsrStore, c: torch.Tensor, a: torch.Tensor, flags:
     if want_trades:
         delta = torch.zeros(B if shared else 1, store.nnz, **f64)
         lam = torch.zeros(B if shared else 1, store.nnz, **f64)
-    if lanes is not None:           # 1 = a problem per thread (default), 32 = a problem per warp (see cfmm_small.cu)
-        _lib.check(store.lib.cfmm_set_batch_lanes(int(lanes)), "cfmm_set_batch_lanes")
+    if lanes is None:
+        # a problem per warp for small batches (latency: the two-asset.py sweep of 50 problems takes 0.75 ms that way
+        # against 1.14 ms with a thread per problem), a problem per thread for large ones (throughput: 4096 problems
+        # 1.27 ms against 2.67 ms) -- measured on B200, profiles/r2a_batch_lanes.txt
+        lanes = LANES_SMALL_BATCH if B <= SMALL_BATCH else 1
+    _lib.check(store.lib.cfmm_set_batch_lanes(int(lanes)), "cfmm_set_batch_lanes")
     work = store.work(B, nnz_max)
     batch = _lib.Batch(B, None if shared else pool_range.data_ptr(), c.data_ptr(), a.data_ptr(), flags.data_ptr(),
                        nu.data_ptr(), psi.data_ptr(), stats.data_ptr(),
@@ -113,7 +121,7 @@ def pack_utilities(utilities: Sequence, n: int, nu0=None):
 def solve_batch(hp: HostPools, utilities: Sequence, nu0=None, tol: float = 1e-8, device="cuda",
                 want_trades: bool = True, store: Optional[CsrStore] = None, max_inner: int = 100):
     """All problems (same pools, one utility each) in one launch.  Returns a list of api.Result."""
-    from .api import Result
+    from .api import Result, infeasible_suspected
     t0 = time.perf_counter()
     from .api import _check_structurally_feasible
     for u in utilities:
@@ -137,9 +145,12 @@ def solve_batch(hp: HostPools, utilities: Sequence, nu0=None, tol: float = 1e-8,
         s = stats_h[p]
         deltas = [d_h[p, ptr[i]:ptr[i + 1]] for i in range(hp.m)] if want_trades else []
         lambdas = [l_h[p, ptr[i]:ptr[i + 1]] for i in range(hp.m)] if want_trades else []
+        status = names[int(s[7])]
+        if status in ("max_iter", "stalled") and infeasible_suspected(utilities[p].spec(hp.n_tokens), nu_h[p], psi_h[p], status):
+            status = "infeasible"
         out.append(Result(value=float(s[0]), psi=psi_h[p], deltas=deltas, lambdas=lambdas, nu=nu_h[p],
                           dual_value=float(s[1]), gap=float(s[2]), primal_infeas=float(s[3]), iters=int(s[5]),
-                          evals=int(s[6]), hvps=0, status=names[int(s[7])], wall_s=wall, info=None))
+                          evals=int(s[6]), hvps=0, status=status, wall_s=wall, info=None))
     return out
 
 

@@ -350,6 +350,27 @@ def test_full_size_solve_reaches_1e6_gap():
     assert r.value > 0
 
 
+def test_infeasible_problem_is_flagged_by_every_solver_path():
+    """a token that must be received in a quantity no pool can deliver (cvxpy: prob.status == 'infeasible'): the python
+    loop, the persistent kernel and the per-thread batch solver all end uncertified and the API reports 'infeasible'"""
+    class Need:                                   # psi_1 == +100 with 10 in the only pool; objective: psi_0
+        def spec(self, n):
+            return cf.DualSpec(np.array([1.0, 0.0]), np.array([0.0, -100.0]), np.array([False, True]), np.array([True, False]))
+    hp_list = cf.HostPools.from_lists(2, [[0, 1]], [[10.0, 10.0]], [0.997], ["product"], [None])
+    hp_pair = cf.HostPools.from_pairs(2, [[0, 1]], [[10.0, 10.0]], [0.997])
+    assert cf.solve_pools(hp_list, Need(), method="pools", native=False, max_iter=60).status == "infeasible"
+    assert cf.solve_pools(hp_pair, Need(), method="pools", max_iter=60).status == "infeasible"          # persistent kernel
+    assert cf.solve_pools(hp_list, Need(), method="thread", max_iter=60).status == "infeasible"
+    class Fine(Need):
+        def spec(self, n):
+            return cf.DualSpec(np.array([1.0, 0.0]), np.array([0.0, -5.0]), np.array([False, True]), np.array([True, False]))
+    for kw in (dict(method="pools", native=False), dict(method="thread")):
+        r = cf.solve_pools(hp_list, Fine(), **kw)
+        assert r.status == "optimal" and abs(r.psi[1] - 5.0) <= 1e-6
+    r = cf.solve_pools(hp_pair, Fine(), method="pools")
+    assert r.status == "optimal" and abs(r.psi[1] - 5.0) <= 1e-6 and r.info.history == []
+
+
 def test_error_codes_and_empty_bucket():
     lib = _lib.load()
     b = _lib.Bucket(_lib.KIND_PRODUCT, 2, 10, 10, None, None, None, None, None, None)

@@ -139,6 +139,28 @@ def test_cpu_twin_cfg4_small_liquidation_matches_oracle():
     assert np.abs(r.psi.numpy()[1:] + basket[1:]).max() <= 1e-7 * basket.max()
 
 
+def test_infeasible_problems_are_flagged_not_reported_optimal():
+    """cvxpy's prob.status == 'infeasible' (arbitrage.py:82): a token that must be RECEIVED in a quantity the pools cannot
+    deliver -- the dual is unbounded (its price runs away) and the solve ends uncertified; api.infeasible_suspected turns
+    that pattern into status 'infeasible'.  A feasible problem that merely ran out of iterations keeps 'max_iter'."""
+    from cfmm_routing_code_b200.api import infeasible_suspected
+    hp = cf.HostPools.from_lists(2, [[0, 1]], [[10.0, 10.0]], [0.997], ["product"], [None])
+    spec = cf.DualSpec(np.array([1.0, 0.0]), np.array([0.0, -100.0]), np.array([False, True]), np.array([True, False]))
+    r = solve_dual(OracleEvaluator(hp), spec, tol=1e-8, max_inner=60)
+    assert r.status != "optimal"
+    assert infeasible_suspected(spec, r.nu.numpy(), r.psi.numpy(), r.status)
+    # the same pool can deliver 5 units: feasible, certified, not flagged
+    spec2 = cf.DualSpec(np.array([1.0, 0.0]), np.array([0.0, -5.0]), np.array([False, True]), np.array([True, False]))
+    r2 = solve_dual(OracleEvaluator(hp), spec2, tol=1e-8)
+    assert r2.status == "optimal" and not infeasible_suspected(spec2, r2.nu.numpy(), r2.psi.numpy(), r2.status)
+    assert abs(float(r2.psi[1]) - 5.0) <= 1e-7
+    # a feasible problem stopped early is 'max_iter', not 'infeasible'
+    hp3, s3 = H.cp_host_pools(2000, 40, seed=3)
+    sp3 = cf.Arbitrage(s3["prices"]).spec(40)
+    r3 = solve_dual(OracleEvaluator(hp3), sp3, tol=1e-12, max_inner=2)
+    assert r3.status == "max_iter" and not infeasible_suspected(sp3, r3.nu.numpy(), r3.psi.numpy(), r3.status)
+
+
 def test_solver_logic_on_random_small_problems_matches_the_oracle():
     """the product's python outer loop (dense Newton path, look-ahead on) on 45 random problems of the reference's
     scale, evaluations by the CPU stand-in for PoolStore: same optimal values as the oracle's own solve"""
