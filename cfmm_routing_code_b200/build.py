@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, os.environ.get("CFMM_LIB", "libcfmm_b200.so"))      # (CFMM_LIB: load / build an experiment variant)
-SOURCES = ["cfmm_kernels.cu", "cfmm_blocked.cu", "cfmm_persist.cu", "cfmm_solver.cu", "cfmm_allreduce.cu", "cfmm_small.cu"]
+SOURCES = ["cfmm_kernels.cu", "cfmm_blocked.cu", "cfmm_layout.cu", "cfmm_persist.cu", "cfmm_solver.cu", "cfmm_allreduce.cu", "cfmm_small.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v",
@@ -27,6 +27,8 @@ def _nvcc() -> str:
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
+    if os.environ.get("CFMM_LIB"):          # an experiment variant built by hand (its -D flags are not known here): use as is
+        return False
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, s) for s in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "cfmm_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)

@@ -374,6 +374,12 @@ class BlockedBucket:
         self.spec = spec
         P, rows_stride, tok_stride, row_cap = blocked_layout_info(lib)
         f64 = dict(dtype=torch.float64, device=device)
+        self.theta_bar = None
+        self.delta = self.lam = self.hcoef = self.hmask = None
+        self._device = device
+        self._sel = self._off = None
+        if spec.identity and int(hp.pool_ptr[-1]) == 2 * hp.m and self._build_native(hp, spec, device, lib, P, rows_stride, tok_stride):
+            return                              # the whole layout was built by three launches of csrc/cfmm_layout.cu
         if spec.identity:                       # raw arrays go up as they are; all reordering happens on the GPU
             lo, hi = spec.lo, spec.hi            # a rank's shard uploads only its own slice of the (pinned) host arrays
             R = torch.from_numpy(hp.reserves[2 * lo:2 * hi]).to(device, non_blocking=True).view(-1, 2)
@@ -393,10 +399,6 @@ class BlockedBucket:
         self.order = order                               # blocked position -> bucket-local pool index (device)
         self.residual = residual.cpu().numpy() if residual.numel() else np.zeros(0, np.int64)
         self.m = int(order.numel())
-        self.theta_bar = None
-        self.delta = self.lam = self.hcoef = self.hmask = None
-        self._device = device
-        self._sel = self._off = None
         if self.m == 0:
             self.tables = None
             return
@@ -414,11 +416,64 @@ class BlockedBucket:
                                            self.gamma_inv.data_ptr(), t["lid"].data_ptr(), t["pos"].data_ptr(),
                                            t["rows"].data_ptr(), t["tok"].data_ptr(), t["desc"].data_ptr())
 
+    def _build_native(self, hp, spec, device, lib, P, rows_stride, tok_stride) -> bool:
+        """cfmm_blocked_build (csrc/cfmm_layout.cu): upload the pools' own arrays (this rank's slice) and build the blocked
+        layout on the device in three launches.  False = not applicable (keys would not fit 32 bits, or some tile would
+        touch more tokens than a tile may): the caller takes the general torch builder."""
+        lo, hi = spec.lo, spec.hi
+        m = hi - lo
+        if m <= 0:
+            return False
+        nb = max(1, int(round((m / P) ** 0.5)))
+        if nb * nb * hp.n_tokens >= 2 ** 32 or m >= 2 ** 31:
+            return False
+        T = -(-m // P)
+        M = T * P
+        f64 = dict(dtype=torch.float64, device=device)
+        i32 = dict(dtype=torch.int32, device=device)
+        idx = torch.from_numpy(np.ascontiguousarray(hp.tok_idx[2 * lo:2 * hi], np.int32)).to(device, non_blocking=True)
+        R = torch.from_numpy(hp.reserves[2 * lo:2 * hi]).to(device, non_blocking=True)
+        gam = torch.from_numpy(hp.gamma[lo:hi]).to(device, non_blocking=True)
+        slabs = torch.empty((3, M), **f64)
+        words = torch.empty((2, M), **i32)
+        rows = torch.empty((T, rows_stride), **i32)
+        tok = torch.empty((T, tok_stride), **i32)
+        desc = torch.empty((T, 4), **i32)
+        order = torch.empty(m, **i32)
+        status = torch.empty(4, **i32)
+        nbytes = int(lib.cfmm_blocked_build_work_bytes(m))
+        if nbytes <= 0:
+            return False
+        work = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        cb = _lib.BlockedPairs(m, T, P, 0, slabs[0].data_ptr(), slabs[1].data_ptr(), slabs[2].data_ptr(), words[0].data_ptr(),
+                               words[1].data_ptr(), rows.data_ptr(), tok.data_ptr(), desc.data_ptr())
+        st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        rc = lib.cfmm_blocked_build(m, hp.n_tokens, idx.data_ptr(), R.data_ptr(), gam.data_ptr(), C.byref(cb), order.data_ptr(),
+                                    status.data_ptr(), work.data_ptr(), nbytes, st)
+        if rc == -3:                              # CFMM_E_SIZE: outside the native builder's key range
+            return False
+        _lib.check(rc, "cfmm_blocked_build")
+        st_h = status.cpu()                       # the one synchronisation of the build
+        if int(st_h[1]) != 0:
+            raise ValueError("invalid pool data (reserves > 0 and finite, fees in (0, 1], two distinct token ids in range)")
+        if int(st_h[0]) != 0:                     # a tile touches more tokens than it may: general builder + plain residual bucket
+            return False
+        self.order = order
+        self.residual = np.zeros(0, np.int64)
+        self.m = m
+        self.stride = M
+        self.r0, self.r1, self.gamma_inv = slabs[0], slabs[1], slabs[2]
+        self._keep = (idx, R, gam, work)          # the build is asynchronous: its inputs live as long as the bucket
+        self.tables = dict(n_tiles=T, M=M, lid=words[0], pos=words[1], rows=rows, tok=tok, desc=desc,
+                           rows_per_pool=int(st_h[2]) / m, tok_per_tile=None)
+        self.c_blocked = cb
+        return True
+
     # host-side index maps are only needed for read-back / dense assembly: built on first use
     @property
     def sel(self) -> np.ndarray:
         if self._sel is None:
-            self._sel = self.spec.sel[self.order.cpu().numpy()]
+            self._sel = self.spec.sel[self.order.cpu().numpy().astype(np.int64)]
         return self._sel
 
     @property

@@ -121,6 +121,22 @@ int cfmm_blocked_layout_info(int32_t* pools_per_tile, int32_t* rows_stride, int3
  * 896 / per-tile planned sizes measured on B200, profiles/r2a_tile_variants.txt.) */
 int cfmm_set_blocked_config(int32_t cfg);
 
+/*
+ * Native layout builder (csrc/cfmm_layout.cu): the reference's literals -- local_indices as idx [m][2] int32, reserves
+ * [m][2] f64, fees as gamma [m] f64 (arbitrage.py:6-28), contiguous on the device -- become the blocked layout in three
+ * launches (pool keys + validation, radix sort, one CTA per tile).  `out`: a cfmm_blocked_pairs with n_pools = m,
+ * n_tiles = ceil(m / P), pools_per_tile = P whose array members point at caller-allocated device buffers (strides from
+ * cfmm_blocked_layout_info; slabs / lid / pos of n_tiles * P entries); all of them are filled.  order [m] uint32 (out):
+ * the pool at every blocked position.  status [4] int32 (device, out): [0] tiles that touch more tokens than a tile may
+ * (then the layout is unusable: use a plain bucket), [1] != 0: invalid pools (reserves <= 0 or not finite, fees outside
+ * (0, 1], token ids out of range or equal), [2] rows in total.  CFMM_E_SIZE if the sort keys would not fit 32 bits
+ * (token_blocks^2 * n_tokens >= 2^32).  work: cfmm_blocked_build_work_bytes(m) bytes.  Asynchronous on `stream`.
+ */
+int64_t cfmm_blocked_build_work_bytes(int64_t n_pools);
+int cfmm_blocked_build(int64_t n_pools, int32_t n_tokens, const int32_t* idx, const double* reserves, const double* gamma,
+                       const cfmm_blocked_pairs* out, uint32_t* order, int32_t* status, void* work, int64_t work_bytes,
+                       void* stream);
+
 /* Same contract as cfmm_arb_eval for a blocked constant-product bucket: psi/arb ACCUMULATE (one red.add per row
  * of <= 32 entries, ~0.35 per pool, instead of 2 per pool).  Per-pool outputs (delta/lambda [2][n_tiles*P], hcoef
  * [n_tiles*P]) are in BLOCKED order.  If zero_next != NULL the launch also clears zero_next[0..n_zero): callers that

@@ -75,3 +75,42 @@ def random_utilities(rng, n, prices):
             basket[j] = float(np.exp(rng.normal(1, 1)) / prices[j])
     us.append(O.Utility.liquidate(n, tgt, basket))
     return us
+
+
+def check_blocked_tables(t, idx, order, n, P, rs, ts, cap):
+    """Invariants of a blocked layout (tables `t` as CPU tensors, idx (2, m) int64, order = pool at each blocked position):
+    emulate the kernels' scatter -- the pool phase writes the two flows of every pool to its slots of the tile's
+    row-ordered array, one thread sums each row -- and compare with a plain index_add; rows longest first, inside the
+    tile's 2 P slots; local ids map back to the pools' tokens."""
+    import torch
+    M, T = t["M"], t["n_tiles"]
+    desc = t["desc"].to(torch.int64)
+    assert M == T * P
+    nq = len(order)
+    q = torch.arange(nq)
+    tl = q // P
+    f = torch.randn(nq, 2, dtype=torch.float64)                     # flows of (pool, slot), blocked order
+    pos = t["pos"].to(torch.int64)[:nq] & 0xffffffff
+    g = torch.zeros(T, 2 * P, dtype=torch.float64)                  # the pool phase scatters into row order
+    g[tl, pos & 0xffff] = f[:, 0]
+    g[tl, pos >> 16] = f[:, 1]
+    padpos = t["pos"].to(torch.int64)[nq:] & 0xffffffff             # padding pools of the last tile: slots past the real flows
+    assert bool(((padpos & 0xffff) < 2 * P).all() and ((padpos >> 16) < 2 * P).all())
+    rows = t["rows"].to(torch.int64) & 0xffffffff
+    out = torch.zeros(n, dtype=torch.float64)
+    for tile in range(T):
+        ntok, nrow = desc[tile, 0].item(), desc[tile, 1].item()
+        assert 0 < ntok <= ts and 0 < nrow <= rs
+        w = rows[tile, :nrow]
+        st, ln, lt = w & 0xffff, (w >> 16) & 0x3f, w >> 22
+        assert bool((ln[:-1] >= ln[1:]).all()) and int(ln.max()) <= cap and int(ln.min()) >= 1     # longest rows first
+        assert int((st + ln).max()) <= 2 * P                        # rows stay inside the tile's 2 P flow slots
+        assert bool((lt < ntok).all())
+        for r in range(nrow):
+            out[t["tok"][tile, lt[r]]] += g[tile, st[r]:st[r] + ln[r]].sum()
+    a, b = idx[0][order], idx[1][order]
+    ref = torch.zeros(n, dtype=torch.float64)
+    ref.index_add_(0, a, f[q, 0]); ref.index_add_(0, b, f[q, 1])
+    assert float((out - ref).abs().max()) <= 1e-12 * float(ref.abs().max())
+    lid = t["lid"].to(torch.int64)[:nq] & 0xffffffff
+    assert bool((t["tok"][tl, lid & 0xffff] == a).all() and (t["tok"][tl, lid >> 16] == b).all())

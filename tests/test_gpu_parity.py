@@ -76,6 +76,31 @@ def test_blocked_hvp_and_diag_match_oracle_over_several_tiles_per_cta():
         np.testing.assert_allclose(st.hess_diag().cpu().numpy(), np.diag(Hs), atol=1e-11 * np.abs(Hs).max())
 
 
+def test_native_layout_builder_tables_satisfy_the_layout_invariants():
+    """cfmm_blocked_build (csrc/cfmm_layout.cu: keys + radix sort + one CTA per tile): the same invariants the CPU test
+    checks for the torch builder -- emulated scatter == index_add, rows longest first, ids map back to tokens -- plus
+    agreement of the slabs with the pools' own data, for ragged last tiles, tiny and many-token problems"""
+    from cfmm_routing_code_b200 import pools as PL
+    lib = _lib.load()
+    P, rs, ts, cap = PL.blocked_layout_info(lib)
+    for m, n in ((5000, 300), (700, 3), (40_000, 2000), (896, 8), (897, 3000), (200_000, 4096)):
+        hp, s = H.cp_host_pools(m, n, seed=m % 13)
+        st = cf.PoolStore(hp)
+        b = st.buckets[0]
+        assert b.blocked and b.tables["tok_per_tile"] is None and not len(b.residual)       # the native path built it
+        order = b.order.cpu().to(torch.int64)
+        assert sorted(order.tolist()) == list(range(m))                                     # a permutation of the pools
+        t = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in b.tables.items()}
+        idx = torch.as_tensor(hp.tok_idx.reshape(-1, 2).T.astype(np.int64).copy())
+        H.check_blocked_tables(t, idx, order, n, P, rs, ts, cap)
+        R = torch.as_tensor(hp.reserves.reshape(-1, 2))
+        assert torch.equal(b.r0[:m].cpu(), R[order, 0]) and torch.equal(b.r1[:m].cpu(), R[order, 1])
+        np.testing.assert_allclose(b.gamma_inv[:m].cpu().numpy(), 1.0 / hp.gamma[order.numpy()], rtol=1e-15)
+        assert bool((b.r0[m:] == 1).all() and (b.gamma_inv[m:] == 1).all())                 # padding pools: inert
+    with pytest.raises(ValueError):                                                          # validation lives in the key kernel
+        cf.PoolStore(cf.HostPools.from_pairs(2, [[0, 0]] * 4, [[1.0, 1.0]] * 4, [0.99] * 4))
+
+
 def test_blocked_layout_falls_back_when_tiles_touch_too_many_tokens():
     """every pool on its own pair of tokens: no tile can stay under the per-tile token cap -> plain bucket"""
     m = 4 * 896                         # whole tiles only (a ragged last tile of few pools would stay blocked)

@@ -246,35 +246,7 @@ def test_blocked_layout_builder_tables_reproduce_the_scatter():
         idx = torch.as_tensor(s["idx"].T.astype(np.int64).copy())
         order, res, t = PL.build_blocked_pairs(idx, n, P, rs, ts, cap)
         assert len(order) + len(res) == m and t is not None
-        M, T = t["M"], t["n_tiles"]
-        desc = t["desc"].to(torch.int64)
-        assert M == T * P
-        q = torch.arange(len(order))
-        tl = q // P
-        f = torch.randn(len(order), 2, dtype=torch.float64)            # flows of (pool, slot), blocked order
-        pos = t["pos"].to(torch.int64)[:len(order)] & 0xffffffff
-        g = torch.zeros(T, 2 * P, dtype=torch.float64)                  # the pool phase scatters into row order
-        g[tl, pos & 0xffff] = f[:, 0]
-        g[tl, pos >> 16] = f[:, 1]
-        padpos = t["pos"].to(torch.int64)[len(order):] & 0xffffffff     # padding pools of the last tile: slots past the real flows
-        assert bool(((padpos & 0xffff) < 2 * P).all() and ((padpos >> 16) < 2 * P).all())
-        rows = t["rows"].to(torch.int64) & 0xffffffff
-        out = torch.zeros(n, dtype=torch.float64)
-        for tile in range(T):
-            ntok, nrow = desc[tile, 0].item(), desc[tile, 1].item()
-            assert ntok <= ts and nrow <= rs
-            w = rows[tile, :nrow]
-            st, ln, lt = w & 0xffff, (w >> 16) & 0x3f, w >> 22
-            assert bool((ln[:-1] >= ln[1:]).all()) and int(ln.max()) <= cap     # longest rows first
-            assert int((st + ln).max()) <= 2 * P                        # rows stay inside the tile's 2 P flow slots
-            for r in range(nrow):
-                out[t["tok"][tile, lt[r]]] += g[tile, st[r]:st[r] + ln[r]].sum()
-        a, b = idx[0][order], idx[1][order]
-        ref = torch.zeros(n, dtype=torch.float64)
-        ref.index_add_(0, a, f[q, 0]); ref.index_add_(0, b, f[q, 1])
-        assert float((out - ref).abs().max()) <= 1e-12 * float(ref.abs().max())
-        lid = t["lid"].to(torch.int64)[:len(order)]
-        assert bool((t["tok"][tl, lid & 0xffff] == a).all() and (t["tok"][tl, lid >> 16] == b).all())
+        H.check_blocked_tables(t, idx, order, n, P, rs, ts, cap)
 
 
 # ---------------------------------------------------------------------------------------------------------
