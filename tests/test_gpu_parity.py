@@ -83,7 +83,7 @@ def test_native_layout_builder_tables_satisfy_the_layout_invariants():
     from cfmm_routing_code_b200 import pools as PL
     lib = _lib.load()
     P, rs, ts, cap = PL.blocked_layout_info(lib)
-    for m, n in ((5000, 300), (700, 3), (40_000, 2000), (896, 8), (897, 3000), (200_000, 4096)):
+    for m, n in ((5000, 300), (700, 3), (40_000, 2000), (896, 8), (897, 300), (200_000, 4096)):
         hp, s = H.cp_host_pools(m, n, seed=m % 13)
         st = cf.PoolStore(hp)
         b = st.buckets[0]
@@ -99,6 +99,12 @@ def test_native_layout_builder_tables_satisfy_the_layout_invariants():
         assert bool((b.r0[m:] == 1).all() and (b.gamma_inv[m:] == 1).all())                 # padding pools: inert
     with pytest.raises(ValueError):                                                          # validation lives in the key kernel
         cf.PoolStore(cf.HostPools.from_pairs(2, [[0, 0]] * 4, [[1.0, 1.0]] * 4, [0.99] * 4))
+    # a tile that would touch more tokens than a tile may (897 pools over 3000 tokens): the native builder reports it and
+    # the general builder takes over (blocked part + plain residual bucket); results are checked against the oracle in
+    # test_blocked_product_eval_matches_oracle[897-3000]
+    hp, s = H.cp_host_pools(897, 3000, seed=1)
+    st = cf.PoolStore(hp)
+    assert sum(b.m for b in st.buckets) == 897 and any(not getattr(b, "blocked", False) for b in st.buckets)
 
 
 def test_blocked_layout_falls_back_when_tiles_touch_too_many_tokens():
