@@ -184,7 +184,7 @@ k_solve_dist(const __grid_constant__ DistArgs D) {
         ds.phase = PH_KKT; ds.set = 0; ds.cur = 0; ds.iters = 0; ds.evals = 0; ds.hvps = 0; ds.status = 1; ds.cg_k = 0; ds.ls = 0;
         ds.yb = 0; ds.first_step = 1; ds.dir_ok = 0; ds.aborted = 0; ds.parity = 0; ds.flat = 0;
         ds.err = INFINITY; ds.g0 = 0.0; ds.rz = 0.0; ds.r0n = 0.0; ds.eta = 0.1; ds.alpha = 1.0; ds.lin1 = 0.0; ds.beta = 0.0;
-        ds.al = 0.0; ds.imx = 0.0; ds.thr = 1e-2;
+        ds.al = 0.0; ds.imx = 0.0; ds.thr = 1e-5;
         ds.kc.err = INFINITY; ds.kc.g = 0.0; ds.kc.primal = 0.0; ds.kc.infeas = 0.0; ds.kc.lin = 0.0;
         ds.seq_acc = S.seq_acc; ds.seq_vec = S.seq_vec; ds.bar = 0;
         for (int k = 0; k < 16; ++k) ds.prof[k] = 0;
@@ -408,7 +408,7 @@ k_solve_dist(const __grid_constant__ DistArgs D) {
                 }
             } else {                                 // PH_STEP -> evaluate the trial point
                 ds.set = cur ^ 1;
-                ds.thr = fmin(1e-2, fmax(isfinite(ds.err) ? ds.err : 1e-2, 1e-14));
+                ds.thr = fmin(1e-2, fmax(1e-3 * (isfinite(ds.err) ? ds.err : 1e-2), 1e-14));     // active-set width (see solver.py)
                 next = PH_KKT;
             }
             if (next == PH_DONE && ds.status == 1 && ds.err <= S.tol) ds.status = 0;

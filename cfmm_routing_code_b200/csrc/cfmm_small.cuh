@@ -253,7 +253,7 @@ CFMM_HD inline double dual_value(const Problem& Q, const Vec& nu, double arb) {
 CFMM_HD inline double kkt(const Problem& Q, const Vec& nu, const Vec& psi, const Vec& lb, double g, double err_prev,
                           const Vec& grad, const Vec& pg, uint64_t* free_mask) {
     const double ep = isfinite(err_prev) ? err_prev : 1e-2;
-    const double thr = fmin(1e-2, fmax(ep, 1e-14));
+    const double thr = fmin(1e-2, fmax(1e-3 * ep, 1e-14));       // active-set width: 1e-3 x the KKT residual (see solver.py)
     double num = 0.0, wsum = 0.0, gmax = 0.0, scl = 0.0;
     uint64_t fm = 0;
     for (int j = 0; j < Q.n; ++j) {

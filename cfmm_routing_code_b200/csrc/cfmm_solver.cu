@@ -283,7 +283,7 @@ int cfmm_blocked_solve_peer(const cfmm_blocked_pairs* b, int32_t n_tokens, const
     constexpr int kCgBatch = 3;    // PCG iterations launched per host synchronisation
     for (; iters < prm->max_iter;) {
         ++iters;
-        const double thr = fmin(1e-2, fmax(isfinite(err) ? err : 1e-2, 1e-14));
+        const double thr = fmin(1e-2, fmax(1e-3 * (isfinite(err) ? err : 1e-2), 1e-14));     // active-set width (see solver.py)
         if (!have_kkt) {
             k_kkt<<<1, kVT, 0, st>>>(V, cur_nu, cur_acc, thr);
             if (!fetch()) return CFMM_E_CUDA;

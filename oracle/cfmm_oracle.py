@@ -438,7 +438,7 @@ def solve(pools: Pools, util: Utility, nu0=None, tol=1e-9, eps=0.1, eps_min=1e-4
         by token (liquidation.py:77-80, arbitrage.py:77), so a cheap token must not hide a large residual (nor may
         the unconstrained output of an objective-only token set the scale)."""
         grad = util.a + ev_["psi"]
-        thr = min(1e-2, max(err_prev if np.isfinite(err_prev) else 1e-2, 1e-14))
+        thr = min(1e-2, max(1e-3 * (err_prev if np.isfinite(err_prev) else 1e-2), 1e-14))     # active-set width (see solver.py)
         near = (nu_ <= lb * (1 + thr)) & ~util.eq
         free = ~(fixed | (near & (grad > 0)))
         pg = np.where(free, nu_ * grad, 0.0)

@@ -202,7 +202,7 @@ typedef struct {
 static double kkt_c(const spec_t* S, const double* nu, const double* psi, double g, double err_prev, double* grad,
                     double* fr, double* pg) {
     const double ep = isfinite(err_prev) ? err_prev : 1e-2;
-    const double thr = fmin(1e-2, fmax(ep, 1e-14));
+    const double thr = fmin(1e-2, fmax(1e-3 * ep, 1e-14));       // active-set width: 1e-3 x the KKT residual (see solver.py)
     double num = 0, wsum = 0, gmax = 0, scl = S->a_inf;
     for (int32_t j = 0; j < S->n; ++j) {
         const double gr = S->a[j] + psi[j];

@@ -352,6 +352,31 @@ def test_cfg4_small_liquidation_matches_oracle():
     np.testing.assert_allclose(r.psi[1:], -basket[1:], atol=1e-6 * basket.max())
 
 
+def test_full_size_mixed_configs_reach_a_certified_optimum():
+    """BASELINE.json configs[2] and [3] at full size (100k mixed pools, 1000 tokens; the liquidation.py objective over
+    them): oracle-free certificates -- weak duality, relative gap, value-weighted infeasibility AND every token's own
+    residual (liquidation.py:77-80 constrains psi token by token) -- plus shard additivity of the mixed evaluation"""
+    s = I.synth_mixed(100_000, 1000, seed=1)
+    hp = cf.HostPools(1000, s["pool_ptr"], s["tok_idx"], s["reserves"], s["weights"], s["gamma"], s["kind"])
+    st = cf.PoolStore(hp)
+    r = cf.solve_pools(hp, cf.Arbitrage(s["prices"]), tol=1e-6, store=st, want_trades=False)
+    assert r.status == "optimal" and abs(r.gap) <= 1e-6 and r.primal_infeas <= 1e-6
+    assert r.dual_value >= r.value - 1e-6 * abs(r.dual_value)                       # weak duality
+    assert r.psi.min() >= -1e-6 * np.abs(r.psi).max()                               # arbitrage.py:77, token by token
+    assert np.all(r.nu >= s["prices"] * (1 - 1e-12))                                # dual box nu >= c
+    nu = torch.as_tensor(H.random_prices(s["prices"], 5, 0.01), **F64)
+    full = st.evaluate(nu, 1e-3).clone()
+    halves = sum(cf.PoolStore(hp, rank=k, world=2).evaluate(nu, 1e-3).clone() for k in range(2))
+    assert float((full - halves)[:-1].abs().max()) <= 1e-9 * float(full[:-1].abs().max())
+    s = I.synth_mixed(100_000, 1000, seed=2)
+    hp = cf.HostPools(1000, s["pool_ptr"], s["tok_idx"], s["reserves"], s["weights"], s["gamma"], s["kind"])
+    basket = I.synth_basket(1000, s["prices"], seed=2)
+    r = cf.solve_pools(hp, cf.Liquidate(0, basket), nu0=s["prices"] / s["prices"][0], tol=1e-6, want_trades=False)
+    assert r.status == "optimal" and abs(r.gap) <= 1e-6 and r.primal_infeas <= 1e-6
+    np.testing.assert_allclose(r.psi[1:], -basket[1:], atol=1e-6 * basket.max())    # psi_j + a_j == 0 for every basket token
+    assert r.value > 0 and abs(r.value - r.psi[0]) <= 1e-12 * abs(r.value)
+
+
 def test_full_size_properties_1m_pools():
     """BASELINE.json configs[4] size (1M pools, 4096 tokens): oracle-free invariants."""
     hp, s = H.cp_host_pools(1_000_000, 4096, seed=3)
