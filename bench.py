@@ -247,10 +247,12 @@ def timed_steps(step, steps, warmup, barrier, clock_index, n_inst, preroll_ms=40
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(clock_index) as clocks:
         barrier()
-        t0 = time.perf_counter()
-        while (time.perf_counter() - t0) * 1e3 < preroll_ms:       # untimed pre-roll: clocks at their loaded value
+        # untimed pre-roll (clocks at their loaded value before the timed region).  A FIXED number of replays, the same on
+        # every rank: the graphs contain the collective, so a time-based loop would let ranks replay different counts and
+        # dead-lock in the all-reduce (it did, at N=4, this round).
+        for _ in range(max(1, int(preroll_ms * 1e-3 / (12e-6 * CHUNK)))):
             graph.replay()
-            torch.cuda.synchronize()
+        torch.cuda.synchronize()
         barrier()
         torch.cuda.profiler.start()
         e0.record()
