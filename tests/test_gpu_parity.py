@@ -327,8 +327,11 @@ def test_persistent_and_hostloop_solvers_take_the_same_path():
             rb = cf.solve_pools(hp, util, nu0=nu0, tol=1e-8, store=st, native="hostloop", want_trades=False)
             assert ra.status == rb.status == "optimal", (m, ra.status, rb.status)
             assert abs(ra.value - rb.value) <= 1e-9 * max(abs(rb.value), 1e-300) + 1e-12 * abs(rb.dual_value)
-            # same method; summation orders differ (atomics, fused PCG recurrences), so the paths may part by an iteration or two
-            assert abs(ra.iters - rb.iters) <= 4 and abs(ra.evals - rb.evals) <= 6, (ra.iters, rb.iters, ra.evals, rb.evals)
+            # same method; summation orders differ (atomics, fused PCG recurrences), so the paths may part by an iteration or
+            # two.  The host loop re-evaluates the current point after every rejected trial and, once g no longer resolves the
+            # steps, can spend dozens of evaluations backtracking where the persistent kernel (KKT data of both points kept)
+            # needs none: only an upper bound on the persistent solver's evaluations is asserted
+            assert abs(ra.iters - rb.iters) <= 4 and ra.evals <= rb.evals + 6, (ra.iters, rb.iters, ra.evals, rb.evals)
             np.testing.assert_allclose(ra.nu, rb.nu, rtol=1e-6)
 
 
