@@ -520,6 +520,10 @@ def main():
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N>1: cfmm_allreduce_ll over NVLink peer memory (default) or NCCL all_reduce")
     args = ap.parse_args()
+    # safety net: a wedged collective (a rank that died, a peer that never pushes) must end the run, not hold the box
+    watchdog = threading.Timer(float(os.environ.get("CFMM_BENCH_WATCHDOG_S", "900")), lambda: os._exit(3))
+    watchdog.daemon = True
+    watchdog.start()
     if args.impl == "reference":
         if args.steps > 20:
             args.steps = 10         # each reference step is seconds of CPU work
