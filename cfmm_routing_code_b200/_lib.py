@@ -122,6 +122,8 @@ def load(build_if_missing: bool = True):
     lib.cfmm_blocked_hvp.restype = C.c_int
     lib.cfmm_blocked_diag.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp]
     lib.cfmm_blocked_diag.restype = C.c_int
+    lib.cfmm_blocked_dense.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp]
+    lib.cfmm_blocked_dense.restype = C.c_int
     lib.cfmm_blocked_solve_work_bytes.argtypes = [C.POINTER(BlockedPairs), i32]
     lib.cfmm_blocked_solve_work_bytes.restype = i64
     lib.cfmm_blocked_solve.argtypes = [C.POINTER(BlockedPairs), i32, vp, vp, vp, vp, vp, vp, vp,

@@ -227,6 +227,24 @@ k_blocked_regs(const BlockedArgs A) {
     }
 }
 
+// dense assembly (small-n direct solves of mixed problems): H += sum_i A_i h_i [[1,-1],[-1,1]] A_i' straight from the blocked
+// layout -- the pool's global tokens are its tile's token list at its 16-bit local ids
+__global__ void __launch_bounds__(256)
+k_blocked_dense(long long n_pools, int n, const uint32_t* __restrict__ lid, const int32_t* __restrict__ tok,
+                const double* __restrict__ hcoef, double* H) {
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n_pools; q += (long long)gridDim.x * blockDim.x) {
+        const double h = hcoef[q];
+        if (h != 0.0) {
+            const long long tile = q / kTileP;
+            const uint32_t li = lid[q];
+            const long long a = tok[tile * BlockedCfg<kTileP>::kTokMax + (li & 0xffffu)];
+            const long long b = tok[tile * BlockedCfg<kTileP>::kTokMax + (li >> 16)];
+            atomicAdd(H + a * n + a, h); atomicAdd(H + b * n + b, h);
+            atomicAdd(H + a * n + b, -h); atomicAdd(H + b * n + a, -h);
+        }
+    }
+}
+
 // ---- launch: evaluation through the TMA-staged pass; Hessian products / diagonal (1 slab, less data per tile) through
 // the register-fed single-barrier variant -- each is the faster one for its mode (profiles/r1f_*, r2a_*).  Both run
 // kCtasPerSm CTAs of kTileT threads per SM.
@@ -349,6 +367,20 @@ int cfmm_blocked_hvp(const cfmm_blocked_pairs* b, int32_t n_tokens, const double
     A.slab[0] = hcoef; A.vec = vt; A.out = y;
     A.zero_next = zero_next; A.n_zero = zero_next ? n_tokens : 0;
     return launch_regs<1>(A, static_cast<cudaStream_t>(stream));
+}
+
+int cfmm_blocked_dense(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* hcoef, double* H, void* stream) {
+    BlockedArgs A;
+    int rc = fill_blocked_args(b, A);
+    if (rc) return rc;
+    if (n_tokens <= 0) return CFMM_E_SIZE;
+    if (!hcoef || !H) return CFMM_E_NULL;
+    if (b->n_tiles == 0) return CFMM_OK;
+    // (pools of the padded tail carry hcoef = 0: the evaluation writes 0 for them)
+    const long long total = b->n_tiles * (long long)kTileP;
+    const long long need = (total + 255) / 256, cap = 8LL * num_sms();
+    k_blocked_dense<<<(int)(need < cap ? need : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(total, n_tokens, b->lid, b->tok, hcoef, H);
+    return check_launch();
 }
 
 int cfmm_blocked_diag(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* hcoef, double* diag, void* stream) {

@@ -707,23 +707,12 @@ class PoolStore:
         H = torch.zeros((self.n_tokens, self.n_tokens), dtype=torch.float64, device=self.device)
         for b in self.buckets:
             if getattr(b, "blocked", False):
-                # dense assembly is a small-n path: scatter the blocked hcoef with torch index_put (plumbing)
-                i0 = torch.as_tensor(self._tok_of(b, 0), device=self.device)
-                i1 = torch.as_tensor(self._tok_of(b, 1), device=self.device)
-                h = b.hcoef[:b.m]
-                H.index_put_((i0, i0), h, accumulate=True); H.index_put_((i1, i1), h, accumulate=True)
-                H.index_put_((i0, i1), -h, accumulate=True); H.index_put_((i1, i0), -h, accumulate=True)
+                _lib.check(self.lib.cfmm_blocked_dense(C.byref(b.c_blocked), self.n_tokens, b.hcoef.data_ptr(), H.data_ptr(), st),
+                           "cfmm_blocked_dense")
                 continue
             _lib.check(self.lib.cfmm_hess_dense(C.byref(b.c_bucket), self.n_tokens, b.hcoef.data_ptr(),
                                                 b.hmask.data_ptr(), H.data_ptr(), st), "cfmm_hess_dense")
         return H
-
-    def _tok_of(self, b, slot):
-        key = (id(b), slot)
-        cache = self.__dict__.setdefault("_tok_cache", {})
-        if key not in cache:
-            cache[key] = self._tok_idx_host[b.off[slot]].astype(np.int64)
-        return cache[key]
 
     def update_multipliers(self) -> torch.Tensor:
         """theta_bar <- fills of the last trades=True evaluation; returns max relative change (device)."""

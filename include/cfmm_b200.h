@@ -147,6 +147,8 @@ int cfmm_blocked_eval(const cfmm_blocked_pairs* b, int32_t n_tokens, const doubl
 int cfmm_blocked_hvp(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* hcoef, const double* vt, double* y,
                      double* zero_next, void* stream);
 int cfmm_blocked_diag(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* hcoef, double* diag, void* stream);
+/* H[j*n_tokens + k] += (Hs)_jk of the blocked bucket, dense row-major (the direct Newton solves of small-n mixed problems) */
+int cfmm_blocked_dense(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* hcoef, double* H, void* stream);
 
 /*
  * Native outer loop (csrc/cfmm_solver.cu) for problems whose pools are ONE blocked constant-product bucket: the
