@@ -136,6 +136,8 @@ def load(build_if_missing: bool = True):
     lib.cfmm_persist_solve_work_bytes.restype = i64
     lib.cfmm_persist_solve.argtypes = lib.cfmm_blocked_solve_peer.argtypes
     lib.cfmm_persist_solve.restype = C.c_int
+    lib.cfmm_set_persist_cooperative.argtypes = [i32]
+    lib.cfmm_set_persist_cooperative.restype = C.c_int
     lib.cfmm_persist_last_profile.argtypes = [vp]
     lib.cfmm_persist_last_profile.restype = C.c_int
     lib.cfmm_batch_solve_work_bytes.argtypes = [C.POINTER(CsrPools), i32, i64]

@@ -36,24 +36,34 @@ k_allreduce_ll(const double* __restrict__ local, LLCell* const* __restrict__ rec
 #pragma unroll
     for (int r = 0; r < kMaxWorld; ++r)
         if (r < world && r != rank) st_ll(recv[r] + slot_off + (long long)rank * src_stride + j, mine, seq);
+    // Poll all peers' cells TOGETHER: the loads of a round are independent (one L2 round trip for the lot instead of one
+    // per peer); cells that carry this step's sequence number are taken, the rest are asked again.
     double v[kMaxWorld];
+    unsigned pending = 0u;
 #pragma unroll
     for (int r = 0; r < kMaxWorld; ++r) {
-        if (r < world) {
-            if (r == rank) { v[r] = mine; continue; }
-            const LLCell* c = recv[rank] + slot_off + (long long)r * src_stride + j;
-            unsigned long long f;
-            const long long t0 = clock64();
-            unsigned spins = 0;
-            do {
-                ld_ll(c, v[r], f);
-                // a peer that never shows up (crashed rank, mismatched call sequence) must not hang the GPU: ~3 s of SM
-                // clocks (looked at every 256 polls), then the element becomes NaN and the caller's certificate fails loudly
-                if (f != seq && (++spins & 255u) == 0u && (unsigned long long)(clock64() - t0) > 6000000000ull) {
-                    v[r] = __longlong_as_double(0x7ff8000000000000ll);
-                    break;
-                }
-            } while (f != seq);
+        v[r] = mine;
+        if (r < world && r != rank) pending |= 1u << r;
+    }
+    const LLCell* base = recv[rank] + slot_off + j;
+    const long long t0 = clock64();
+    unsigned spins = 0;
+    while (pending) {
+        double t[kMaxWorld];
+        unsigned long long f[kMaxWorld];
+#pragma unroll
+        for (int r = 0; r < kMaxWorld; ++r)
+            if (pending >> r & 1u) ld_ll(base + (long long)r * src_stride, t[r], f[r]);
+#pragma unroll
+        for (int r = 0; r < kMaxWorld; ++r)
+            if ((pending >> r & 1u) && f[r] == seq) { v[r] = t[r]; pending &= ~(1u << r); }
+        // a peer that never shows up (crashed rank, mismatched call sequence) must not hang the GPU: ~3 s of SM clocks
+        // (looked at every 64 rounds), then the element becomes NaN and the caller's certificate fails loudly
+        if (pending && (++spins & 63u) == 0u && (unsigned long long)(clock64() - t0) > 6000000000ull) {
+#pragma unroll
+            for (int r = 0; r < kMaxWorld; ++r)
+                if (pending >> r & 1u) v[r] = __longlong_as_double(0x7ff8000000000000ll);
+            break;
         }
     }
     double s = 0.0;

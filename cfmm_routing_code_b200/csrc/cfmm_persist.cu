@@ -149,25 +149,44 @@ __device__ __forceinline__ void ll_push(double mine, LLCell* const* recv, long l
     for (int r = 0; r < world; ++r)
         if (r != rank) st_ll(recv[r] + slot + (long long)rank * stride + j, mine, seq);
 }
-__device__ __forceinline__ double ll_poll_sum(double mine, LLCell* const* recv, long long slot, long long stride, int j,
-                                              int rank, int world, unsigned long long seq, unsigned* ctl) {
-    double s = 0.0;
+// Sum over the ranks of element j, in rank order (same bits on every rank).  The peers' cells are polled FOUR AT A TIME:
+// the loads of a round are independent, so a round costs one L2 round trip instead of one per peer (the one-after-the-
+// other version cost ~19 us per phase at 8 ranks); cells that carry this step's sequence number are taken, the others
+// are asked again.  Not inlined: seven call sites, and the four loads in flight must not add to the kernel's registers.
+__device__ __noinline__ double ll_poll_sum(double mine, LLCell* const* recv, long long slot, long long stride, int j,
+                                           int rank, int world, unsigned long long seq, unsigned* ctl) {
+    const LLCell* base = recv[rank] + slot + j;
     const long long t0 = clock64();
-    for (int r = 0; r < world; ++r) {
-        double v = mine;
-        if (r != rank) {
-            const LLCell* c = recv[rank] + slot + (long long)r * stride + j;
-            unsigned long long f;
-            do {
-                ld_ll(c, v, f);
-                if (f != seq && (unsigned long long)(clock64() - t0) > kSpinLimit) { ctl[32] = 1u; v = 0.0; break; }
-            } while (f != seq);
+    double s = 0.0;
+    for (int r0 = 0; r0 < world; r0 += 4) {
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        unsigned pending = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (r0 + k < world && r0 + k != rank) pending |= 1u << k;
+        unsigned spins = 0u;
+        while (pending) {
+            double t[4];
+            unsigned long long f[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (pending >> k & 1u) ld_ll(base + (long long)(r0 + k) * stride, t[k], f[k]);
+            if ((pending & 1u) && f[0] == seq) { v0 = t[0]; pending &= ~1u; }
+            if ((pending & 2u) && f[1] == seq) { v1 = t[1]; pending &= ~2u; }
+            if ((pending & 4u) && f[2] == seq) { v2 = t[2]; pending &= ~4u; }
+            if ((pending & 8u) && f[3] == seq) { v3 = t[3]; pending &= ~8u; }
+            if (pending && (++spins & 63u) == 0u && (unsigned long long)(clock64() - t0) > kSpinLimit) { ctl[32] = 1u; break; }
         }
-        s += v;
+        if (r0 + 0 < world) s += (r0 + 0 == rank) ? mine : v0;
+        if (r0 + 1 < world) s += (r0 + 1 == rank) ? mine : v1;
+        if (r0 + 2 < world) s += (r0 + 2 == rank) ? mine : v2;
+        if (r0 + 3 < world) s += (r0 + 3 == rank) ? mine : v3;
     }
     return s;
 }
 
+// MULTI = false is the single-GPU instantiation: no exchange code, no calls (the registers of the passes stay as they were)
+template <bool MULTI>
 __global__ void __launch_bounds__(PT, kCtasPerSm)
 k_solve_dist(const __grid_constant__ DistArgs D) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -219,7 +238,7 @@ k_solve_dist(const __grid_constant__ DistArgs D) {
         // ---- slice phase
         const int par = ds.parity;
         double* P0 = D.partial + (size_t)par * kQ * kSliceMax;
-        const bool multi = S.world > 1;
+        constexpr bool multi = MULTI;
         unsigned long long seq = 0;
         if (phase == PH_KKT) seq = ds.seq_acc + 1; else if (phase == PH_DIAG || phase == PH_HVP) seq = ds.seq_vec + 1;
         const long long slot_acc = (long long)(seq % 3) * S.world * (n + 1), slot_vec = (long long)(seq % 3) * S.world * (n + 2);
@@ -445,6 +464,7 @@ k_solve_dist(const __grid_constant__ DistArgs D) {
 
 inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 thread_local long long g_last_prof[16] = {0};
+int g_persist_cooperative = 1;
 
 }  // namespace
 
@@ -506,11 +526,16 @@ int cfmm_persist_solve(const cfmm_blocked_pairs* b, int32_t n_tokens, const doub
     D.nsl = (n + 15) / 16 < kSliceMax ? ((n + 15) / 16 > 0 ? (n + 15) / 16 : 1) : kSliceMax;
     D.P = S;
     const size_t sm = pass_smem_bytes<kTileP, kTileStages>(3);
-    static int occ = -1;
+    const bool multi = S.world > 1;
+    auto kern = multi ? k_solve_dist<true> : k_solve_dist<false>;
+    static int occs[2] = {-1, -1};
+    int& occ = occs[multi ? 1 : 0];
     if (occ < 0) {
-        cudaError_t e = cudaFuncSetAttribute(k_solve_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_solve_dist, PT, sm);
-        if (e != cudaSuccess || occ < 1) { occ = -1; g_last_err = e; return CFMM_E_CUDA; }
+        int o = -1;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, PT, sm);
+        if (e != cudaSuccess || o < 1) { g_last_err = e; return CFMM_E_CUDA; }
+        occ = o;
     }
     const long long cap = (long long)occ * num_sms();
     const int grid = (int)(S.B.n_tiles < cap ? S.B.n_tiles : cap);
@@ -519,9 +544,9 @@ int cfmm_persist_solve(const cfmm_blocked_pairs* b, int32_t n_tokens, const doub
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PT); cfg.dynamicSmemBytes = sm; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeCooperative;       // all CTAs co-resident (they wait for each other) or the launch fails
-    at[0].val.cooperative = 1;
+    at[0].val.cooperative = g_persist_cooperative;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, k_solve_dist, D);
+    cudaLaunchKernelEx(&cfg, kern, D);
     rc = check_launch();
     if (rc) return rc;
     static thread_local DevResult* hres = nullptr;          // pinned mirror of the result struct
@@ -534,6 +559,15 @@ int cfmm_persist_solve(const cfmm_blocked_pairs* b, int32_t n_tokens, const doub
     if (peer) { peer->seq_acc = hres->seq_acc; peer->seq_vec = hres->seq_vec; }
     for (int k = 0; k < 16; ++k) g_last_prof[k] = hres->prof[k];
     return hres->status == 3 ? CFMM_E_STATE : CFMM_OK;
+}
+
+/* 1 (default): cooperative launch -- the driver guarantees that all CTAs of a solve are co-resident or fails the launch.
+ * 0: plain launch (the grid is still sized to fit the device): for tests that run several "ranks" as concurrent solves on
+ * ONE GPU (tests/test_loopback_ranks.py), where each small grid is resident anyway. */
+int cfmm_set_persist_cooperative(int32_t on) {
+    if (on != 0 && on != 1) return CFMM_E_KIND;
+    g_persist_cooperative = on;
+    return CFMM_OK;
 }
 
 /* CTA 0's clock64 totals of the last cfmm_persist_solve of this thread (SM cycles): [0..2] its own evaluation / Hessian-

@@ -207,6 +207,7 @@ int cfmm_blocked_solve_peer(const cfmm_blocked_pairs* b, int32_t n_tokens, const
  * and the kernel gave up.  work: cfmm_persist_solve_work_bytes().
  */
 int64_t cfmm_persist_solve_work_bytes(const cfmm_blocked_pairs* b, int32_t n_tokens);
+int cfmm_set_persist_cooperative(int32_t on);   /* 1 (default) cooperative launch; 0 plain launch (single-GPU loopback tests) */
 int cfmm_persist_last_profile(int64_t* out8);   /* development aid: CTA 0's cycle totals of the last persistent solve */
 int cfmm_persist_solve(const cfmm_blocked_pairs* b, int32_t n_tokens, const double* c, const double* a,
                        const uint8_t* eq, const uint8_t* pinned, double* nu, double* psi_out, void* work,
