@@ -64,6 +64,23 @@ class Swap:
         return DualSpec(c, a, np.zeros(n, bool), np.zeros(n, bool))
 
 
+class LinearUtility:
+    """maximise c @ psi  s.t.  psi_j + a_j >= 0 | psi_j + a_j == 0 (eq) | psi_j unconstrained (pinned): the linear + box form
+    the three utilities above reduce to, for any mix of them (what cvxpy_compat recognises in a model's objective and
+    token constraints)"""
+
+    def __init__(self, c, a, eq, pinned):
+        self.c, self.a = np.asarray(c, float), np.asarray(a, float)
+        self.eq, self.pinned = np.asarray(eq, bool), np.asarray(pinned, bool)
+        if np.any(self.c < 0) or np.any(self.pinned & (self.c <= 0)) or np.any(self.eq & self.pinned):
+            raise ValueError("LinearUtility: c >= 0, unconstrained tokens need c > 0, eq and pinned exclude each other")
+
+    def spec(self, n):
+        if not (len(self.c) == len(self.a) == len(self.eq) == len(self.pinned) == n):
+            raise ValueError("LinearUtility needs one entry per token")
+        return DualSpec(self.c, self.a, self.eq, self.pinned)
+
+
 # ----------------------------------------------------------------------------------------------
 @dataclasses.dataclass
 class Result:
