@@ -345,7 +345,7 @@ def recognise(objective: Maximize, constraints) -> RoutingModel:
     token_rows = []                # (Expression, op)
     sum_levels = []                # scalar affine constraints that look like a trading-function level
 
-    def pool_of(D, L, R, gamma):
+    def pool_of(pos, D, L, R, gamma):
         key = (id(D), id(L))
         if key not in pools:
             for k2 in pools:
@@ -353,7 +353,7 @@ def recognise(objective: Maximize, constraints) -> RoutingModel:
                     raise NotRoutingProblem("a trade variable is used by two different pools")
             if not (D.nonneg and L.nonneg):
                 raise NotRoutingProblem("tendered / received baskets must be Variable(..., nonneg=True)   (arbitrage.py:51-52)")
-            pools[key] = dict(D=D, L=L, R=R, gamma=gamma, kind=None, w=None, nonneg=False)
+            pools[key] = dict(D=D, L=L, R=R, gamma=gamma, kind=None, w=None, nonneg=False, pos=pos)
             order.append(key)
         p = pools[key]
         if np.any(p["R"] != R) or p["gamma"] != gamma:
@@ -361,12 +361,12 @@ def recognise(objective: Maximize, constraints) -> RoutingModel:
         return p
 
     affine = []
-    for con in constraints:                          # trading functions first: they define which variables are pools
+    for pos, con in enumerate(constraints):          # trading functions first: they define which variables are pools
         if isinstance(con, PoolConstraint):
             nr = _reserves_after_trade(con.x)
             if nr is None:
                 raise NotRoutingProblem("geo_mean(x) >= level: x is not of the form R + gamma * Delta - Lambda   (arbitrage.py:60)")
-            p = pool_of(*nr)
+            p = pool_of(pos, *nr)
             here = float(np.prod(nr[2] ** con.w))
             if abs(con.level - here) > _RTOL * abs(here):
                 raise NotRoutingProblem(f"geo_mean level {con.level!r} differs from the trading function at the current reserves "
@@ -376,18 +376,18 @@ def recognise(objective: Maximize, constraints) -> RoutingModel:
             equal = bool(np.all(con.w == con.w[0]))
             p["kind"], p["w"] = ("product", None) if (len(con.w) == 2 and equal) else ("geomean", con.w.copy())
         elif isinstance(con, Constraint):
-            affine.append(con)
+            affine.append((pos, con))
         elif isinstance(con, (bool, np.bool_)):
             if not con:
                 raise NotRoutingProblem("a constraint between constants is False")
         else:
             raise NotRoutingProblem(f"unsupported constraint object {type(con).__name__}")
-    for con in affine:
+    for pos, con in affine:
         nr = _reserves_after_trade(con.expr) if con.op == ">=" else None
         if nr is not None and (id(nr[1]), id(nr[0])) in pools:
             nr = None                                # psi + a >= 0 of a one-pool problem: the known pool's net flow, not reserves
         if nr is not None:                           # new_reserves >= 0   (arbitrage.py:74)
-            pool_of(*nr)["nonneg"] = True
+            pool_of(pos, *nr)["nonneg"] = True
         elif con.op == ">=" and con.expr.scalar and _looks_like_sum_level(con.expr):
             sum_levels.append(con.expr)
         else:
@@ -408,6 +408,7 @@ def recognise(objective: Maximize, constraints) -> RoutingModel:
         if not p["nonneg"]:
             raise NotRoutingProblem("constant-sum pool without new_reserves >= 0")
         p["kind"] = "sum"
+    order.sort(key=lambda k: pools[k]["pos"])        # pools in the order the model states them
     for key in order:
         if pools[key]["kind"] is None:
             raise NotRoutingProblem("a pool has reserves (new_reserves >= 0) but no trading-function constraint")

@@ -231,6 +231,58 @@ def test_minimize_and_equal_weight_geomean_and_infeasible(with_oracle_backend):
     np.testing.assert_allclose(out[0][1], out[1][1], atol=1e-7)
 
 
+def wire_general(d, util):
+    """any list-form problem (geomean / product / sum pools) and any linear + box utility, wired the reference's way"""
+    n = d["n_tokens"]
+    A = []
+    for l in d["local_indices"]:
+        A_i = np.zeros((n, len(l)))
+        for i, idx in enumerate(l):
+            A_i[idx, i] = 1
+        A.append(A_i)
+    deltas = [cp.Variable(len(l), nonneg=True) for l in d["local_indices"]]
+    lambdas = [cp.Variable(len(l), nonneg=True) for l in d["local_indices"]]
+    psi = cp.sum([A_i @ (L - D) for A_i, D, L in zip(A, deltas, lambdas)])
+    cons = []
+    for R, g, D, L, kind, w in zip(d["reserves"], d["fees"], deltas, lambdas, d["kinds"], d["weights"]):
+        x = np.array(R) + g * D - L
+        if kind == "sum":
+            cons += [cp.sum(x) >= cp.sum(np.array(R)), x >= 0]
+        else:
+            p = None if kind == "product" else np.array(w)
+            cons.append(cp.geo_mean(x, p=p) >= cp.geo_mean(np.array(R), p=p))
+    for j in range(n):
+        if not util.pinned[j]:
+            cons.append(psi[j] + util.a[j] == 0 if util.eq[j] else psi[j] + util.a[j] >= 0)
+    return cp.Problem(cp.Maximize(util.c @ psi), cons), psi, deltas, lambdas
+
+
+def test_random_models_round_trip(with_oracle_backend):
+    """random problems of the reference's scale, every pool kind and utility: the recogniser returns the literals the model
+    was wired from, and prob.solve() leaves the oracle's optimum in the script-side expressions"""
+    rng = np.random.default_rng(11)
+    done = 0
+    for _ in range(12):
+        hp, d, prices = H.random_small_problem(rng, all_kinds=False)
+        for util in H.random_utilities(rng, d["n_tokens"], prices):
+            prob, psi, deltas, lambdas = wire_general(d, util)
+            m = cp.recognise(prob.objective, prob.constraints)
+            assert m.local_indices == d["local_indices"] and m.kinds == d["kinds"] and m.fees == d["fees"]
+            assert [list(r) for r in m.reserves] == d["reserves"]
+            for w, w0 in zip(m.weights, d["weights"]):
+                assert (w is None) == (w0 is None) and (w is None or np.allclose(w, np.asarray(w0) / np.sum(w0), rtol=1e-15))
+            assert np.array_equal(m.c, util.c) and np.array_equal(m.eq, util.eq) and np.array_equal(m.pinned, util.pinned)
+            assert np.array_equal(m.a, np.where(util.pinned, 0.0, util.a))
+            ro = O.solve(H.oracle_pools(hp), util, tol=1e-9)
+            if ro.status != "optimal":
+                continue
+            prob.solve()
+            assert prob.status == "optimal" and abs(prob.value - ro.value) <= 1e-8 * max(abs(ro.value), 1.0)
+            np.testing.assert_allclose(psi.value, ro.psi, atol=1e-7 * max(np.abs(ro.psi).max(), 1.0))
+            done += 1
+    assert done >= 30
+
+
 @pytest.mark.skipif(not os.path.exists(os.path.join(REF, "arbitrage.py")), reason="the reference tree only exists in the build container")
 def test_reference_scripts_run_unmodified_through_the_compat_module(with_oracle_backend, ref_run, capsys):
     g = run_script.run(os.path.join(REF, "arbitrage.py"))
