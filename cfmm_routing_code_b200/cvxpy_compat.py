@@ -14,7 +14,8 @@ subset those scripts touch, so that changing their ``import cvxpy as cp`` line i
 It is NOT a general convex modelling layer.  ``Problem.solve()`` *recognises* the optimal-routing program
 
     maximise  c' psi + const                     psi = sum_i A_i (Lambda_i - Delta_i)
-    s.t.      phi_i(R_i + gamma_i Delta_i - Lambda_i) >= phi_i(R_i)      (geo_mean / 2-token product / sum with x >= 0)
+    s.t.      phi_i(R_i + gamma_i Delta_i - Lambda_i) >= phi_i(R_i)      (geo_mean / 2-token product / sum with x >= 0 /
+                                                                         product on virtual reserves with real x >= 0)
               psi_j + a_j >= 0  |  psi_j + a_j == 0  |  psi_j free       (token by token)
               Delta_i, Lambda_i >= 0
 
@@ -317,7 +318,7 @@ class RoutingModel:
 _RTOL = 1e-9
 
 
-def _reserves_after_trade(x: Expression):
+def _reserves_after_trade(x: Expression, allow_zero: bool = False):
     """x == R + gamma * Delta - Lambda  (arbitrage.py:60) -> (Delta, Lambda, R, gamma), else None"""
     if x.scalar or len(x.coef) != 2:
         return None
@@ -333,7 +334,7 @@ def _reserves_after_trade(x: Expression):
     if set(found) != {"lam", "del"}:
         return None
     gamma = found["del"][1]
-    if not (0.0 < gamma <= 1.0) or np.any(x.const <= 0):
+    if not (0.0 < gamma <= 1.0) or np.any(x.const < 0) or (not allow_zero and np.any(x.const == 0)):
         return None
     return found["del"][0], found["lam"][0], x.const.copy(), gamma
 
@@ -386,7 +387,13 @@ def recognise(objective: Maximize, constraints) -> RoutingModel:
         nr = _reserves_after_trade(con.expr) if con.op == ">=" else None
         if nr is not None and (id(nr[1]), id(nr[0])) in pools:
             nr = None                                # psi + a >= 0 of a one-pool problem: the known pool's net flow, not reserves
-        if nr is not None:                           # new_reserves >= 0   (arbitrage.py:74)
+        real = _reserves_after_trade(con.expr, allow_zero=True) if con.op == ">=" else None
+        p = pools.get((id(real[0]), id(real[1]))) if real is not None else None
+        if p is not None and p["kind"] == "product" and p["gamma"] == real[3] and np.all(real[2] <= p["R"]) and np.any(real[2] < p["R"]):
+            # geo_mean(R + o + gamma D - L) >= geo_mean(R + o) together with R + gamma D - L >= 0: a constant product on
+            # VIRTUAL reserves whose real reserves stay non-negative (one tick range of a concentrated-liquidity pool)
+            p["kind"], p["w"], p["R"], p["nonneg"] = "bounded_product", p["R"] - real[2], real[2], True
+        elif nr is not None:                         # new_reserves >= 0   (arbitrage.py:74)
             pool_of(pos, *nr)["nonneg"] = True
         elif con.op == ">=" and con.expr.scalar and _looks_like_sum_level(con.expr):
             sum_levels.append(con.expr)

@@ -248,6 +248,8 @@ def wire_general(d, util):
         x = np.array(R) + g * D - L
         if kind == "sum":
             cons += [cp.sum(x) >= cp.sum(np.array(R)), x >= 0]
+        elif kind == "bounded_product":              # product on virtual reserves R + o, real reserves >= 0
+            cons += [cp.geo_mean(x + np.array(w)) >= cp.geo_mean(np.array(R) + np.array(w)), x >= 0]
         else:
             p = None if kind == "product" else np.array(w)
             cons.append(cp.geo_mean(x, p=p) >= cp.geo_mean(np.array(R), p=p))
@@ -263,14 +265,18 @@ def test_random_models_round_trip(with_oracle_backend):
     rng = np.random.default_rng(11)
     done = 0
     for _ in range(12):
-        hp, d, prices = H.random_small_problem(rng, all_kinds=False)
+        hp, d, prices = H.random_small_problem(rng, all_kinds=True)
         for util in H.random_utilities(rng, d["n_tokens"], prices):
             prob, psi, deltas, lambdas = wire_general(d, util)
             m = cp.recognise(prob.objective, prob.constraints)
             assert m.local_indices == d["local_indices"] and m.kinds == d["kinds"] and m.fees == d["fees"]
-            assert [list(r) for r in m.reserves] == d["reserves"]
-            for w, w0 in zip(m.weights, d["weights"]):
-                assert (w is None) == (w0 is None) and (w is None or np.allclose(w, np.asarray(w0) / np.sum(w0), rtol=1e-15))
+            assert all(np.allclose(r, r0, rtol=1e-15, atol=0) for r, r0 in zip(m.reserves, d["reserves"]))
+            for w, w0, kind in zip(m.weights, d["weights"], d["kinds"]):
+                assert (w is None) == (w0 is None)
+                if kind == "bounded_product":        # offsets come back as (R + o) - R
+                    assert np.allclose(w, w0, rtol=1e-12)
+                elif w is not None:
+                    assert np.allclose(w, np.asarray(w0) / np.sum(w0), rtol=1e-15)
             assert np.array_equal(m.c, util.c) and np.array_equal(m.eq, util.eq) and np.array_equal(m.pinned, util.pinned)
             assert np.array_equal(m.a, np.where(util.pinned, 0.0, util.a))
             ro = O.solve(H.oracle_pools(hp), util, tol=1e-9)
