@@ -163,9 +163,9 @@ class Expression:
     def value(self):
         out = self.const.copy()
         for v, C in self.coef.items():
-            if v.value is None:
+            if v._value is None:
                 return None
-            out = out + C @ np.asarray(v.value, float)
+            out = out + C @ v._value
         return float(out[0]) if self.scalar else out
 
 

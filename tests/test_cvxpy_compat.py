@@ -155,6 +155,9 @@ def test_expression_algebra_matches_numpy():
     assert c.op == ">=" and abs(c.expr.value - (1.0 - e.value[0])) <= 1e-12
     assert (e[0] == 2.0).op == "=="
     assert len(cp.Problem(cp.Maximize(e[0]), [e >= 0, y >= 1]).variables()) == 2
+    z = cp.Variable()                                   # scalar variable
+    z.value = 3.0
+    assert z.shape == () and z.value == 3.0 and (2 * z + 1).value == 7.0 and np.allclose((x + z).value, x.value + 3.0)
 
 
 def test_models_outside_the_routing_family_are_refused_by_name():
