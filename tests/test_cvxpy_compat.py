@@ -41,44 +41,47 @@ def with_oracle_backend(monkeypatch):
     monkeypatch.setattr(cp, "_backend", oracle_backend)
 
 
-def wire(d, weights0, objective, token_constraints):
-    """the model of the reference scripts (arbitrage.py:38-78), built from instance literals"""
-    n, local_indices = d["n_tokens"], d["local_indices"]
-    reserves = list(map(np.array, d["reserves"]))
-    A = []
-    for l in local_indices:
-        A_i = np.zeros((n, len(l)))
-        for i, idx in enumerate(l):
-            A_i[idx, i] = 1
-        A.append(A_i)
-    deltas = [cp.Variable(len(l), nonneg=True) for l in local_indices]
-    lambdas = [cp.Variable(len(l), nonneg=True) for l in local_indices]
-    psi = cp.sum([A_i @ (L - D) for A_i, D, L in zip(A, deltas, lambdas)])
-    new_reserves = [R + gamma_i * D - L for R, gamma_i, D, L in zip(reserves, d["fees"], deltas, lambdas)]
-    cons = [cp.geo_mean(new_reserves[0], p=np.array(weights0)) >= cp.geo_mean(reserves[0], p=np.array(weights0)),
-            cp.geo_mean(new_reserves[1]) >= cp.geo_mean(reserves[1]),
-            cp.geo_mean(new_reserves[2]) >= cp.geo_mean(reserves[2]),
-            cp.geo_mean(new_reserves[3]) >= cp.geo_mean(reserves[3]),
-            cp.sum(new_reserves[4]) >= cp.sum(reserves[4]),
-            new_reserves[4] >= 0] + token_constraints(psi)
-    return cp.Problem(cp.Maximize(objective(psi)), cons), psi, deltas, lambdas
+def pools_model(d):
+    """trade variables, net flow psi and the trading-function constraints of a list-form problem, in cvxpy terms
+    (what arbitrage.py:42-74 states for its five pools)"""
+    n = d["n_tokens"]
+    deltas = [cp.Variable(len(l), nonneg=True) for l in d["local_indices"]]
+    lambdas = [cp.Variable(len(l), nonneg=True) for l in d["local_indices"]]
+    psi = cp.sum([np.eye(n)[:, l] @ (L - D) for l, D, L in zip(d["local_indices"], deltas, lambdas)])
+    cons = []
+    for R, g, D, L, kind, w in zip(d["reserves"], d["fees"], deltas, lambdas, d["kinds"], d["weights"]):
+        R = np.array(R, float)
+        x = R + g * D - L
+        if kind == "sum":
+            cons += [cp.sum(x) >= cp.sum(R), x >= 0]
+        elif kind == "bounded_product":              # INTEGRATION.md: product on virtual reserves R + o, real reserves >= 0
+            cons += [cp.geo_mean(x + np.array(w)) >= cp.geo_mean(R + np.array(w)), x >= 0]
+        else:
+            p = None if kind == "product" else np.array(w)
+            cons.append(cp.geo_mean(x, p=p) >= cp.geo_mean(R, p=p))
+    return psi, deltas, lambdas, cons
+
+
+def wire(d, objective, token_constraints):
+    psi, deltas, lambdas, cons = pools_model(d)
+    return cp.Problem(cp.Maximize(objective(psi)), cons + token_constraints(psi)), psi, deltas, lambdas
 
 
 def arbitrage_model():
     d = I.arbitrage_instance()
-    return d, wire(d, d["weights"][0], lambda psi: np.array(d["market_value"]) @ psi, lambda psi: [psi >= 0])
+    return d, wire(d, lambda psi: np.array(d["market_value"]) @ psi, lambda psi: [psi >= 0])
 
 
 def liquidation_model():
     d = I.liquidation_instance()
     ca = d["current_assets"]
-    return d, wire(d, d["weights"][0], lambda psi: psi[4], lambda psi: [psi[j] + ca[j] == 0 for j in range(4)])
+    return d, wire(d, lambda psi: psi[4], lambda psi: [psi[j] + ca[j] == 0 for j in range(4)])
 
 
 def swap_model(t):
     d = I.two_asset_instance()
     assets = np.array([t, 0, 0])
-    return d, wire(d, d["weights"][0], lambda psi: psi[2], lambda psi: [psi + assets >= 0])
+    return d, wire(d, lambda psi: psi[2], lambda psi: [psi + assets >= 0])
 
 
 def check_literals(m, d):
@@ -235,28 +238,9 @@ def test_minimize_and_equal_weight_geomean_and_infeasible(with_oracle_backend):
 
 
 def wire_general(d, util):
-    """any list-form problem (geomean / product / sum pools) and any linear + box utility, wired the reference's way"""
-    n = d["n_tokens"]
-    A = []
-    for l in d["local_indices"]:
-        A_i = np.zeros((n, len(l)))
-        for i, idx in enumerate(l):
-            A_i[idx, i] = 1
-        A.append(A_i)
-    deltas = [cp.Variable(len(l), nonneg=True) for l in d["local_indices"]]
-    lambdas = [cp.Variable(len(l), nonneg=True) for l in d["local_indices"]]
-    psi = cp.sum([A_i @ (L - D) for A_i, D, L in zip(A, deltas, lambdas)])
-    cons = []
-    for R, g, D, L, kind, w in zip(d["reserves"], d["fees"], deltas, lambdas, d["kinds"], d["weights"]):
-        x = np.array(R) + g * D - L
-        if kind == "sum":
-            cons += [cp.sum(x) >= cp.sum(np.array(R)), x >= 0]
-        elif kind == "bounded_product":              # INTEGRATION.md: product on virtual reserves R + o, real reserves >= 0
-            cons += [cp.geo_mean(x + np.array(w)) >= cp.geo_mean(np.array(R) + np.array(w)), x >= 0]
-        else:
-            p = None if kind == "product" else np.array(w)
-            cons.append(cp.geo_mean(x, p=p) >= cp.geo_mean(np.array(R), p=p))
-    for j in range(n):
+    """any list-form problem and any linear + box utility"""
+    psi, deltas, lambdas, cons = pools_model(d)
+    for j in range(d["n_tokens"]):
         if not util.pinned[j]:
             cons.append(psi[j] + util.a[j] == 0 if util.eq[j] else psi[j] + util.a[j] >= 0)
     return cp.Problem(cp.Maximize(util.c @ psi), cons), psi, deltas, lambdas
