@@ -548,6 +548,11 @@ class Problem:
 
     def solve(self, tol: float = 1e-9, verbose: bool = False, **kw):
         """arbitrage.py:82.  Recognise the routing program, solve it on the GPU, write the trades back."""
+        for ignored in ("solver", "warm_start", "ignore_dpp", "gp", "qcp", "requires_grad", "enforce_dpp"):
+            kw.pop(ignored, None)        # cvxpy arguments that select or tune ITS back ends: meaningless here
+        for alias in ("max_iters", "max_iter"):
+            if alias in kw:
+                kw["max_iter"] = int(kw.pop(alias))
         m = self.model = recognise(self.objective, self.constraints)
         from .api import LinearUtility, solve as gpu_solve           # torch + the CUDA library load here, not at import
         util = LinearUtility(m.c, m.a, m.eq, m.pinned)
